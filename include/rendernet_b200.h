@@ -1,0 +1,119 @@
+/* rendernet_b200.h -- C ABI of librendernet_b200.so: the B200 (sm_100a) kernels behind RenderNet's
+ * forward-rendering hot path.
+ *
+ * The reference (thunguyenphuoc/RenderNet) is pure Python over TensorFlow-1 and has NO FFI of its own;
+ * its boundary is the set of graph-building Python functions cited per entry point below (file:line into
+ * the reference tree).  A maintainer would bind these with ctypes.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless stated otherwise; the caller owns every buffer (the
+ *     library never allocates device memory).  `stream` is a cudaStream_t passed as void*; calls are
+ *     asynchronous and stream-ordered; no global mutable state besides cached function attributes.
+ *   - Tensors are channel-last and dense: 2-D [B,H,W,C], 3-D [B,H,W,D,C] (D innermost spatial axis),
+ *     exactly the reference's layouts (tools/layer_util.py:228,147).
+ *   - "16-bit" tensors are IEEE fp16 (fmt=0) or bfloat16 (fmt=1); accumulation is always fp32.
+ *   - Return value: 0 = ok; <0 = invalid argument (see source for the code); >0 = CUDA / driver error.
+ */
+#ifndef RENDERNET_B200_H_
+#define RENDERNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RN_ACT_NONE 0
+#define RN_ACT_PRELU 1   /* max(0,x) + alpha[c]*min(0,x)    tools/layer_util.py:27-45 */
+#define RN_ACT_SIGMOID 2 /* tf.nn.sigmoid                   RenderNet_Shader.py:127,130 */
+
+int rn_version(void);
+const char* rn_error_string(int code);
+
+/* ---- resampler ----------------------------------------------------------------------------------
+ * Replaces tf_resampling + tf_interpolate + tf_voxel_meshgrid (tools/resampling_voxel_grid.py:381-614)
+ * fused with tf_transform_voxel_to_match_image (tools/model_util.py:41-49).
+ *   vox   [B,size,size,size,C] fp32        minv [B,3,4] fp32 = inverse(T'.S.R.T)[:, :3, :] (:579-602)
+ *   out   [B,new,new,new,C] fp32
+ * transform=0: out[b,i,j,k,c] = sample(minv . (k,j,i,1))           (tf_resampling output)
+ * transform=1: out[b,p,q,r,c] = sample(minv . (r,new-1-p,q,1))     (+ axis transform, the network input)
+ * Corner clamp / weight rule of :410-485: points with any source coordinate outside [0,size-1) give 0. */
+int rn_resample_f32(const float* vox, const float* minv, float* out, int B, int C, int size, int new_size,
+                    int transform, void* stream);
+
+/* ---- weight packing -------------------------------------------------------------------------------
+ * TF filter (fp32) -> [n_sel][cout_pad][Cin] 16-bit, K-major rows for the tensor-core kernel.
+ *   transposed=0: w is [ntaps_total][Cin][Cout]   (tf.nn.conv2d / conv3d filters, layer_util.py:162,243)
+ *   transposed=1: w is [ntaps_total][Cout][Cin]   (tf.nn.conv2d_transpose filters, layer_util.py:201)
+ * tap_sel (HOST pointer, n_sel ints) selects/reorders source taps; rows co >= Cout are zero. */
+int rn_pack_conv_weights(const float* w, void* packed, int ntaps_total, int Cin, int Cout, int cout_pad,
+                         int transposed, const int* tap_sel, int n_sel, int fmt, void* stream);
+/* fp32 -> 16-bit cast with zero padding of the tail: dst[0..n_pad) */
+int rn_cast_f32_to_16(const float* src, void* dst, long long n, long long n_pad, int fmt, void* stream);
+int rn_cast_16_to_f32(const void* src, float* dst, long long n, int fmt, void* stream);
+
+/* ---- tensor-core implicit-GEMM convolution (tcgen05 + TMA) ----------------------------------------
+ * out[b,y,x,z,n] = act( bias[n] + sum_t sum_ci  x[b, y+dy_t, x+dx_t, z+dz_t, ci] * w_packed[t][n][ci] ) + residual
+ * with zero outside the input (TF SAME padding is expressed through the tap offsets).
+ * The output element offset is o_base + b*o_b + y*o_y + x*o_x + z*o_z + n, which lets one call write a
+ * strided sub-lattice (the 4 phases of a stride-2 transposed convolution). */
+typedef struct rn_conv_desc {
+  int ndim;                 /* 2 or 3 spatial dims */
+  int B, H, W, D;           /* extents (D ignored for ndim == 2) */
+  int Cin;                  /* multiple of 16 */
+  int Cout;                 /* real output channels */
+  int cout_pad;             /* rows of w_packed / entries of bias, alpha; multiple of 16 */
+  int ntaps;                /* <= 28 */
+  const int8_t* taps;       /* HOST pointer: ntaps x (dx, dy, dz) */
+  const void* x;            /* 16-bit [B,H,W,(D),Cin] */
+  const void* w_packed;     /* 16-bit [ntaps][cout_pad][Cin] */
+  const float* bias;        /* fp32 [cout_pad] */
+  const float* alpha;       /* fp32 [cout_pad] or NULL */
+  int act;                  /* RN_ACT_* */
+  const void* residual;     /* NULL, or same indexing as the output */
+  int residual_is_f32;
+  void* out16;              /* 16-bit output or NULL */
+  float* out32;             /* fp32 output or NULL */
+  long long o_base, o_b, o_y, o_x, o_z;
+  int fmt;                  /* 0 fp16, 1 bf16 */
+  int force_bn, force_kps, max_ctas; /* 0 = auto (tuning / tests) */
+} rn_conv_desc;
+int rn_conv_igemm(const rn_conv_desc* d, void* stream);
+
+/* Reference-shaped wrappers over rn_conv_igemm (stride 1, TF SAME), 16-bit in/out:
+ * slim.conv2d / layer_util.conv2d (layer_util.py:147, RenderNet_Shader.py:83,87,98,102),
+ * layer_util.conv3d (:228), projection_unit's 1x1 conv (:8-22). */
+int rn_conv2d_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
+                   const void* residual, int residual_is_f32, void* out16, float* out32, int B, int H, int W,
+                   int Cin, int Cout, int cout_pad, int kh, int kw, int fmt, void* stream);
+int rn_conv3d_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
+                   const void* residual, int residual_is_f32, void* out16, float* out32, int B, int H, int W,
+                   int D, int Cin, int Cout, int cout_pad, int k, int fmt, void* stream);
+/* slim.conv2d_transpose / layer_util.conv2d_transpose (layer_util.py:186; RenderNet_Shader.py:106-129),
+ * SAME, out = in*stride.  w_packed holds the stride^2 phase filters back to back, as produced by
+ * rn_pack_conv2d_transpose_weights: [phase = ay*s+ax][taps_of_phase][cout_pad][Cin]. */
+int rn_pack_conv2d_transpose_weights(const float* w, void* packed, int kh, int kw, int Cin, int Cout,
+                                     int cout_pad, int stride, int fmt, void* stream);
+int rn_conv2d_transpose_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
+                             void* out16, float* out32, int B, int H, int W, int Cin, int Cout, int cout_pad,
+                             int kh, int kw, int stride, int fmt, void* stream);
+
+/* ---- thin 3-D convolutions on CUDA cores (too few channels for the tensor pipe) ---------------------
+ * tf.nn.conv3d SAME + bias + PReLU (layer_util.py:228-265, RenderNet_Shader.py:36-43): e_conv1 (Cin=1,
+ * 5^3, stride 2) and e_conv2 (Cin=8, 3^3, stride (1,1,2)).  x fp32 or 16-bit, w fp32 TF layout
+ * [k,k,k,Cin,Cout], out 16-bit [B,H/sy,W/sx,D/sz,Cout]. */
+int rn_conv3d_direct(const void* x, int x_is_f32, const float* w, const float* bias, const float* alpha,
+                     void* out16, int B, int H, int W, int D, int Cin, int Cout, int k, int sy, int sx, int sz,
+                     int fmt, void* stream);
+
+/* ---- Phong composite (tools/Phong_shading.py:138-228, RenderNet_demo.py:54-58) -----------------------
+ * img [B,H,W,3] fp32 normal map in [0,1]; light_dir [B,3]; light_col [B,3]; out_f32 [B,H,W,3] and/or
+ * out_u8 = clip(255*out,0,255) as uint8.  background: 0 = "Black" (threshold 150), 1 = white (80). */
+int rn_phong_composite(const float* img, const float* light_dir, const float* light_col, float ambient,
+                       float k_diffuse, int background_white, int with_mask, float* out_f32, uint8_t* out_u8,
+                       int B, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RENDERNET_B200_H_ */

@@ -1,0 +1,72 @@
+"""ctypes binding of librendernet_b200.so (C ABI declared in include/rendernet_b200.h).
+
+The library is built in-tree by ``rendernet_b200/csrc/Makefile`` (``__graft_entry__.build()``).
+There is NO fallback: if the shared object is missing the import fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librendernet_b200.so")
+
+
+class rn_conv_desc(C.Structure):
+    _fields_ = [
+        ("ndim", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("D", C.c_int),
+        ("Cin", C.c_int), ("Cout", C.c_int), ("cout_pad", C.c_int), ("ntaps", C.c_int),
+        ("taps", C.c_void_p), ("x", C.c_void_p), ("w_packed", C.c_void_p), ("bias", C.c_void_p),
+        ("alpha", C.c_void_p), ("act", C.c_int), ("residual", C.c_void_p), ("residual_is_f32", C.c_int),
+        ("out16", C.c_void_p), ("out32", C.c_void_p),
+        ("o_base", C.c_longlong), ("o_b", C.c_longlong), ("o_y", C.c_longlong), ("o_x", C.c_longlong),
+        ("o_z", C.c_longlong), ("fmt", C.c_int), ("force_bn", C.c_int), ("force_kps", C.c_int),
+        ("max_ctas", C.c_int),
+    ]
+
+
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> (restype, argtypes); mirrors include/rendernet_b200.h one to one
+SIGNATURES = {
+    "rn_version": (_i, []),
+    "rn_error_string": (C.c_char_p, [_i]),
+    "rn_resample_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rn_pack_conv_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "rn_cast_f32_to_16": (_i, [_vp, _vp, _ll, _ll, _i, _vp]),
+    "rn_cast_16_to_f32": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "rn_conv_igemm": (_i, [C.POINTER(rn_conv_desc), _vp]),
+    "rn_conv2d_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rn_conv3d_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rn_pack_conv2d_transpose_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rn_conv2d_transpose_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rn_conv3d_direct": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rn_phong_composite": (_i, [_vp, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"rendernet_b200: CUDA extension not built ({LIB_PATH} missing). "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C rendernet_b200/csrc`. "
+            "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class RenderNetCudaError(RuntimeError):
+    pass
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib.rn_error_string(code).decode()
+        raise RenderNetCudaError(f"{what}: rc={code} ({msg})")

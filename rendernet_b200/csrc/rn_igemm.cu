@@ -1,0 +1,452 @@
+// rn_igemm.cu -- implicit-GEMM convolution on 5th-gen tensor cores (tcgen05) for sm_100a.
+//
+// One kernel serves every dense contraction of the RenderNet forward path (reference call sites:
+// tools/layer_util.py:21 projection 1x1, :101-104 3x3 res blocks, :253 conv3d, :212 conv2d_transpose;
+// RenderNet_Shader.py:83-129): M = output pixels/voxels, N = Cout, K = taps x Cin.
+//
+//   * A (activations, channel-last fp16/bf16) is never im2col'ed in memory: for filter tap (dx,dy,dz) the
+//     128-row A tile is ONE tiled-TMA box {KB channels, BD, BW, BH} fetched at a shifted coordinate; TMA's
+//     out-of-bounds zero fill implements TF "SAME" padding (asymmetric pads are just different offsets).
+//   * B (weights) is pre-packed [tap][Cout][Cin] so a {KB, BN} box is a K-major operand tile.
+//   * Both land in shared memory in the 32/64/128-byte swizzled K-major layout that tcgen05.mma reads
+//     through shared-memory descriptors; accumulators live in TMEM (2 x BN fp32 columns, double-buffered
+//     so the epilogue of tile i overlaps the MMAs of tile i+1).
+//   * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+//     warps 2..5 = epilogue (tcgen05.ld -> bias/PReLU/residual/sigmoid -> 16B global stores).
+//   * Persistent: grid = #SMs, static round-robin tile schedule with N fastest so concurrently running
+//     CTAs share the same activation rows in L2.
+#include <cstdio>
+#include <cstring>
+#include <cuda_bf16.h>
+
+#include "rn_igemm.cuh"
+#include "rn_ptx.cuh"
+
+namespace rn {
+
+constexpr int kNumThreads = 192;
+
+struct TileCoord {
+  int b, x0, y0, z0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile, int BN) {
+  TileCoord t;
+  const int n_tile = tile % p.n_tiles;
+  int m_tile = tile / p.n_tiles;
+  const int per_img = p.tiles_x * p.tiles_y * p.tiles_z;
+  t.b = m_tile / per_img;
+  m_tile -= t.b * per_img;
+  const int tz = m_tile % p.tiles_z;
+  m_tile /= p.tiles_z;
+  const int tx = m_tile % p.tiles_x;
+  const int ty = m_tile / p.tiles_x;
+  t.x0 = tx * p.BW;
+  t.y0 = ty * p.BH;
+  t.z0 = tz * p.BD;
+  t.n0 = n_tile * BN;
+  return t;
+}
+
+template <int CW>
+__device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint32_t (&r)[32], int n0, long long off,
+                                               bool row_valid) {
+  if (!row_valid) return;
+  float v[CW];
+#pragma unroll
+  for (int i = 0; i < CW; i += 4) {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+    v[i + 0] = __uint_as_float(r[i + 0]) + b4.x;
+    v[i + 1] = __uint_as_float(r[i + 1]) + b4.y;
+    v[i + 2] = __uint_as_float(r[i + 2]) + b4.z;
+    v[i + 3] = __uint_as_float(r[i + 3]) + b4.w;
+  }
+  if (p.act == ACT_PRELU) {
+#pragma unroll
+    for (int i = 0; i < CW; i += 4) {
+      const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.alpha + n0 + i));
+      v[i + 0] = fmaxf(v[i + 0], 0.f) + a4.x * fminf(v[i + 0], 0.f);
+      v[i + 1] = fmaxf(v[i + 1], 0.f) + a4.y * fminf(v[i + 1], 0.f);
+      v[i + 2] = fmaxf(v[i + 2], 0.f) + a4.z * fminf(v[i + 2], 0.f);
+      v[i + 3] = fmaxf(v[i + 3], 0.f) + a4.w * fminf(v[i + 3], 0.f);
+    }
+  } else if (p.act == ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = 1.f / (1.f + __expf(-v[i]));
+  }
+  const bool full = p.vec_ok && (n0 + CW <= p.n_valid);
+  if (full) {
+    if (p.res != nullptr) {
+      if (p.res_is_f32) {
+        const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + off + n0);
+#pragma unroll
+        for (int i = 0; i < CW / 4; ++i) {
+          const float4 q = __ldg(rp + i);
+          v[4 * i + 0] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+        }
+      } else {
+        const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res) + off + n0);
+#pragma unroll
+        for (int i = 0; i < CW / 8; ++i) {
+          const uint4 q = __ldg(rp + i);
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f;
+            if (p.ab_fmt == 0) f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+            else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+            v[8 * i + 2 * j] += f.x;
+            v[8 * i + 2 * j + 1] += f.y;
+          }
+        }
+      }
+    }
+    if (p.out16 != nullptr) {
+      uint4* op = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out16) + off + n0);
+#pragma unroll
+      for (int i = 0; i < CW / 8; ++i) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (p.ab_fmt == 0) {
+            __half2 h = __floats2half2_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&h);
+          } else {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+        }
+        op[i] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    if (p.out32 != nullptr) {
+      float4* op = reinterpret_cast<float4*>(p.out32 + off + n0);
+#pragma unroll
+      for (int i = 0; i < CW / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+  } else {
+    // ragged / unaligned columns (e.g. the 3-channel image head): scalar path
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      const int n = n0 + i;
+      if (n < p.n_valid) {
+        float x = v[i];
+        if (p.res != nullptr) {
+          if (p.res_is_f32) x += static_cast<const float*>(p.res)[off + n];
+          else if (p.ab_fmt == 0) x += __half2float(static_cast<const __half*>(p.res)[off + n]);
+          else x += __bfloat162float(static_cast<const __nv_bfloat16*>(p.res)[off + n]);
+        }
+        if (p.out16 != nullptr) {
+          if (p.ab_fmt == 0) static_cast<__half*>(p.out16)[off + n] = __float2half_rn(x);
+          else static_cast<__nv_bfloat16*>(p.out16)[off + n] = __float2bfloat16_rn(x);
+        }
+        if (p.out32 != nullptr) p.out32[off + n] = x;
+      }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  constexpr int CW = (BN >= 32) ? 32 : 16;                     // epilogue column chunk
+  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // double-buffered accumulator
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sub_bytes = p.a_sub_bytes + p.b_sub_bytes;
+  const int stage_bytes = p.kps * sub_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tfull_bar = empty_bar + p.stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_k = p.ntaps * p.kblocks;
+  const int kb_elems = p.row_bytes >> 1;
+  const uint32_t a_tx = kTileM * p.row_bytes;
+  const uint32_t b_tx = BN * p.row_bytes;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BN);
+        for (int it = 0; it < total_k;) {
+          const int n_here = min(p.kps, total_k - it);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], n_here * (a_tx + b_tx));
+          uint8_t* sbase = smem + static_cast<size_t>(stage) * stage_bytes;
+          for (int j = 0; j < n_here; ++j) {
+            const int kit = it + j;
+            const int tap = kit / p.kblocks;
+            const int kb = kit - tap * p.kblocks;
+            uint8_t* a_dst = sbase + j * sub_bytes;
+            uint8_t* b_dst = a_dst + p.a_sub_bytes;
+            const int cx = t.x0 + p.tap[tap][0], cy = t.y0 + p.tap[tap][1], cz = t.z0 + p.tap[tap][2];
+            if (p.rank == 4) tma_load_4d(a_dst, &p.tmA, &full_bar[stage], kb * kb_elems, cx, cy, t.b);
+            else tma_load_5d(a_dst, &p.tmA, &full_bar[stage], kb * kb_elems, cz, cx, cy, t.b);
+            tma_load_3d(b_dst, &p.tmB, &full_bar[stage], kb * kb_elems, t.n0, tap);
+          }
+          it += n_here;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(kTileM, BN, p.ab_fmt);
+      const int mma_per_kit = p.row_bytes >> 5;  // 32 B (= 16 elements, UMMA_K) per instruction
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int it = 0; it < total_k;) {
+          const int n_here = min(p.kps, total_k - it);
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          for (int j = 0; j < n_here; ++j) {
+            const uint64_t da = make_smem_desc(sbase + j * sub_bytes, p.row_bytes);
+            const uint64_t db = make_smem_desc(sbase + j * sub_bytes + p.a_sub_bytes, p.row_bytes);
+            for (int k = 0; k < mma_per_kit; ++k)
+              umma_f16<1>(d_tmem, da + 2 * k, db + 2 * k, idesc, (it + j > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit<1>(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          it += n_here;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit<1>(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int zl = m % p.BD;
+    const int xl = (m / p.BD) % p.BW;
+    const int yl = m / (p.BD * p.BW);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile, BN);
+      const int x = t.x0 + xl, y = t.y0 + yl, z = t.z0 + zl;
+      const bool row_valid = (x < p.W) && (y < p.H) && (z < p.D);
+      const long long off = p.o_base + t.b * p.o_b + y * p.o_y + x * p.o_x + z * p.o_z;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += CW) {
+        uint32_t r[32];
+        if constexpr (CW == 32) tmem_ld_32x32b_x32(taddr + c, r);
+        else tmem_ld_32x32b_x16(taddr + c, r);
+        tmem_ld_wait();
+        if (c + CW >= BN) {  // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        epilogue_chunk<CW>(p, r, t.n0 + c, off, row_valid);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_of(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+template <int BN>
+static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  igemm_kernel<BN><<<grid, kNumThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace rn
+
+#include "../../include/rendernet_b200.h"
+
+extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
+  using namespace rn;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (d == nullptr || d->x == nullptr || d->w_packed == nullptr || d->bias == nullptr) return -1;
+  if (d->ndim != 2 && d->ndim != 3) return -2;
+  if (d->ntaps < 1 || d->ntaps > kMaxTaps) return -3;
+  if (d->Cin % 16 != 0 || d->cout_pad % 16 != 0 || d->Cout > d->cout_pad || d->Cout < 1) return -4;
+  if (d->act == ACT_PRELU && d->alpha == nullptr) return -5;
+  if (d->out16 == nullptr && d->out32 == nullptr) return -6;
+  const int D = d->ndim == 3 ? d->D : 1;
+  if (d->B < 1 || d->H < 1 || d->W < 1 || D < 1) return -7;
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) return -8;
+
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  // K block: as many input channels as fit one 128/64/32-byte swizzle row
+  p.row_bytes = (d->Cin % 64 == 0) ? 128 : ((d->Cin % 32 == 0) ? 64 : 32);
+  const int KB = p.row_bytes / 2;
+  p.kblocks = d->Cin / KB;
+  p.ntaps = d->ntaps;
+  // N tile
+  int BN = 16;
+  for (int c : {256, 128, 64, 32, 16})
+    if (d->cout_pad % c == 0) { BN = c; break; }
+  if (d->force_bn > 0) {
+    if (d->cout_pad % d->force_bn != 0) return -9;
+    BN = d->force_bn;
+  }
+  p.n_tiles = d->cout_pad / BN;
+  // M tile box: BD x BW x BH == 128, innermost spatial dim first
+  auto pow2_le = [](int v, int cap) { int r = 1; while (r * 2 <= cap && r < v) r *= 2; return r; };
+  int rem = kTileM;
+  p.BD = d->ndim == 3 ? pow2_le(D, rem) : 1;
+  rem /= p.BD;
+  p.BW = pow2_le(d->W, rem);
+  rem /= p.BW;
+  p.BH = rem;
+  p.rank = d->ndim == 3 ? 5 : 4;
+  p.W = d->W; p.H = d->H; p.D = D; p.B = d->B;
+  p.tiles_x = (d->W + p.BW - 1) / p.BW;
+  p.tiles_y = (d->H + p.BH - 1) / p.BH;
+  p.tiles_z = (D + p.BD - 1) / p.BD;
+  p.num_tiles = d->B * p.tiles_x * p.tiles_y * p.tiles_z * p.n_tiles;
+  for (int t = 0; t < d->ntaps; ++t) {
+    p.tap[t][0] = d->taps[3 * t + 0];
+    p.tap[t][1] = d->taps[3 * t + 1];
+    p.tap[t][2] = d->taps[3 * t + 2];
+  }
+  p.ab_fmt = d->fmt;
+  p.a_sub_bytes = kTileM * p.row_bytes;
+  p.b_sub_bytes = ((BN * p.row_bytes + 1023) / 1024) * 1024;
+  const int sub = p.a_sub_bytes + p.b_sub_bytes;
+  const int total_k = p.ntaps * p.kblocks;
+  p.kps = 32768 / sub;
+  if (p.kps < 1) p.kps = 1;
+  if (p.kps > total_k) p.kps = total_k;
+  if (d->force_kps > 0) p.kps = d->force_kps;
+  const int budget = 232448 - 1024 - 256;
+  p.stages = budget / (p.kps * sub);
+  if (p.stages > 12) p.stages = 12;
+  if (p.stages < 2) return -10;
+  const size_t smem = static_cast<size_t>(p.stages) * p.kps * sub + 1024 + 256;
+
+  const CUtensorMapDataType dt = d->fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r;
+  if (p.rank == 4) {
+    const cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    const cuuint64_t strides[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * d->W,
+                                   (cuuint64_t)d->Cin * 2 * d->W * d->H};
+    const cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
+    r = enc(&p.tmA, dt, 4, const_cast<void*>(d->x), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)D, (cuuint64_t)d->W, (cuuint64_t)d->H,
+                                (cuuint64_t)d->B};
+    const cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * D,
+                                   (cuuint64_t)d->Cin * 2 * D * d->W, (cuuint64_t)d->Cin * 2 * D * d->W * d->H};
+    const cuuint32_t box[5] = {(cuuint32_t)KB, (cuuint32_t)p.BD, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
+    r = enc(&p.tmA, dt, 5, const_cast<void*>(d->x), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) return 1000 + static_cast<int>(r);
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->cout_pad, (cuuint64_t)d->ntaps};
+    const cuuint64_t strides[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * d->cout_pad};
+    const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)BN, 1};
+    r = enc(&p.tmB, dt, 3, const_cast<void*>(d->w_packed), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) return 2000 + static_cast<int>(r);
+
+  p.out16 = d->out16; p.out32 = d->out32; p.res = d->residual; p.res_is_f32 = d->residual_is_f32;
+  p.bias = d->bias; p.alpha = d->alpha; p.act = d->act; p.n_valid = d->Cout;
+  p.o_base = d->o_base; p.o_b = d->o_b; p.o_y = d->o_y; p.o_x = d->o_x; p.o_z = d->o_z;
+  const bool strides8 = (d->o_base % 8 == 0) && (d->o_b % 8 == 0) && (d->o_y % 8 == 0) && (d->o_x % 8 == 0) &&
+                        (d->o_z % 8 == 0);
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  p.vec_ok = strides8 && al16(d->out16) && al16(d->out32) && al16(d->residual) ? 1 : 0;
+
+  int grid = num_sms();
+  if (d->max_ctas > 0 && d->max_ctas < grid) grid = d->max_ctas;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  cudaError_t e;
+  switch (BN) {
+    case 256: e = launch_bn<256>(p, grid, smem, stream); break;
+    case 128: e = launch_bn<128>(p, grid, smem, stream); break;
+    case 64: e = launch_bn<64>(p, grid, smem, stream); break;
+    case 32: e = launch_bn<32>(p, grid, smem, stream); break;
+    default: e = launch_bn<16>(p, grid, smem, stream); break;
+  }
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}

@@ -1,0 +1,42 @@
+// rn_igemm.cuh -- parameter block shared by the host launcher and the tcgen05 implicit-GEMM kernel.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+
+namespace rn {
+
+constexpr int kMaxTaps = 28;
+constexpr int kTileM = 128;  // rows (pixels / voxels) per CTA tile == TMEM lanes
+
+enum Act : int { ACT_NONE = 0, ACT_PRELU = 1, ACT_SIGMOID = 2 };
+
+struct alignas(64) IgemmParams {
+  CUtensorMap tmA;  // activations, channel-last: rank 4 {C,W,H,B} or rank 5 {C,D,W,H,B}; box {KB,[BD],BW,BH,1}
+  CUtensorMap tmB;  // weights [tap][CoutPad][Cin]: rank 3 {Cin,CoutPad,taps}; box {KB,BN,1}
+  int rank;
+  int W, H, D, B;                 // extents of the output (== input) pixel space; D = 1 for rank 4
+  int BW, BH, BD;                 // M tile box, BW*BH*BD == 128
+  int tiles_x, tiles_y, tiles_z;  // per image
+  int n_tiles;                    // CoutPad / BN
+  int num_tiles;                  // B*tiles_y*tiles_x*tiles_z*n_tiles
+  int ntaps, kblocks;             // k-iterations = ntaps * kblocks, each KB = row_bytes/2 input channels
+  int row_bytes;                  // 32 / 64 / 128 (== TMA + UMMA swizzle span)
+  int kps;                        // k-iterations per pipeline stage
+  int stages;
+  int a_sub_bytes, b_sub_bytes;   // smem bytes of one k-iteration's A / B sub-buffer (1024-multiples)
+  int ab_fmt;                     // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
+  int8_t tap[kMaxTaps][4];        // (dx, dy, dz, _) input offset of each filter tap
+  // fused epilogue: v = acc + bias; v = act(v); v += residual; store
+  void* out16;                    // 16-bit output or nullptr
+  float* out32;                   // fp32 output or nullptr
+  const void* res;                // residual (same indexing as the output) or nullptr
+  int res_is_f32;
+  const float* bias;              // [CoutPad]
+  const float* alpha;             // [CoutPad] (PReLU) or nullptr
+  int act;
+  int n_valid;                    // real Cout (<= CoutPad); columns beyond are dropped
+  int vec_ok;                     // output/residual rows are 16B aligned -> vector path
+  long long o_base, o_b, o_y, o_x, o_z;  // output element offset = o_base + b*o_b + y*o_y + x*o_x + z*o_z + n
+};
+
+}  // namespace rn

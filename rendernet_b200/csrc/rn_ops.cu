@@ -1,0 +1,498 @@
+// rn_ops.cu -- the non-tensor-core kernels of the RenderNet forward path and the reference-shaped C-ABI
+// wrappers over the implicit-GEMM kernel (rn_igemm.cu).
+//   * fused rotate + trilinear resample + axis transform  (tools/resampling_voxel_grid.py:381-614,
+//     tools/model_util.py:41-49)                                               -> HBM-bound gather
+//   * weight packing / casts
+//   * thin 3-D convolutions e_conv1 / e_conv2 on CUDA cores (RenderNet_Shader.py:36-43)
+//   * Phong composite + uint8 quantisation (tools/Phong_shading.py:138-228, RenderNet_demo.py:54-58)
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/rendernet_b200.h"
+
+namespace rn {
+
+// ------------------------------------------------------------------------------------------ resampler
+// One warp per output row (innermost output axis); each lane owns 4 consecutive points per iteration so
+// C=1 rows are written with one 16-byte store per lane (512 B per warp instruction).
+template <int C>
+__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ vox, const float* __restrict__ minv,
+                                                       float* __restrict__ out, int B, int size, int nsz,
+                                                       int transform) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rows = B * nsz * nsz;
+  if (warp_global >= rows) return;
+  const int b = warp_global / (nsz * nsz);
+  const int o1 = (warp_global / nsz) % nsz;
+  const int o2 = warp_global % nsz;
+  const float* M = minv + b * 12;
+  const float m00 = __ldg(M + 0), m01 = __ldg(M + 1), m02 = __ldg(M + 2), m03 = __ldg(M + 3);
+  const float m10 = __ldg(M + 4), m11 = __ldg(M + 5), m12 = __ldg(M + 6), m13 = __ldg(M + 7);
+  const float m20 = __ldg(M + 8), m21 = __ldg(M + 9), m22 = __ldg(M + 10), m23 = __ldg(M + 11);
+  // grid point (gx, gy, gz) = (k, j, i) (:500-512); with the axis transform N[b,p,q,r] = T[b,q,nsz-1-p,r]
+  const float gy = transform ? static_cast<float>(nsz - 1 - o1) : static_cast<float>(o2);
+  const float gz = transform ? static_cast<float>(o2) : static_cast<float>(o1);
+  const float bx = fmaf(m01, gy, fmaf(m02, gz, m03));
+  const float by = fmaf(m11, gy, fmaf(m12, gz, m13));
+  const float bz = fmaf(m21, gy, fmaf(m22, gz, m23));
+  const float lim = static_cast<float>(size - 1);
+  const float* vb = vox + static_cast<size_t>(b) * size * size * size * C;
+  float* orow = out + static_cast<size_t>(warp_global) * nsz * C;
+
+  for (int r0 = lane * 4; r0 < nsz; r0 += 128) {
+    float res[4][C];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float gx = static_cast<float>(r0 + u);
+      const float x = fmaf(m00, gx, bx), y = fmaf(m10, gx, by), z = fmaf(m20, gx, bz);
+#pragma unroll
+      for (int c = 0; c < C; ++c) res[u][c] = 0.f;
+      // clamp-then-weight rule (:410-485): both clamped corners coincide outside [0,size-1) -> weights cancel
+      if (x >= 0.f && x < lim && y >= 0.f && y < lim && z >= 0.f && z < lim && (r0 + u) < nsz) {
+        const float x0f = floorf(x), y0f = floorf(y), z0f = floorf(z);
+        const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f), z0 = static_cast<int>(z0f);
+        const float x1f = x0f + 1.f, y1f = y0f + 1.f, z1f = z0f + 1.f;
+        const float ax = __fsub_rn(x1f, x), bxw = __fsub_rn(x, x0f);
+        const float ay = __fsub_rn(y1f, y), byw = __fsub_rn(y, y0f);
+        const float az = __fsub_rn(z1f, z), bzw = __fsub_rn(z, z0f);
+        const float wa = __fmul_rn(__fmul_rn(ax, ay), az), wb = __fmul_rn(__fmul_rn(ax, byw), az);
+        const float wc = __fmul_rn(__fmul_rn(bxw, ay), az), wd = __fmul_rn(__fmul_rn(bxw, byw), az);
+        const float we = __fmul_rn(__fmul_rn(ax, ay), bzw), wf = __fmul_rn(__fmul_rn(ax, byw), bzw);
+        const float wg = __fmul_rn(__fmul_rn(bxw, ay), bzw), wh = __fmul_rn(__fmul_rn(bxw, byw), bzw);
+        const size_t i000 = ((static_cast<size_t>(z0) * size + y0) * size + x0) * C;  // flat = z*W*H + y*W + x
+        const size_t sy = static_cast<size_t>(size) * C, sz = static_cast<size_t>(size) * size * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float Ia = __ldg(vb + i000 + c), Ib = __ldg(vb + i000 + sy + c);
+          const float Ic = __ldg(vb + i000 + C + c), Id = __ldg(vb + i000 + sy + C + c);
+          const float Ie = __ldg(vb + i000 + sz + c), If = __ldg(vb + i000 + sz + sy + c);
+          const float Ig = __ldg(vb + i000 + sz + C + c), Ih = __ldg(vb + i000 + sz + sy + C + c);
+          float s = __fmul_rn(wa, Ia);                       // add_n order a..h (:485)
+          s = __fadd_rn(s, __fmul_rn(wb, Ib));
+          s = __fadd_rn(s, __fmul_rn(wc, Ic));
+          s = __fadd_rn(s, __fmul_rn(wd, Id));
+          s = __fadd_rn(s, __fmul_rn(we, Ie));
+          s = __fadd_rn(s, __fmul_rn(wf, If));
+          s = __fadd_rn(s, __fmul_rn(wg, Ig));
+          s = __fadd_rn(s, __fmul_rn(wh, Ih));
+          res[u][c] = s;
+        }
+      }
+    }
+    if constexpr (C == 1) {
+      if (r0 + 3 < nsz) {
+        *reinterpret_cast<float4*>(orow + r0) = make_float4(res[0][0], res[1][0], res[2][0], res[3][0]);
+      } else {
+        for (int u = 0; u < 4 && r0 + u < nsz; ++u) orow[r0 + u] = res[u][0];
+      }
+    } else {
+      for (int u = 0; u < 4 && r0 + u < nsz; ++u) {
+        if constexpr (C == 4) {
+          *reinterpret_cast<float4*>(orow + static_cast<size_t>(r0 + u) * 4) =
+              make_float4(res[u][0], res[u][1], res[u][2], res[u][3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) orow[static_cast<size_t>(r0 + u) * C + c] = res[u][c];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ packing / casts
+struct TapSel { int n; int idx[64]; };
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ packed, int Cin, int Cout,
+                                    int cout_pad, int transposed, TapSel sel, int fmt) {
+  const long long total = static_cast<long long>(sel.n) * cout_pad * Cin;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Cin);
+    const int co = static_cast<int>((i / Cin) % cout_pad);
+    const int t = static_cast<int>(i / (static_cast<long long>(Cin) * cout_pad));
+    float v = 0.f;
+    if (co < Cout) {
+      const long long base = static_cast<long long>(sel.idx[t]) * Cin * Cout;
+      v = transposed ? w[base + static_cast<long long>(co) * Cin + ci] : w[base + static_cast<long long>(ci) * Cout + co];
+    }
+    if (fmt == 0) { __half h = __float2half_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
+    else { __nv_bfloat16 h = __float2bfloat16_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
+  }
+}
+
+__global__ void cast_f32_to_16_kernel(const float* __restrict__ s, uint16_t* __restrict__ d, long long n,
+                                      long long n_pad, int fmt) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_pad;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = i < n ? s[i] : 0.f;
+    if (fmt == 0) { __half h = __float2half_rn(v); d[i] = *reinterpret_cast<uint16_t*>(&h); }
+    else { __nv_bfloat16 h = __float2bfloat16_rn(v); d[i] = *reinterpret_cast<uint16_t*>(&h); }
+  }
+}
+
+__global__ void cast_16_to_f32_kernel(const uint16_t* __restrict__ s, float* __restrict__ d, long long n, int fmt) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint16_t u = s[i];
+    d[i] = fmt == 0 ? __half2float(*reinterpret_cast<const __half*>(&u))
+                    : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ thin conv3d
+// Direct SAME convolution, one thread per output voxel, all COUT accumulators in registers; the filter
+// ([tap][ci][co] fp32, <= 14 KB) sits in shared memory and is read as warp-broadcast float4.
+template <int CIN, int COUT, int K, bool X_F32>
+__global__ void __launch_bounds__(256) conv3d_direct_kernel(const void* __restrict__ xv, const float* __restrict__ w,
+                                                            const float* __restrict__ bias,
+                                                            const float* __restrict__ alpha,
+                                                            uint16_t* __restrict__ out, int B, int H, int W, int D,
+                                                            int Ho, int Wo, int Do, int sy, int sx, int sz, int py,
+                                                            int px, int pz, int fmt) {
+  __shared__ __align__(16) float ws[K * K * K * CIN * COUT];
+  for (int i = threadIdx.x; i < K * K * K * CIN * COUT; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const long long total = static_cast<long long>(B) * Ho * Wo * Do;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int oz = static_cast<int>(idx % Do);
+  const int ox = static_cast<int>((idx / Do) % Wo);
+  const int oy = static_cast<int>((idx / (static_cast<long long>(Do) * Wo)) % Ho);
+  const int b = static_cast<int>(idx / (static_cast<long long>(Do) * Wo * Ho));
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  const int iy0 = oy * sy - py, ix0 = ox * sx - px, iz0 = oz * sz - pz;
+  for (int ky = 0; ky < K; ++ky) {
+    const int iy = iy0 + ky;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < K; ++kx) {
+      const int ix = ix0 + kx;
+      if (ix < 0 || ix >= W) continue;
+      const size_t rowbase = ((static_cast<size_t>(b) * H + iy) * W + ix) * D;
+#pragma unroll
+      for (int kz = 0; kz < K; ++kz) {
+        const int iz = iz0 + kz;
+        if (iz < 0 || iz >= D) continue;
+        float xin[CIN];
+        if constexpr (X_F32) {
+          const float* xp = static_cast<const float*>(xv) + (rowbase + iz) * CIN;
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) xin[ci] = __ldg(xp + ci);
+        } else {
+          static_assert(X_F32 || CIN % 8 == 0, "16-bit input needs CIN % 8 == 0");
+          const uint4* xp = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(xv) + (rowbase + iz) * CIN);
+#pragma unroll
+          for (int v = 0; v < CIN / 8; ++v) {
+            const uint4 q = __ldg(xp + v);
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f;
+              if (fmt == 0) f = __half22float2(*reinterpret_cast<const __half2*>(&u[j]));
+              else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[j]));
+              xin[v * 8 + 2 * j] = f.x;
+              xin[v * 8 + 2 * j + 1] = f.y;
+            }
+          }
+        }
+        const float* wt = ws + ((ky * K + kx) * K + kz) * CIN * COUT;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+          for (int c4 = 0; c4 < COUT; c4 += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wt + ci * COUT + c4);
+            acc[c4 + 0] = fmaf(xin[ci], w4.x, acc[c4 + 0]);
+            acc[c4 + 1] = fmaf(xin[ci], w4.y, acc[c4 + 1]);
+            acc[c4 + 2] = fmaf(xin[ci], w4.z, acc[c4 + 2]);
+            acc[c4 + 3] = fmaf(xin[ci], w4.w, acc[c4 + 3]);
+          }
+        }
+      }
+    }
+  }
+  uint32_t pk[COUT / 2];
+#pragma unroll
+  for (int c = 0; c < COUT; c += 2) {
+    float v0 = acc[c] + __ldg(bias + c), v1 = acc[c + 1] + __ldg(bias + c + 1);
+    if (alpha != nullptr) {
+      v0 = fmaxf(v0, 0.f) + __ldg(alpha + c) * fminf(v0, 0.f);
+      v1 = fmaxf(v1, 0.f) + __ldg(alpha + c + 1) * fminf(v1, 0.f);
+    }
+    if (fmt == 0) { __half2 h = __floats2half2_rn(v0, v1); pk[c / 2] = *reinterpret_cast<uint32_t*>(&h); }
+    else { __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1); pk[c / 2] = *reinterpret_cast<uint32_t*>(&h); }
+  }
+  uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(idx) * COUT);
+#pragma unroll
+  for (int v = 0; v < COUT / 8; ++v) op[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+}
+
+// ------------------------------------------------------------------------------------------ Phong
+__global__ void phong_kernel(const float* __restrict__ img, const float* __restrict__ light_dir,
+                             const float* __restrict__ light_col, float ambient, float k_diffuse, int white,
+                             int with_mask, float* __restrict__ out_f32, uint8_t* __restrict__ out_u8, int B,
+                             long long npix) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(B) * npix) return;
+  const int b = static_cast<int>(i / npix);
+  const float r = img[3 * i], g = img[3 * i + 1], bl = img[3 * i + 2];
+  // np_phong_shading (:162-200): n = (img-0.5)/|img-0.5| ; diffuse = k_d * max(n.l, 0) * light_col, clipped
+  const float nx = r - 0.5f, ny = g - 0.5f, nz = bl - 0.5f;
+  const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+  float lx = light_dir[3 * b], ly = light_dir[3 * b + 1], lz = light_dir[3 * b + 2];
+  const float linv = 1.0f / sqrtf(lx * lx + ly * ly + lz * lz);
+  lx *= linv; ly *= linv; lz *= linv;
+  const float ndl = fmaxf((nx * lx + ny * ly + nz * lz) * inv, 0.f);
+  float mask = 1.f;
+  if (with_mask) {  // np_mask (:138-148) / np_mask_white (:150-160)
+    const float nrm = white ? sqrtf((1.f - r) * (1.f - r) + (1.f - g) * (1.f - g) + (1.f - bl) * (1.f - bl))
+                            : sqrtf(r * r + g * g + bl * bl);
+    mask = 1.f / (1.f + expf(-(255.f * nrm - (white ? 80.f : 150.f))));
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float diff = fminf(fmaxf(k_diffuse * ndl * light_col[3 * b + c], 0.f), 1.f);
+    float v = with_mask ? mask * (ambient + diff) + (1.f - mask) : ambient + diff;
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    if (out_f32 != nullptr) out_f32[3 * i + c] = v;
+    if (out_u8 != nullptr) out_u8[3 * i + c] = static_cast<uint8_t>(fminf(fmaxf(255.f * v, 0.f), 255.f));
+  }
+}
+
+static inline int grid_for(long long n, int block, int cap = 148 * 32) {
+  long long g = (n + block - 1) / block;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+static void same_pad(int n_in, int k, int s, int* n_out, int* pb) {
+  *n_out = (n_in + s - 1) / s;
+  int total = (*n_out - 1) * s + k - n_in;
+  if (total < 0) total = 0;
+  *pb = total / 2;
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+extern "C" int rn_version(void) { return 100; }
+
+extern "C" const char* rn_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code < 0) return "rendernet_b200: invalid argument";
+  if (code >= 1000) return "rendernet_b200: cuTensorMapEncodeTiled failed";
+  return cudaGetErrorString(static_cast<cudaError_t>(code));
+}
+
+extern "C" int rn_resample_f32(const float* vox, const float* minv, float* out, int B, int C, int size, int new_size,
+                               int transform, void* stream) {
+  if (!vox || !minv || !out || B < 1 || size < 2 || new_size < 1) return -1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long rows = static_cast<long long>(B) * new_size * new_size;
+  const int block = 256;
+  const int grid = static_cast<int>((rows * 32 + block - 1) / block);
+  switch (C) {
+    case 1: resample_kernel<1><<<grid, block, 0, st>>>(vox, minv, out, B, size, new_size, transform); break;
+    case 2: resample_kernel<2><<<grid, block, 0, st>>>(vox, minv, out, B, size, new_size, transform); break;
+    case 3: resample_kernel<3><<<grid, block, 0, st>>>(vox, minv, out, B, size, new_size, transform); break;
+    case 4: resample_kernel<4><<<grid, block, 0, st>>>(vox, minv, out, B, size, new_size, transform); break;
+    default: return -2;
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_pack_conv_weights(const float* w, void* packed, int ntaps_total, int Cin, int Cout, int cout_pad,
+                                    int transposed, const int* tap_sel, int n_sel, int fmt, void* stream) {
+  if (!w || !packed || Cin < 1 || Cout < 1 || cout_pad < Cout) return -1;
+  TapSel sel;
+  if (tap_sel == nullptr) {
+    if (ntaps_total > 64) return -2;
+    sel.n = ntaps_total;
+    for (int i = 0; i < ntaps_total; ++i) sel.idx[i] = i;
+  } else {
+    if (n_sel > 64 || n_sel < 1) return -2;
+    sel.n = n_sel;
+    for (int i = 0; i < n_sel; ++i) {
+      if (tap_sel[i] < 0 || tap_sel[i] >= ntaps_total) return -3;
+      sel.idx[i] = tap_sel[i];
+    }
+  }
+  const long long total = static_cast<long long>(sel.n) * cout_pad * Cin;
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<uint16_t*>(packed), Cin, Cout, cout_pad, transposed, sel, fmt);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_cast_f32_to_16(const float* src, void* dst, long long n, long long n_pad, int fmt, void* stream) {
+  if (!src || !dst || n < 0 || n_pad < n) return -1;
+  if (n_pad == 0) return 0;
+  cast_f32_to_16_kernel<<<grid_for(n_pad, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<uint16_t*>(dst), n, n_pad, fmt);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_cast_16_to_f32(const void* src, float* dst, long long n, int fmt, void* stream) {
+  if (!src || !dst || n < 0) return -1;
+  if (n == 0) return 0;
+  cast_16_to_f32_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(src), dst, n, fmt);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------- igemm wrappers
+extern "C" int rn_conv2d_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
+                              const void* residual, int residual_is_f32, void* out16, float* out32, int B, int H,
+                              int W, int Cin, int Cout, int cout_pad, int kh, int kw, int fmt, void* stream) {
+  if (kh * kw > 28 || kh < 1 || kw < 1) return -20;
+  int8_t taps[28 * 3];
+  const int pby = (kh - 1) / 2, pbx = (kw - 1) / 2;  // SAME, stride 1: before = (k-1)//2
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) {
+      int8_t* t = taps + 3 * (ky * kw + kx);
+      t[0] = static_cast<int8_t>(kx - pbx); t[1] = static_cast<int8_t>(ky - pby); t[2] = 0;
+    }
+  rn_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.ndim = 2; d.B = B; d.H = H; d.W = W; d.D = 1; d.Cin = Cin; d.Cout = Cout; d.cout_pad = cout_pad;
+  d.ntaps = kh * kw; d.taps = taps; d.x = x; d.w_packed = w_packed; d.bias = bias; d.alpha = alpha; d.act = act;
+  d.residual = residual; d.residual_is_f32 = residual_is_f32; d.out16 = out16; d.out32 = out32;
+  d.o_base = 0; d.o_x = Cout; d.o_y = static_cast<long long>(W) * Cout; d.o_b = static_cast<long long>(H) * W * Cout;
+  d.o_z = 0; d.fmt = fmt;
+  return rn_conv_igemm(&d, stream);
+}
+
+extern "C" int rn_conv3d_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
+                              const void* residual, int residual_is_f32, void* out16, float* out32, int B, int H,
+                              int W, int D, int Cin, int Cout, int cout_pad, int k, int fmt, void* stream) {
+  if (k * k * k > 28 || k < 1) return -20;
+  int8_t taps[28 * 3];
+  const int pb = (k - 1) / 2;
+  for (int k0 = 0; k0 < k; ++k0)
+    for (int k1 = 0; k1 < k; ++k1)
+      for (int k2 = 0; k2 < k; ++k2) {
+        int8_t* t = taps + 3 * ((k0 * k + k1) * k + k2);  // TF filter [k0,k1,k2,..] over axes (H, W, D)
+        t[0] = static_cast<int8_t>(k1 - pb); t[1] = static_cast<int8_t>(k0 - pb); t[2] = static_cast<int8_t>(k2 - pb);
+      }
+  rn_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.ndim = 3; d.B = B; d.H = H; d.W = W; d.D = D; d.Cin = Cin; d.Cout = Cout; d.cout_pad = cout_pad;
+  d.ntaps = k * k * k; d.taps = taps; d.x = x; d.w_packed = w_packed; d.bias = bias; d.alpha = alpha; d.act = act;
+  d.residual = residual; d.residual_is_f32 = residual_is_f32; d.out16 = out16; d.out32 = out32;
+  d.o_base = 0; d.o_z = Cout; d.o_x = static_cast<long long>(D) * Cout; d.o_y = static_cast<long long>(W) * D * Cout;
+  d.o_b = static_cast<long long>(H) * W * D * Cout; d.fmt = fmt;
+  return rn_conv_igemm(&d, stream);
+}
+
+// Transposed SAME conv: o = i*s + kk - pb, pb = max(k-s,0)/2.  Output phase a (o = j*s + a) receives the
+// filter taps kk == (a+pb) mod s, read at input offset d = (a + pb - kk)/s.
+namespace {
+struct PhaseTaps { int n; int src[28]; int8_t d[28 * 3]; };
+void phase_taps(int kh, int kw, int s, int ay, int ax, PhaseTaps* pt) {
+  const int pby = (kh - s > 0 ? kh - s : 0) / 2, pbx = (kw - s > 0 ? kw - s : 0) / 2;
+  pt->n = 0;
+  for (int ky = 0; ky < kh; ++ky) {
+    const int ny = ay + pby - ky;
+    if (((ny % s) + s) % s != 0) continue;
+    for (int kx = 0; kx < kw; ++kx) {
+      const int nx = ax + pbx - kx;
+      if (((nx % s) + s) % s != 0) continue;
+      const int dy = (ny >= 0) ? ny / s : -((-ny) / s), dx = (nx >= 0) ? nx / s : -((-nx) / s);
+      pt->src[pt->n] = ky * kw + kx;
+      pt->d[3 * pt->n + 0] = static_cast<int8_t>(dx);
+      pt->d[3 * pt->n + 1] = static_cast<int8_t>(dy);
+      pt->d[3 * pt->n + 2] = 0;
+      ++pt->n;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int rn_pack_conv2d_transpose_weights(const float* w, void* packed, int kh, int kw, int Cin, int Cout,
+                                                int cout_pad, int stride, int fmt, void* stream) {
+  if (kh * kw > 28 || stride < 1) return -20;
+  size_t off = 0;
+  for (int ay = 0; ay < stride; ++ay)
+    for (int ax = 0; ax < stride; ++ax) {
+      PhaseTaps pt;
+      phase_taps(kh, kw, stride, ay, ax, &pt);
+      if (pt.n == 0) continue;
+      int r = rn_pack_conv_weights(w, static_cast<uint16_t*>(packed) + off, kh * kw, Cin, Cout, cout_pad, 1, pt.src,
+                                   pt.n, fmt, stream);
+      if (r != 0) return r;
+      off += static_cast<size_t>(pt.n) * cout_pad * Cin;
+    }
+  return 0;
+}
+
+extern "C" int rn_conv2d_transpose_same(const void* x, const void* w_packed, const float* bias, const float* alpha,
+                                        int act, void* out16, float* out32, int B, int H, int W, int Cin, int Cout,
+                                        int cout_pad, int kh, int kw, int stride, int fmt, void* stream) {
+  if (kh * kw > 28 || stride < 1) return -20;
+  const int Ho = H * stride, Wo = W * stride;
+  size_t off = 0;
+  for (int ay = 0; ay < stride; ++ay)
+    for (int ax = 0; ax < stride; ++ax) {
+      PhaseTaps pt;
+      phase_taps(kh, kw, stride, ay, ax, &pt);
+      if (pt.n == 0) return -21;  // k < stride: holes in the output are not supported
+      rn_conv_desc d;
+      memset(&d, 0, sizeof(d));
+      d.ndim = 2; d.B = B; d.H = H; d.W = W; d.D = 1; d.Cin = Cin; d.Cout = Cout; d.cout_pad = cout_pad;
+      d.ntaps = pt.n; d.taps = pt.d; d.x = x;
+      d.w_packed = static_cast<const uint16_t*>(w_packed) + off;
+      d.bias = bias; d.alpha = alpha; d.act = act; d.out16 = out16; d.out32 = out32;
+      d.o_base = (static_cast<long long>(ay) * Wo + ax) * Cout;
+      d.o_x = static_cast<long long>(stride) * Cout;
+      d.o_y = static_cast<long long>(stride) * Wo * Cout;
+      d.o_b = static_cast<long long>(Ho) * Wo * Cout;
+      d.fmt = fmt;
+      int r = rn_conv_igemm(&d, stream);
+      if (r != 0) return r;
+      off += static_cast<size_t>(pt.n) * cout_pad * Cin;
+    }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- thin conv3d
+extern "C" int rn_conv3d_direct(const void* x, int x_is_f32, const float* w, const float* bias, const float* alpha,
+                                void* out16, int B, int H, int W, int D, int Cin, int Cout, int k, int sy, int sx,
+                                int sz, int fmt, void* stream) {
+  if (!x || !w || !bias || !out16) return -1;
+  int Ho, Wo, Do, py, px, pz;
+  same_pad(H, k, sy, &Ho, &py);
+  same_pad(W, k, sx, &Wo, &px);
+  same_pad(D, k, sz, &Do, &pz);
+  const long long total = static_cast<long long>(B) * Ho * Wo * Do;
+  const int block = 256;
+  const int grid = static_cast<int>((total + block - 1) / block);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint16_t* o = static_cast<uint16_t*>(out16);
+#define RN_LAUNCH_DIRECT(CI, CO, KK, XF)                                                                          \
+  conv3d_direct_kernel<CI, CO, KK, XF><<<grid, block, 0, st>>>(x, w, bias, alpha, o, B, H, W, D, Ho, Wo, Do, sy, \
+                                                                  sx, sz, py, px, pz, fmt)
+  if (Cin == 1 && Cout == 8 && k == 5 && x_is_f32) RN_LAUNCH_DIRECT(1, 8, 5, true);
+  else if (Cin == 5 && Cout == 8 && k == 5 && x_is_f32) RN_LAUNCH_DIRECT(5, 8, 5, true);
+  else if (Cin == 8 && Cout == 16 && k == 3 && !x_is_f32) RN_LAUNCH_DIRECT(8, 16, 3, false);
+  else if (Cin == 8 && Cout == 8 && k == 3 && !x_is_f32) RN_LAUNCH_DIRECT(8, 8, 3, false);
+  else if (Cin == 2 && Cout == 8 && k == 3 && x_is_f32) RN_LAUNCH_DIRECT(2, 8, 3, true);
+  else return -2;
+#undef RN_LAUNCH_DIRECT
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_phong_composite(const float* img, const float* light_dir, const float* light_col, float ambient,
+                                  float k_diffuse, int background_white, int with_mask, float* out_f32,
+                                  uint8_t* out_u8, int B, int H, int W, void* stream) {
+  if (!img || !light_dir || !light_col || (!out_f32 && !out_u8)) return -1;
+  const long long npix = static_cast<long long>(H) * W;
+  const long long total = npix * B;
+  const int block = 256;
+  phong_kernel<<<static_cast<int>((total + block - 1) / block), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, light_dir, light_col, ambient, k_diffuse, background_white, with_mask, out_f32, out_u8, B, npix);
+  return static_cast<int>(cudaGetLastError());
+}

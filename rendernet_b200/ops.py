@@ -1,0 +1,256 @@
+"""Torch-facing wrappers of the C-ABI kernels.  PyTorch is plumbing here (device memory, streams);
+all arithmetic happens in librendernet_b200.so.  Everything requires CUDA tensors; there is no
+CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from ._lib import check, lib, rn_conv_desc
+
+ACT_NONE, ACT_PRELU, ACT_SIGMOID = 0, 1, 2
+_ACT = {None: ACT_NONE, "none": ACT_NONE, "prelu": ACT_PRELU, "sigmoid": ACT_SIGMOID}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _cuda(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("rendernet_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def fmt_of(dtype: torch.dtype) -> int:
+    if dtype == torch.float16:
+        return 0
+    if dtype == torch.bfloat16:
+        return 1
+    raise TypeError(f"16-bit dtype expected, got {dtype}")
+
+
+def round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+# --------------------------------------------------------------------------------------- resampler
+def resample(vox: torch.Tensor, minv: torch.Tensor, new_size: int, transform: bool) -> torch.Tensor:
+    """vox [B,S,S,S,C] fp32, minv [B,3,4] fp32 -> [B,N,N,N,C] fp32 (rn_resample_f32)."""
+    vox = _cuda(vox, torch.float32)
+    minv = _cuda(minv, torch.float32)
+    B, S, _, _, Cc = vox.shape
+    out = torch.empty((B, new_size, new_size, new_size, Cc), device=vox.device, dtype=torch.float32)
+    check(lib.rn_resample_f32(vox.data_ptr(), minv.data_ptr(), out.data_ptr(), B, Cc, S, new_size,
+                              1 if transform else 0, _stream()), "rn_resample_f32")
+    return out
+
+
+# --------------------------------------------------------------------------------------- packed layers
+@dataclass
+class PackedConv:
+    """Device-resident, kernel-ready parameters of one convolution layer."""
+    kind: str                      # conv2d | conv3d | conv2d_transpose
+    ksize: Sequence[int]
+    stride: int
+    cin: int
+    cout: int
+    cout_pad: int
+    w: torch.Tensor                # 16-bit packed filter
+    bias: torch.Tensor             # fp32 [cout_pad]
+    alpha: Optional[torch.Tensor]  # fp32 [cout_pad]
+    dtype: torch.dtype
+
+
+def _pad_vec(v: Optional[torch.Tensor], n: int, n_pad: int, device) -> Optional[torch.Tensor]:
+    if v is None:
+        return None
+    out = torch.zeros(n_pad, device=device, dtype=torch.float32)
+    out[:n] = v.to(device=device, dtype=torch.float32).reshape(-1)
+    return out
+
+
+def pack_conv(kind: str, w_tf: torch.Tensor, bias: Optional[torch.Tensor], alpha: Optional[torch.Tensor],
+              stride: int = 1, dtype: torch.dtype = torch.float16, device="cuda") -> PackedConv:
+    """w_tf in TF filter layout: conv2d [kh,kw,Cin,Cout]; conv3d [k,k,k,Cin,Cout];
+    conv2d_transpose [kh,kw,Cout,Cin]."""
+    w_tf = torch.as_tensor(w_tf, dtype=torch.float32).to(device).contiguous()
+    fmt = fmt_of(dtype)
+    if kind == "conv2d_transpose":
+        kh, kw, cout, cin = w_tf.shape
+        ks = (kh, kw)
+    elif kind == "conv2d":
+        kh, kw, cin, cout = w_tf.shape
+        ks = (kh, kw)
+    elif kind == "conv3d":
+        k0, k1, k2, cin, cout = w_tf.shape
+        ks = (k0, k1, k2)
+    else:
+        raise ValueError(kind)
+    cout_pad = round_up(cout, 16)
+    ntaps = 1
+    for k in ks:
+        ntaps *= k
+    packed = torch.empty((ntaps, cout_pad, cin), device=device, dtype=dtype)
+    if kind == "conv2d_transpose":
+        check(lib.rn_pack_conv2d_transpose_weights(w_tf.data_ptr(), packed.data_ptr(), ks[0], ks[1], cin, cout,
+                                                   cout_pad, stride, fmt, _stream()), "pack transpose")
+    else:
+        if stride != 1:
+            raise ValueError("tensor-core conv path is stride 1")
+        check(lib.rn_pack_conv_weights(w_tf.data_ptr(), packed.data_ptr(), ntaps, cin, cout, cout_pad, 0, None, 0,
+                                       fmt, _stream()), "pack")
+    b = _pad_vec(bias if bias is not None else torch.zeros(cout), cout, cout_pad, device)
+    a = _pad_vec(alpha, cout, cout_pad, device)
+    return PackedConv(kind, ks, stride, cin, cout, cout_pad, packed, b, a, dtype)
+
+
+def _out_buffers(shape, dtype, device, want16, want32, out16, out32):
+    if want16 and out16 is None:
+        out16 = torch.empty(shape, device=device, dtype=dtype)
+    if want32 and out32 is None:
+        out32 = torch.empty(shape, device=device, dtype=torch.float32)
+    return out16, out32
+
+
+def conv2d(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, residual: Optional[torch.Tensor] = None,
+           want16: bool = True, want32: bool = False, out16=None, out32=None):
+    """SAME stride-1 conv2d + bias (+PReLU/sigmoid) (+residual).  x [B,H,W,Cin] 16-bit."""
+    x = _cuda(x, L.dtype)
+    B, H, W, Cin = x.shape
+    assert Cin == L.cin and L.kind == "conv2d"
+    out16, out32 = _out_buffers((B, H, W, L.cout), L.dtype, x.device, want16, want32, out16, out32)
+    res_f32 = 0
+    if residual is not None:
+        residual = _cuda(residual)
+        res_f32 = 1 if residual.dtype == torch.float32 else 0
+        assert tuple(residual.shape) == (B, H, W, L.cout)
+    a = _ACT[act]
+    check(lib.rn_conv2d_same(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(),
+                             _ptr(L.alpha) if a == ACT_PRELU else None, a, _ptr(residual), res_f32,
+                             _ptr(out16), _ptr(out32), B, H, W, Cin, L.cout, L.cout_pad, L.ksize[0], L.ksize[1],
+                             fmt_of(L.dtype), _stream()), "rn_conv2d_same")
+    return out16 if not want32 else ((out16, out32) if want16 else out32)
+
+
+def conv3d(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, residual: Optional[torch.Tensor] = None,
+           want16: bool = True, want32: bool = False, out16=None, out32=None):
+    """SAME stride-1 k^3 conv3d on the tensor pipe.  x [B,H,W,D,Cin] 16-bit."""
+    x = _cuda(x, L.dtype)
+    B, H, W, D, Cin = x.shape
+    assert Cin == L.cin and L.kind == "conv3d"
+    out16, out32 = _out_buffers((B, H, W, D, L.cout), L.dtype, x.device, want16, want32, out16, out32)
+    res_f32 = 0
+    if residual is not None:
+        residual = _cuda(residual)
+        res_f32 = 1 if residual.dtype == torch.float32 else 0
+    a = _ACT[act]
+    check(lib.rn_conv3d_same(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(),
+                             _ptr(L.alpha) if a == ACT_PRELU else None, a, _ptr(residual), res_f32,
+                             _ptr(out16), _ptr(out32), B, H, W, D, Cin, L.cout, L.cout_pad, L.ksize[0],
+                             fmt_of(L.dtype), _stream()), "rn_conv3d_same")
+    return out16 if not want32 else ((out16, out32) if want16 else out32)
+
+
+def conv2d_transpose(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, want16: bool = True,
+                     want32: bool = False, out16=None, out32=None):
+    """SAME transposed conv, out = in*stride.  x [B,H,W,Cin] 16-bit."""
+    x = _cuda(x, L.dtype)
+    B, H, W, Cin = x.shape
+    assert Cin == L.cin and L.kind == "conv2d_transpose"
+    s = L.stride
+    out16, out32 = _out_buffers((B, H * s, W * s, L.cout), L.dtype, x.device, want16, want32, out16, out32)
+    a = _ACT[act]
+    check(lib.rn_conv2d_transpose_same(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(),
+                                       _ptr(L.alpha) if a == ACT_PRELU else None, a, _ptr(out16), _ptr(out32),
+                                       B, H, W, Cin, L.cout, L.cout_pad, L.ksize[0], L.ksize[1], s,
+                                       fmt_of(L.dtype), _stream()), "rn_conv2d_transpose_same")
+    return out16 if not want32 else ((out16, out32) if want16 else out32)
+
+
+def conv_igemm_raw(x, w_packed, bias, taps, ndim, B, H, W, D, Cin, Cout, cout_pad, out16=None, out32=None,
+                   alpha=None, act=ACT_NONE, residual=None, o=None, fmt=0, force_bn=0, force_kps=0, max_ctas=0):
+    """Direct access to rn_conv_igemm for tests / tuning.  taps: list of (dx,dy,dz)."""
+    n = len(taps)
+    arr = (C.c_int8 * (3 * n))(*[v for t in taps for v in t])
+    d = rn_conv_desc()
+    d.ndim, d.B, d.H, d.W, d.D = ndim, B, H, W, D
+    d.Cin, d.Cout, d.cout_pad, d.ntaps = Cin, Cout, cout_pad, n
+    d.taps = C.cast(arr, C.c_void_p)
+    d.x, d.w_packed, d.bias, d.alpha = x.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), _ptr(alpha)
+    d.act = act
+    d.residual = _ptr(residual)
+    d.residual_is_f32 = 1 if (residual is not None and residual.dtype == torch.float32) else 0
+    d.out16, d.out32 = _ptr(out16), _ptr(out32)
+    if o is None:
+        if ndim == 2:
+            o = (0, H * W * Cout, W * Cout, Cout, 0)
+        else:
+            o = (0, H * W * D * Cout, W * D * Cout, D * Cout, Cout)
+    d.o_base, d.o_b, d.o_y, d.o_x, d.o_z = o
+    d.fmt, d.force_bn, d.force_kps, d.max_ctas = fmt, force_bn, force_kps, max_ctas
+    check(lib.rn_conv_igemm(C.byref(d), _stream()), "rn_conv_igemm")
+
+
+# --------------------------------------------------------------------------------------- thin conv3d
+def conv3d_direct(x: torch.Tensor, w_tf: torch.Tensor, bias: torch.Tensor, alpha: Optional[torch.Tensor],
+                  stride: Sequence[int], dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """CUDA-core SAME conv3d + bias + PReLU for the thin first layers.  x fp32 or 16-bit
+    [B,H,W,D,Cin]; w_tf fp32 [k,k,k,Cin,Cout]; returns 16-bit."""
+    x = _cuda(x)
+    w_tf = _cuda(w_tf, torch.float32)
+    bias = _cuda(bias, torch.float32)
+    B, H, W, D, Cin = x.shape
+    k = w_tf.shape[0]
+    Cout = w_tf.shape[4]
+    sy, sx, sz = stride
+    Ho, Wo, Do = -(-H // sy), -(-W // sx), -(-D // sz)
+    out = torch.empty((B, Ho, Wo, Do, Cout), device=x.device, dtype=dtype)
+    check(lib.rn_conv3d_direct(x.data_ptr(), 1 if x.dtype == torch.float32 else 0, w_tf.data_ptr(),
+                               bias.data_ptr(), _ptr(alpha), out.data_ptr(), B, H, W, D, Cin, Cout, k, sy, sx, sz,
+                               fmt_of(dtype), _stream()), "rn_conv3d_direct")
+    return out
+
+
+# --------------------------------------------------------------------------------------- misc
+def cast_to_16(x: torch.Tensor, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    x = _cuda(x, torch.float32)
+    out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    check(lib.rn_cast_f32_to_16(x.data_ptr(), out.data_ptr(), x.numel(), x.numel(), fmt_of(dtype), _stream()), "cast")
+    return out
+
+
+def cast_to_f32(x: torch.Tensor) -> torch.Tensor:
+    x = _cuda(x)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    check(lib.rn_cast_16_to_f32(x.data_ptr(), out.data_ptr(), x.numel(), fmt_of(x.dtype), _stream()), "cast")
+    return out
+
+
+def phong_composite(img: torch.Tensor, light_dir: torch.Tensor, light_col: torch.Tensor, ambient: float,
+                    k_diffuse: float, background_white: bool = False, with_mask: bool = True,
+                    want_u8: bool = False):
+    img = _cuda(img, torch.float32)
+    B, H, W, _ = img.shape
+    light_dir = _cuda(light_dir.to(device=img.device, dtype=torch.float32))
+    light_col = _cuda(light_col.to(device=img.device, dtype=torch.float32))
+    if light_dir.shape[0] == 1 and B > 1:
+        light_dir = light_dir.expand(B, 3).contiguous()
+    if light_col.shape[0] == 1 and B > 1:
+        light_col = light_col.expand(B, 3).contiguous()
+    out = torch.empty_like(img)
+    u8 = torch.empty(img.shape, device=img.device, dtype=torch.uint8) if want_u8 else None
+    check(lib.rn_phong_composite(img.data_ptr(), light_dir.data_ptr(), light_col.data_ptr(), float(ambient),
+                                 float(k_diffuse), 1 if background_white else 0, 1 if with_mask else 0,
+                                 out.data_ptr(), _ptr(u8), B, H, W, _stream()), "rn_phong_composite")
+    return (out, u8) if want_u8 else out
