@@ -52,6 +52,11 @@ int rn_pack_conv_weights(const float* w, void* packed, int ntaps_total, int Cin,
 int rn_cast_f32_to_16(const float* src, void* dst, long long n, long long n_pad, int fmt, void* stream);
 int rn_cast_16_to_f32(const void* src, float* dst, long long n, int fmt, void* stream);
 
+/* y = act(x + bias[c]) + residual over a 16-bit channel-last tensor of n elements (c = index % C).
+ * Standalone tools/layer_util.py:27-45 prelu / tf.add / tf.nn.sigmoid when not fused into a conv epilogue. */
+int rn_bias_act_16(const void* x, const float* bias, const float* alpha, int act, const void* residual,
+                   void* out16, float* out32, long long n, int C, int fmt, void* stream);
+
 /* ---- tensor-core implicit-GEMM convolution (tcgen05 + TMA) ----------------------------------------
  * out[b,y,x,z,n] = act( bias[n] + sum_t sum_ci  x[b, y+dy_t, x+dx_t, z+dz_t, ci] * w_packed[t][n][ci] ) + residual
  * with zero outside the input (TF SAME padding is expressed through the tap offsets).

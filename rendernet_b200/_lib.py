@@ -35,6 +35,7 @@ SIGNATURES = {
     "rn_pack_conv_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "rn_cast_f32_to_16": (_i, [_vp, _vp, _ll, _ll, _i, _vp]),
     "rn_cast_16_to_f32": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "rn_bias_act_16": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "rn_conv_igemm": (_i, [C.POINTER(rn_conv_desc), _vp]),
     "rn_conv2d_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rn_conv3d_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

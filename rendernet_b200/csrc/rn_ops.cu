@@ -144,6 +144,35 @@ __global__ void cast_16_to_f32_kernel(const uint16_t* __restrict__ s, float* __r
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ elementwise
+// y = act(x + bias[c]) + residual, 16-bit in/out, channel = innermost axis (standalone prelu / tf.add /
+// sigmoid when they cannot be fused into a convolution epilogue; tools/layer_util.py:27-45,73,105).
+__global__ void bias_act_kernel(const uint16_t* __restrict__ x, const float* __restrict__ bias,
+                                const float* __restrict__ alpha, int act, const uint16_t* __restrict__ res,
+                                uint16_t* __restrict__ out, float* __restrict__ out32, long long n, int C, int fmt) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const uint16_t u = x[i];
+    float v = fmt == 0 ? __half2float(*reinterpret_cast<const __half*>(&u))
+                       : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
+    if (bias != nullptr) v += bias[c];
+    if (act == 1) v = fmaxf(v, 0.f) + alpha[c] * fminf(v, 0.f);
+    else if (act == 2) v = 1.f / (1.f + __expf(-v));
+    if (res != nullptr) {
+      const uint16_t r = res[i];
+      v += fmt == 0 ? __half2float(*reinterpret_cast<const __half*>(&r))
+                    : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&r));
+    }
+    if (out != nullptr) {
+      if (fmt == 0) { __half h = __float2half_rn(v); out[i] = *reinterpret_cast<uint16_t*>(&h); }
+      else { __nv_bfloat16 h = __float2bfloat16_rn(v); out[i] = *reinterpret_cast<uint16_t*>(&h); }
+    }
+    if (out32 != nullptr) out32[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ thin conv3d
 // Direct SAME convolution, one thread per output voxel, all COUT accumulators in registers; the filter
 // ([tap][ci][co] fp32, <= 14 KB) sits in shared memory and is read as warp-broadcast float4.
@@ -341,6 +370,17 @@ extern "C" int rn_cast_16_to_f32(const void* src, float* dst, long long n, int f
   if (n == 0) return 0;
   cast_16_to_f32_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint16_t*>(src), dst, n, fmt);
+  return static_cast<int>(cudaGetLastError());
+}
+
+
+extern "C" int rn_bias_act_16(const void* x, const float* bias, const float* alpha, int act, const void* residual,
+                              void* out16, float* out32, long long n, int C, int fmt, void* stream) {
+  if (!x || (!out16 && !out32) || n < 0 || C < 1 || (act == 1 && !alpha)) return -1;
+  if (n == 0) return 0;
+  bias_act_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(x), bias, alpha, act, static_cast<const uint16_t*>(residual),
+      static_cast<uint16_t*>(out16), out32, n, C, fmt);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -1,0 +1,251 @@
+"""GPU-backed stand-in for the handful of TensorFlow-1 idioms the reference's *model functions* use
+(RenderNet_Shader.py:32-131, tools/layer_util.py): variable scopes, `tf.get_variable`, `tf.add`,
+`tf.cast`, `tf.nn.dropout/sigmoid/relu`, `tf.cond`, `slim.conv2d(_transpose)`.
+
+Design: the reference builds a TF graph node by node; TF then runs each node as its own kernel.  Here
+each convolution call returns a *deferred* tensor (`Deferred`) whose epilogue is still open, so that the
+`prelu(...)`, `tf.add(conv, shortcut)` or `tf.nn.sigmoid(...)` that the reference applies next is folded
+into the convolution kernel's fused epilogue instead of becoming a separate pass over HBM.  A deferred
+tensor is realised (its kernel launched) the moment anything else consumes it.
+
+Variables live in a process-wide store keyed by the reference's scoped names
+("encoder/res2_3/con1_3X3/weights", ...); kernel-ready packed copies are cached per variable.
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+
+float32 = torch.float32
+float16 = torch.float16
+bfloat16 = torch.bfloat16
+int32 = torch.int32
+
+COMPUTE_DTYPE = torch.float16   # operand / activation storage type of the tensor-core path
+
+
+# ------------------------------------------------------------------------------------------ variables
+class VariableStore:
+    def __init__(self):
+        self.vars: Dict[str, torch.Tensor] = {}
+        self.packed: Dict[str, object] = {}
+        self.scope: List[str] = []
+        self.rng = np.random.default_rng(0)
+        self.device = "cuda"
+
+    def reset(self, seed: int = 0):
+        self.vars.clear()
+        self.packed.clear()
+        self.scope = []
+        self.rng = np.random.default_rng(seed)
+
+    def full_name(self, name: str) -> str:
+        return "/".join(self.scope + [name])
+
+
+_STORE = VariableStore()
+
+
+def get_store() -> VariableStore:
+    return _STORE
+
+
+def reset_default_graph(seed: int = 0):
+    _STORE.reset(seed)
+
+
+def _npz_key(name: str) -> str:
+    """npz-dir spelling of a variable (tools/model_util.py:32-38, Reconstruct_RenderNet_Face.py:128):
+    path with '/' -> '_' minus the leading 'encoder/'."""
+    n = name[len("encoder/"):] if name.startswith("encoder/") else name
+    return n.replace("/", "_")
+
+
+def load_weight_dict(weights: Dict[str, np.ndarray]):
+    """Install pretrained/seeded weights.  Keys may be TF variable names
+    ('encoder/e_conv1/e_conv1/weights[:0]') or the npz-dir spelling ('e_conv1_e_conv1_weights')."""
+    _STORE.packed.clear()
+    for k, v in weights.items():
+        k = k[:-2] if k.endswith(":0") else k
+        _STORE.vars[k] = torch.as_tensor(np.asarray(v), dtype=torch.float32)
+
+
+def _lookup(full: str) -> Optional[torch.Tensor]:
+    v = _STORE.vars.get(full)
+    if v is None:
+        v = _STORE.vars.get(_npz_key(full))
+        if v is not None:
+            _STORE.vars[full] = v
+    return v
+
+
+@contextlib.contextmanager
+def variable_scope(name, reuse=None, **_):
+    _STORE.scope.append(name)
+    try:
+        yield
+    finally:
+        _STORE.scope.pop()
+
+
+class constant_initializer:
+    def __init__(self, value=0.0):
+        self.value = value
+
+    def __call__(self, shape):
+        return np.full(shape, self.value, np.float32)
+
+
+class random_normal_initializer:
+    def __init__(self, mean=0.0, stddev=1.0):
+        self.mean, self.stddev = mean, stddev
+
+    def __call__(self, shape):
+        return (_STORE.rng.standard_normal(shape) * self.stddev + self.mean).astype(np.float32)
+
+
+class xavier_initializer:
+    """tf.contrib.layers.xavier_initializer (uniform): limit = sqrt(6/(fan_in+fan_out))."""
+
+    def __call__(self, shape):
+        rf = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+        lim = math.sqrt(6.0 / (rf * shape[-2] + rf * shape[-1]))
+        return _STORE.rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+def get_variable(name, shape=None, dtype=None, initializer=None, trainable=True, **_) -> torch.Tensor:
+    """tf.get_variable under the current scope; existing (loaded) values win, like a restored checkpoint."""
+    full = _STORE.full_name(name)
+    v = _lookup(full)
+    if v is None:
+        if callable(initializer):
+            shp = tuple(int(s) for s in (shape if isinstance(shape, (list, tuple)) else [shape]))
+            v = torch.from_numpy(initializer(shp))
+        elif initializer is not None:
+            v = torch.as_tensor(np.asarray(initializer), dtype=torch.float32)
+        else:
+            shp = tuple(int(s) for s in shape)
+            v = torch.from_numpy(xavier_initializer()(shp))
+        _STORE.vars[full] = v
+    elif shape is not None:
+        shp = tuple(int(s) for s in (shape if isinstance(shape, (list, tuple)) else [shape]))
+        if tuple(v.shape) != shp:
+            raise ValueError(f"variable {full}: stored shape {tuple(v.shape)} != requested {shp}")
+    v._rn_name = full
+    return v
+
+
+def global_variables() -> Dict[str, torch.Tensor]:
+    return dict(_STORE.vars)
+
+
+# ------------------------------------------------------------------------------------------ deferred tensors
+class Deferred:
+    """A convolution whose fused epilogue (activation, residual) is still open."""
+
+    def __init__(self, run: Callable, shape, dtype):
+        self._run = run                    # run(act, alpha, residual, want32) -> tensor
+        self.shape = tuple(shape)
+        self.dtype = dtype
+        self.act: Optional[str] = None
+        self.alpha: Optional[torch.Tensor] = None
+        self.residual: Optional[torch.Tensor] = None
+        self._value: Optional[torch.Tensor] = None
+        self.want32 = False
+
+    @property
+    def open(self) -> bool:
+        return self._value is None
+
+    def realize(self) -> torch.Tensor:
+        if self._value is None:
+            self._value = self._run(self.act, self.alpha, self.residual, self.want32)
+            self._run = None
+            self.residual = None
+        return self._value
+
+    def get_shape(self):
+        return list(self.shape)
+
+
+def realize(x):
+    """Materialise a (possibly deferred) tensor."""
+    return x.realize() if isinstance(x, Deferred) else x
+
+
+def shape(x):
+    return list(x.shape)
+
+
+def cast(x, dtype):
+    """tf.cast.  The reference casts to float32 around residual adds (layer_util.py:73,105); deferred
+    tensors pass through untouched because the add happens in fp32 inside the epilogue anyway."""
+    if isinstance(x, Deferred):
+        return x
+    if dtype in (torch.float32, "float32") and x.dtype in (torch.float16, torch.bfloat16):
+        return x            # kept in 16-bit storage; arithmetic on it is fp32 in-kernel
+    return x
+
+
+def add(a, b):
+    """tf.add(conv_out, shortcut) -> residual fused into the conv epilogue when possible."""
+    if isinstance(a, Deferred) and a.open and a.residual is None:
+        a.residual = realize(b)
+        return a
+    if isinstance(b, Deferred) and b.open and b.residual is None:
+        b.residual = realize(a)
+        return b
+    a, b = realize(a), realize(b)
+    return ops.bias_act(a, None, None, None, residual=b)
+
+
+def prelu_apply(x, alpha: torch.Tensor):
+    if isinstance(x, Deferred) and x.open and x.act is None and x.residual is None:
+        x.act, x.alpha = "prelu", alpha
+        return x
+    return ops.bias_act(realize(x), None, alpha, "prelu")
+
+
+def cond(pred, true_fn, false_fn):
+    return true_fn() if bool(pred) else false_fn()
+
+
+def constant(v, dtype=None):
+    return v
+
+
+class _NN:
+    @staticmethod
+    def dropout(x, keep_prob):
+        kp = float(keep_prob)
+        if kp != 1.0:
+            raise NotImplementedError("rendernet_b200 is the inference path: dropout keep_prob must be 1 "
+                                      "(layer_util.keep_prob(prob, is_training=False))")
+        return x
+
+    @staticmethod
+    def sigmoid(x, name=None):
+        if isinstance(x, Deferred) and x.open and x.act is None and x.residual is None:
+            x.act = "sigmoid"
+            x.want32 = True            # the network output is float32 like the reference's
+            return x
+        return ops.bias_act(realize(x), None, None, "sigmoid", want32=True)
+
+    @staticmethod
+    def relu(x):
+        zero = None
+        if isinstance(x, Deferred) and x.open and x.act is None and x.residual is None:
+            x.act, x.alpha = "prelu", "zeros"
+            return x
+        x = realize(x)
+        zero = torch.zeros(x.shape[-1], device=x.device, dtype=torch.float32)
+        return ops.bias_act(x, None, zero, "prelu")
+
+
+nn = _NN()
