@@ -254,3 +254,27 @@ def phong_composite(img: torch.Tensor, light_dir: torch.Tensor, light_col: torch
                                  float(k_diffuse), 1 if background_white else 0, 1 if with_mask else 0,
                                  out.data_ptr(), _ptr(u8), B, H, W, _stream()), "rn_phong_composite")
     return (out, u8) if want_u8 else out
+
+
+def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], alpha: Optional[torch.Tensor], act: Optional[str],
+             residual: Optional[torch.Tensor] = None, want32: bool = False):
+    """y = act(x + bias[c]) + residual on a 16-bit channel-last tensor (rn_bias_act_16)."""
+    x = _cuda(x)
+    if x.dtype == torch.float32:
+        x = cast_to_16(x)
+    C_ = x.shape[-1]
+    a = _ACT[act]
+    dev = x.device
+    if bias is not None:
+        bias = _cuda(bias.to(device=dev, dtype=torch.float32))
+    if alpha is not None:
+        alpha = _cuda(alpha.to(device=dev, dtype=torch.float32))
+    if residual is not None:
+        residual = _cuda(residual)
+        if residual.dtype != x.dtype:
+            residual = cast_to_16(residual.float(), x.dtype) if residual.dtype == torch.float32 else residual.to(x.dtype)
+    out16 = None if want32 else torch.empty_like(x)
+    out32 = torch.empty(x.shape, device=dev, dtype=torch.float32) if want32 else None
+    check(lib.rn_bias_act_16(x.data_ptr(), _ptr(bias), _ptr(alpha), a, _ptr(residual), _ptr(out16), _ptr(out32),
+                             x.numel(), C_, fmt_of(x.dtype), _stream()), "rn_bias_act_16")
+    return out32 if want32 else out16
