@@ -1,0 +1,110 @@
+"""RenderEngine: the forward rendering path as one replayable unit.
+
+Owns the device-resident state of one model replica (packed weights in tfcompat's store), fixed-shape
+input/output buffers and a CUDA graph of the whole step (resample -> 3-D encoder -> projection ->
+2-D trunk -> decoder [-> Phong]), so a step is: H2D(voxels, 3x4 matrices) -> graph replay -> D2H(image).
+This is the call a user makes for throughput; `RenderNet_demo.Session.run` routes through it too.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from . import tfcompat as tf
+from .RenderNet_Shader import RenderNet
+from .resampling_voxel_grid import inverse_sampling_matrix, tf_rotation_around_grid_centroid
+
+
+class RenderEngine:
+    def __init__(self, weights: Optional[Dict[str, np.ndarray]], batch: int, is_greyscale: bool = False,
+                 size: int = 64, new_size: int = 128, use_graph: bool = True, phong: Optional[dict] = None,
+                 seed: int = 0, device: str = "cuda"):
+        """weights: {tf variable name: array} (None -> the reference's initialisers, seeded).
+        phong: None, or dict(light_dir[1|B,3], light_col, ambient, k_diffuse) to fuse the demo's
+        Phong composite + uint8 quantisation after the network."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("RenderEngine needs a CUDA device (no CPU fallback)")
+        self.B, self.size, self.new_size = batch, size, new_size
+        self.is_greyscale = is_greyscale
+        self.device = device
+        tf.reset_default_graph(seed)
+        if weights is not None:
+            tf.load_weight_dict(weights)
+        self.vox = torch.zeros((batch, size, size, size, 1), device=device, dtype=torch.float32)
+        self.minv = torch.zeros((batch, 3, 4), device=device, dtype=torch.float32)
+        self.vox_host = torch.zeros(self.vox.shape, dtype=torch.float32).pin_memory()
+        self.minv_host = torch.zeros(self.minv.shape, dtype=torch.float32).pin_memory()
+        self.phong = phong
+        if phong is not None:
+            self.light_dir = torch.as_tensor(np.asarray(phong["light_dir"], np.float32)).reshape(-1, 3).to(device)
+            self.light_col = torch.as_tensor(np.asarray(phong["light_col"], np.float32)).reshape(-1, 3).to(device)
+        self.graph = None
+        self.out = None
+        self.out_u8 = None
+        self.launches_per_step = None
+        # warm-up (packs weights, sets kernel attributes, sizes the allocator), then capture
+        self._forward()
+        torch.cuda.synchronize()
+        if use_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._forward()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._forward()
+            torch.cuda.synchronize()
+        out_shape = tuple(self.out.shape)
+        self.out_host = torch.zeros(out_shape, dtype=torch.float32).pin_memory()
+        self.out_u8_host = torch.zeros(out_shape, dtype=torch.uint8).pin_memory() if phong is not None else None
+
+    # -------------------------------------------------------------------------------------------
+    def _forward(self):
+        grid = ops.resample(self.vox, self.minv, self.new_size, True)
+        img = RenderNet(grid, is_training=False, is_greyscale=self.is_greyscale)
+        if self.phong is not None:
+            shaded, u8 = ops.phong_composite(img, self.light_dir, self.light_col, self.phong["ambient"],
+                                             self.phong["k_diffuse"], want_u8=True)
+            self.out, self.out_u8 = shaded, u8
+        else:
+            self.out = img
+        return self.out
+
+    @staticmethod
+    def pose_to_matrix(view_params, size=64, new_size=128) -> np.ndarray:
+        """[B,3] (azimuth, elevation-param, scale) -> [B,3,4] fp32 inverse sampling matrices (host)."""
+        R, S = tf_rotation_around_grid_centroid(np.asarray(view_params, np.float32))
+        return inverse_sampling_matrix(R, S, size, new_size)
+
+    def step_device(self):
+        """One pass over the inputs already resident in self.vox / self.minv."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._forward()
+        return self.out
+
+    def upload(self, voxels, view_params, non_blocking=True):
+        v = torch.as_tensor(np.asarray(voxels, np.float32)) if not isinstance(voxels, torch.Tensor) else voxels
+        self.vox_host.copy_(v.reshape(self.vox_host.shape))
+        self.minv_host.copy_(torch.from_numpy(self.pose_to_matrix(view_params, self.size, self.new_size)))
+        self.vox.copy_(self.vox_host, non_blocking=non_blocking)
+        self.minv.copy_(self.minv_host, non_blocking=non_blocking)
+
+    def render(self, voxels, view_params, to_host: bool = True):
+        """voxels [B,64,64,64,1] float32 (host), view_params [B,3] -> image [B,512,512,3|1] float32
+        (and uint8 Phong image when configured).  Includes H2D and D2H."""
+        self.upload(voxels, view_params)
+        self.step_device()
+        if not to_host:
+            return self.out if self.phong is None else (self.out, self.out_u8)
+        self.out_host.copy_(self.out, non_blocking=True)
+        if self.phong is not None:
+            self.out_u8_host.copy_(self.out_u8, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.out_host if self.phong is None else (self.out_host, self.out_u8_host)

@@ -1,0 +1,344 @@
+"""Drop-in mirror of the reference's tools/layer_util.py (same function names, argument order, defaults and
+variable-scope naming), executing on the sm_100a kernels.  Citations are into /root/reference.
+
+Differences that are deliberate and documented:
+  * tensors are torch CUDA tensors (16-bit activations, fp32 accumulation) instead of tf.Tensor;
+  * state lives in `tfcompat`'s variable store (names identical to the TF graph's variables);
+  * conv ops return deferred tensors so the following prelu / tf.add / sigmoid fuse into the conv epilogue;
+  * the per-layer `print(...)` calls of the reference (layer_util.py:157-181) are dropped.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from . import tfcompat as tf
+from .tfcompat import Deferred, realize
+
+_XAVIER = tf.xavier_initializer
+_RANDN002 = lambda: tf.random_normal_initializer(stddev=0.02)  # noqa: E731  (layer_util.py:149 default)
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def _store():
+    return tf.get_store()
+
+
+def _packed(wvar: torch.Tensor, bvar: Optional[torch.Tensor], kind: str, stride: int = 1):
+    st = _store()
+    key = (getattr(wvar, "_rn_name", id(wvar)), kind, stride, tf.COMPUTE_DTYPE)
+    L = st.packed.get(key)
+    if L is None:
+        L = ops.pack_conv(kind, wvar, bvar, None, stride=stride, dtype=tf.COMPUTE_DTYPE, device=st.device)
+        st.packed[key] = L
+    return L
+
+
+def _dev_vec(v, n_pad: Optional[int] = None) -> torch.Tensor:
+    """fp32 device copy (zero padded to n_pad) of a small per-channel variable, cached."""
+    st = _store()
+    key = ("vec", getattr(v, "_rn_name", id(v)), n_pad)
+    d = st.packed.get(key)
+    if d is None:
+        t = torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v, dtype=torch.float32).reshape(-1)
+        n = t.numel()
+        d = torch.zeros(n_pad or n, device=st.device, dtype=torch.float32)
+        d[:n] = t.to(st.device)
+        st.packed[key] = d
+    return d
+
+
+def _as16(x: torch.Tensor) -> torch.Tensor:
+    x = realize(x)
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(np.asarray(x))
+    if not x.is_cuda:
+        x = x.to(_store().device)
+    if x.dtype == torch.float32:
+        return ops.cast_to_16(x.contiguous(), tf.COMPUTE_DTYPE)
+    return x
+
+
+def _alpha_arg(alpha, cout_pad):
+    if alpha is None:
+        return None
+    if isinstance(alpha, str) and alpha == "zeros":
+        return torch.zeros(cout_pad, device=_store().device, dtype=torch.float32)
+    return _dev_vec(alpha, cout_pad)
+
+
+# ------------------------------------------------------------------------------------------ reference API
+def projection_unit(input, n_features=18, scope='projection_unit'):
+    """layer_util.py:8-22.  [B,H,W,D,C] -> reshape [B,H,W,D*C] (free in channel-last) -> 1x1 conv -> PReLU.
+    `n_features` is overwritten exactly like the reference does (:19)."""
+    x = realize(input)
+    B, H, W, D, Cc = x.shape
+    with tf.variable_scope(scope):
+        n_features = D * Cc
+        x = x.reshape(B, H, W, n_features)
+        conv = prelu(slim_conv2d(inputs=x, num_outputs=n_features, kernel_size=1, activation_fn=None))
+        return conv
+
+
+def lrelu(x, leak=0.2, name="lrelu"):
+    """layer_util.py:24-25 (dead code in the reference; kept for API completeness)."""
+    x = realize(x)
+    a = torch.full((x.shape[-1],), float(leak), dtype=torch.float32)
+    return ops.bias_act(_as16(x), None, a.to(x.device), "prelu")
+
+
+def prelu(x, trainable=True, alpha=None):
+    """layer_util.py:27-45: max(0,x) + alpha*min(0,x); `alpha` variable of shape [channels], init 0."""
+    nch = x.shape[-1]
+    if alpha is None:
+        alpha = tf.get_variable(name='alpha', shape=[nch], dtype=tf.float32,
+                                initializer=tf.constant_initializer(0.0), trainable=trainable)
+    else:
+        alpha = tf.get_variable(name='alpha', initializer=alpha, dtype=tf.float32, trainable=trainable)
+    if isinstance(x, Deferred) and x.open and x.act is None and x.residual is None:
+        x.act, x.alpha = "prelu", alpha
+        return x
+    return ops.bias_act(_as16(x), None, _dev_vec(alpha), "prelu")
+
+
+def get_weight(weight_name, weight_dict):
+    """layer_util.py:47-58."""
+    if weight_dict is None:
+        return None
+    return weight_dict.get(weight_name)
+
+
+def res_block_3d(input, out_channels=64, scope='res_block', kernel=[3, 3, 3], stride=[1, 1, 1], weight_dict=None,
+                 trainable=True):
+    """layer_util.py:60-88: x + conv2(prelu(conv1(x))) (ReLU instead of PReLU when weight_dict is given, :76)."""
+    if weight_dict is None:
+        with tf.variable_scope(scope):
+            net = prelu(conv3d(input, out_channels, kernel_size=kernel, stride=stride, pad="SAME", scope="con1_3X3",
+                               weight_initializer_type=_XAVIER()))
+            net = conv3d(net, out_channels, kernel_size=kernel, stride=stride, pad="SAME", scope="conv2_3x3",
+                         weight_initializer_type=_XAVIER())
+        return tf.add(tf.cast(net, tf.float32), tf.cast(input, tf.float32))
+    with tf.variable_scope(scope):
+        net = tf.nn.relu(conv3d(input, out_channels, kernel_size=kernel, stride=stride, pad="SAME", scope="con1_3X3",
+                                trainable=trainable,
+                                weight_initializer=get_weight(scope + '_con1_3X3_weights', weight_dict),
+                                bias_initializer=get_weight(scope + '_con1_3X3_biases', weight_dict),
+                                weight_initializer_type=_XAVIER()))
+        net = conv3d(net, out_channels, kernel_size=kernel, stride=stride, pad="SAME", scope="conv2_3x3",
+                     trainable=trainable,
+                     weight_initializer=get_weight(scope + '_conv2_3x3_weights', weight_dict),
+                     bias_initializer=get_weight(scope + '_conv2_3x3_biases', weight_dict),
+                     weight_initializer_type=_XAVIER())
+    return tf.add(tf.cast(net, tf.float32), tf.cast(input, tf.float32))
+
+
+def res_block_2d(input, out_channels=64, scope='res_block', kernel=[3, 3], stride=[1, 1], weight_dict=None,
+                 trainable=True):
+    """layer_util.py:91-121."""
+    if weight_dict is None:
+        with tf.variable_scope(scope):
+            net = prelu(slim_conv2d(input, out_channels, kernel_size=kernel, stride=stride, activation_fn=None,
+                                    scope="con1_3X3"))
+            net = slim_conv2d(net, num_outputs=out_channels, kernel_size=kernel, stride=stride, activation_fn=None,
+                              scope="conv2_3x3")
+        return tf.add(tf.cast(net, tf.float32), tf.cast(input, tf.float32))
+    with tf.variable_scope(scope):
+        net = tf.nn.relu(conv2d(input, out_channels, kernel_size=kernel, stride=stride, pad="SAME", scope="con1_3X3",
+                                trainable=trainable,
+                                weight_initializer=get_weight(scope + '_con1_3X3_weights', weight_dict),
+                                bias_initializer=get_weight(scope + '_con1_3X3_biases', weight_dict),
+                                weight_initializer_type=_XAVIER()))
+        net = conv2d(net, out_channels, kernel_size=kernel, stride=stride, pad="SAME", scope="conv2_3x3",
+                     trainable=trainable,
+                     weight_initializer=get_weight(scope + '_conv2_3x3_weights', weight_dict),
+                     bias_initializer=get_weight(scope + '_conv2_3x3_biases', weight_dict),
+                     weight_initializer_type=_XAVIER())
+    return tf.add(tf.cast(net, tf.float32), tf.cast(input, tf.float32))
+
+
+def keep_prob(dropout, train):
+    """layer_util.py:124-131: dropout keep-probability, 1.0 at inference."""
+    return tf.cond(train, lambda: float(dropout), lambda: 1.0)
+
+
+def bias_variable(shape, bias_initializer=None, trainable=True):
+    """layer_util.py:133-144: `biases`, constant 0.001 unless an initial value is given."""
+    if bias_initializer is None:
+        return tf.get_variable(name='biases', shape=shape, initializer=tf.constant_initializer(0.001),
+                               trainable=trainable)
+    return tf.get_variable(name='biases', initializer=bias_initializer, trainable=trainable)
+
+
+def _weights_var(shape, weight_initializer, weight_initializer_type, trainable):
+    if weight_initializer is None:
+        return tf.get_variable(name='weights', shape=shape, initializer=weight_initializer_type or _RANDN002(),
+                               dtype=tf.float32, trainable=trainable)
+    return tf.get_variable(name='weights', initializer=weight_initializer, dtype=tf.float32, trainable=trainable)
+
+
+def _check_same(pad):
+    if pad != 'SAME':
+        raise NotImplementedError("rendernet_b200 implements TF 'SAME' padding (all the reference ever uses)")
+
+
+def conv2d(input_, num_outputs, kernel_size=[4, 4], stride=[1, 1], pad='SAME', if_bias=True, trainable=True,
+           reuse=False, scope='conv2d', weight_initializer=None, bias_initializer=None,
+           weight_initializer_type=None):
+    """layer_util.py:147-184: tf.nn.conv2d SAME + `biases`.  Returns a deferred tensor."""
+    _check_same(pad)
+    if list(stride) != [1, 1]:
+        raise NotImplementedError("conv2d stride != 1 is not on the hot path")
+    cin = int(input_.shape[-1])
+    with tf.variable_scope(scope, reuse=reuse):
+        w = _weights_var(list(kernel_size) + [cin, int(num_outputs)], weight_initializer, weight_initializer_type,
+                         trainable)
+        b = None
+        if if_bias:
+            b = bias_variable([int(num_outputs)], trainable=trainable, bias_initializer=bias_initializer)
+    return _deferred_conv("conv2d", input_, w, b, 1)
+
+
+def conv2d_transpose(x, num_outputs, kernel_size=(4, 4), stride=(1, 1), pad='SAME', if_bias=True, reuse=False,
+                     scope="conv2d_transpose", trainable=True, weight_initializer=None, bias_initializer=None,
+                     weight_initializer_type=None):
+    """layer_util.py:186-226: tf.nn.conv2d_transpose SAME, output = input*stride, filter [kh,kw,Cout,Cin]."""
+    _check_same(pad)
+    if stride[0] != stride[1]:
+        raise NotImplementedError("anisotropic transposed-conv strides are not on the hot path")
+    cin = int(x.shape[-1])
+    with tf.variable_scope(scope, reuse=reuse):
+        w = _weights_var(list(kernel_size) + [int(num_outputs), cin], weight_initializer, weight_initializer_type,
+                         trainable)
+        b = None
+        if if_bias:
+            b = bias_variable([int(num_outputs)], trainable=trainable, bias_initializer=bias_initializer)
+    return _deferred_conv("conv2d_transpose", x, w, b, int(stride[0]))
+
+
+def conv3d(input_, num_outputs, pad="SAME", reuse=False, kernel_size=[4, 4, 4], stride=[2, 2, 2], if_bias=True,
+           trainable=True, scope="conv3d", weight_initializer=None, bias_initializer=None,
+           weight_initializer_type=None):
+    """layer_util.py:228-265: tf.nn.conv3d SAME + `biases`.
+    Cin % 16 == 0 and stride 1 -> tensor-core implicit GEMM; the thin strided first layers (e_conv1: Cin 1,
+    5^3 s2; e_conv2: Cin 8, 3^3 s(1,1,2)) -> CUDA-core direct kernel."""
+    _check_same(pad)
+    cin = int(input_.shape[-1])
+    with tf.variable_scope(scope, reuse=reuse):
+        w = _weights_var(list(kernel_size) + [cin, int(num_outputs)], weight_initializer, weight_initializer_type,
+                         trainable)
+        b = None
+        if if_bias:
+            b = bias_variable([int(num_outputs)], trainable=trainable, bias_initializer=bias_initializer)
+    if list(stride) == [1, 1, 1] and cin % 16 == 0:
+        return _deferred_conv("conv3d", input_, w, b, 1)
+    return _deferred_direct3d(input_, w, b, list(stride))
+
+
+def conv3d_transpose(x, num_output, kernel_size=(4, 4), stride=(1, 1), pad='SAME', if_bias=True, reuse=False,
+                     scope="conv3d_transpose", trainable=True, weight_initializer=None, bias_initializer=None,
+                     weight_initializer_type=None):
+    """layer_util.py:269-309 (texture decoder only, BASELINE config 4)."""
+    raise NotImplementedError("conv3d_transpose (texture decoder) is scheduled after the Shader path; see DESIGN.md")
+
+
+def fully_connected(input_, output_size, reuse=False, scope='fully_connected', if_bias=True, weight_initializer=None,
+                    bias_initializer=None, trainable=True, weight_initializer_type=None):
+    """layer_util.py:311-343 (texture decoder only, BASELINE config 4)."""
+    raise NotImplementedError("fully_connected (texture decoder) is scheduled after the Shader path; see DESIGN.md")
+
+
+# ------------------------------------------------------------------------------------------ slim look-alikes
+def slim_conv2d(inputs, num_outputs, kernel_size, stride=1, padding='SAME', activation_fn=None, scope=None, **_):
+    """slim.conv2d as the reference calls it (activation_fn=None, SAME, xavier weights, zero `biases`;
+    default scope 'Conv', layer_util.py:21,101-104; RenderNet_Shader.py:83,87,98,102)."""
+    _check_same(padding)
+    if activation_fn is not None:
+        raise NotImplementedError("the reference always passes activation_fn=None")
+    ks = [kernel_size] * 2 if isinstance(kernel_size, int) else list(kernel_size)
+    st = [stride] * 2 if isinstance(stride, int) else list(stride)
+    if st != [1, 1]:
+        raise NotImplementedError("slim.conv2d stride != 1 is not on the hot path")
+    cin = int(inputs.shape[-1])
+    with tf.variable_scope(scope or 'Conv'):
+        w = tf.get_variable('weights', ks + [cin, int(num_outputs)], initializer=_XAVIER())
+        b = tf.get_variable('biases', [int(num_outputs)], initializer=tf.constant_initializer(0.0))
+    return _deferred_conv("conv2d", inputs, w, b, 1)
+
+
+def slim_conv2d_transpose(inputs, num_outputs, kernel_size, stride=1, padding='SAME', activation_fn=None,
+                          scope=None, **_):
+    """slim.conv2d_transpose (RenderNet_Shader.py:106-129); default scope 'Conv2d_transpose'."""
+    _check_same(padding)
+    if activation_fn is not None:
+        raise NotImplementedError("the reference always passes activation_fn=None")
+    ks = [kernel_size] * 2 if isinstance(kernel_size, int) else list(kernel_size)
+    st = [stride] * 2 if isinstance(stride, int) else list(stride)
+    cin = int(inputs.shape[-1])
+    with tf.variable_scope(scope or 'Conv2d_transpose'):
+        w = tf.get_variable('weights', ks + [int(num_outputs), cin], initializer=_XAVIER())
+        b = tf.get_variable('biases', [int(num_outputs)], initializer=tf.constant_initializer(0.0))
+    return _deferred_conv("conv2d_transpose", inputs, w, b, int(st[0]))
+
+
+class _Slim:
+    conv2d = staticmethod(slim_conv2d)
+    conv2d_transpose = staticmethod(slim_conv2d_transpose)
+
+
+slim = _Slim()
+
+
+# ------------------------------------------------------------------------------------------ deferred execution
+def _deferred_conv(kind, x, w, b, stride):
+    xin = x
+    if kind == "conv2d_transpose":
+        oshape = (x.shape[0], x.shape[1] * stride, x.shape[2] * stride, w.shape[-2])
+    else:
+        oshape = tuple(x.shape[:-1]) + (w.shape[-1],)
+
+    def run(act, alpha, residual, want32):
+        xt = _as16(xin)
+        L = _packed(w, b, kind, stride)
+        a = _alpha_arg(alpha, L.cout_pad)
+        want16 = not want32
+        if kind == "conv2d":
+            return ops.conv2d(xt, L, act=act, residual=residual, want16=want16, want32=want32, alpha=a)
+        if kind == "conv3d":
+            return ops.conv3d(xt, L, act=act, residual=residual, want16=want16, want32=want32, alpha=a)
+        if residual is not None:
+            y = ops.conv2d_transpose(xt, L, act=act, alpha=a)
+            return ops.bias_act(y, None, None, None, residual=residual, want32=want32)
+        return ops.conv2d_transpose(xt, L, act=act, want16=want16, want32=want32, alpha=a)
+
+    return Deferred(run, oshape, tf.COMPUTE_DTYPE)
+
+
+def _deferred_direct3d(x, w, b, stride):
+    xin = x
+    oshape = (x.shape[0], -(-x.shape[1] // stride[0]), -(-x.shape[2] // stride[1]), -(-x.shape[3] // stride[2]),
+              w.shape[-1])
+
+    def run(act, alpha, residual, want32):
+        xt = realize(xin)
+        if not xt.is_cuda:
+            xt = xt.to(_store().device)
+        cout = w.shape[-1]
+        wd = _store().packed.get(("w32", w._rn_name))
+        if wd is None:
+            wd = w.to(_store().device).contiguous()
+            _store().packed[("w32", w._rn_name)] = wd
+        bd = _dev_vec(b) if b is not None else torch.zeros(cout, device=xt.device, dtype=torch.float32)
+        if act == "prelu":
+            ad = _alpha_arg(alpha, cout)
+            y = ops.conv3d_direct(xt.contiguous(), wd, bd, ad, stride, tf.COMPUTE_DTYPE)
+            act = None
+        else:
+            y = ops.conv3d_direct(xt.contiguous(), wd, bd, None, stride, tf.COMPUTE_DTYPE)
+        if act is not None or residual is not None or want32:
+            return ops.bias_act(y, None, None, act, residual=residual, want32=want32)
+        return y
+
+    return Deferred(run, oshape, tf.COMPUTE_DTYPE)

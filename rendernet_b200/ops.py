@@ -124,7 +124,7 @@ def _out_buffers(shape, dtype, device, want16, want32, out16, out32):
 
 
 def conv2d(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, residual: Optional[torch.Tensor] = None,
-           want16: bool = True, want32: bool = False, out16=None, out32=None):
+           want16: bool = True, want32: bool = False, out16=None, out32=None, alpha=None):
     """SAME stride-1 conv2d + bias (+PReLU/sigmoid) (+residual).  x [B,H,W,Cin] 16-bit."""
     x = _cuda(x, L.dtype)
     B, H, W, Cin = x.shape
@@ -137,14 +137,14 @@ def conv2d(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, residual: 
         assert tuple(residual.shape) == (B, H, W, L.cout)
     a = _ACT[act]
     check(lib.rn_conv2d_same(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(),
-                             _ptr(L.alpha) if a == ACT_PRELU else None, a, _ptr(residual), res_f32,
+                             _ptr(alpha if alpha is not None else L.alpha) if a == ACT_PRELU else None, a, _ptr(residual), res_f32,
                              _ptr(out16), _ptr(out32), B, H, W, Cin, L.cout, L.cout_pad, L.ksize[0], L.ksize[1],
                              fmt_of(L.dtype), _stream()), "rn_conv2d_same")
     return out16 if not want32 else ((out16, out32) if want16 else out32)
 
 
 def conv3d(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, residual: Optional[torch.Tensor] = None,
-           want16: bool = True, want32: bool = False, out16=None, out32=None):
+           want16: bool = True, want32: bool = False, out16=None, out32=None, alpha=None):
     """SAME stride-1 k^3 conv3d on the tensor pipe.  x [B,H,W,D,Cin] 16-bit."""
     x = _cuda(x, L.dtype)
     B, H, W, D, Cin = x.shape
@@ -156,14 +156,14 @@ def conv3d(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, residual: 
         res_f32 = 1 if residual.dtype == torch.float32 else 0
     a = _ACT[act]
     check(lib.rn_conv3d_same(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(),
-                             _ptr(L.alpha) if a == ACT_PRELU else None, a, _ptr(residual), res_f32,
+                             _ptr(alpha if alpha is not None else L.alpha) if a == ACT_PRELU else None, a, _ptr(residual), res_f32,
                              _ptr(out16), _ptr(out32), B, H, W, D, Cin, L.cout, L.cout_pad, L.ksize[0],
                              fmt_of(L.dtype), _stream()), "rn_conv3d_same")
     return out16 if not want32 else ((out16, out32) if want16 else out32)
 
 
 def conv2d_transpose(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, want16: bool = True,
-                     want32: bool = False, out16=None, out32=None):
+                     want32: bool = False, out16=None, out32=None, alpha=None):
     """SAME transposed conv, out = in*stride.  x [B,H,W,Cin] 16-bit."""
     x = _cuda(x, L.dtype)
     B, H, W, Cin = x.shape
@@ -172,7 +172,7 @@ def conv2d_transpose(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, 
     out16, out32 = _out_buffers((B, H * s, W * s, L.cout), L.dtype, x.device, want16, want32, out16, out32)
     a = _ACT[act]
     check(lib.rn_conv2d_transpose_same(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(),
-                                       _ptr(L.alpha) if a == ACT_PRELU else None, a, _ptr(out16), _ptr(out32),
+                                       _ptr(alpha if alpha is not None else L.alpha) if a == ACT_PRELU else None, a, _ptr(out16), _ptr(out32),
                                        B, H, W, Cin, L.cout, L.cout_pad, L.ksize[0], L.ksize[1], s,
                                        fmt_of(L.dtype), _stream()), "rn_conv2d_transpose_same")
     return out16 if not want32 else ((out16, out32) if want16 else out32)

@@ -1,0 +1,122 @@
+"""Drop-in mirror of the `tf_*` half of the reference's tools/resampling_voxel_grid.py (:370-632): rotate a
+voxel grid into the camera frame by inverse-mapped trilinear resampling.  The ~60 TF ops of
+tf_resampling + tf_interpolate + tf_voxel_meshgrid collapse into ONE gather kernel (rn_resample_f32) that
+also applies tools/model_util.py:41-49's axis transform when that call follows.
+
+Pose -> matrix arithmetic ([B,4,4] fp32, a few hundred flops) stays on the host in NumPy float32, in the
+reference's own operation order (:529-602), so the kernel and the oracle sample at identical coordinates.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _np32(x) -> np.ndarray:
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    return np.asarray(x, dtype=np.float32)
+
+
+def tf_rotation_around_grid_centroid(view_params):
+    """:515-562.  view_params [B,3] = (azimuth rad, elevation-param rad, scale) -> (R [B,4,4], S [B,4,4]).
+    The reference's `== 2` test (:551) is always False in TF1, so the 3-parameter branch always runs."""
+    vp = _np32(view_params)
+    B = vp.shape[0]
+    az = vp[:, 0] - np.float32(math.pi * 0.5)
+    el = vp[:, 1]
+    ca, sa, ce, se = np.cos(az), np.sin(az), np.cos(el), np.sin(el)
+    rot_y = np.zeros((B, 4, 4), np.float32)
+    rot_y[:, 0, 0], rot_y[:, 0, 2] = ca, -sa
+    rot_y[:, 1, 1] = 1
+    rot_y[:, 2, 0], rot_y[:, 2, 2] = sa, ca
+    rot_y[:, 3, 3] = 1
+    rot_z = np.zeros((B, 4, 4), np.float32)
+    rot_z[:, 0, 0], rot_z[:, 0, 1] = ce, se
+    rot_z[:, 1, 0], rot_z[:, 1, 1] = -se, ce
+    rot_z[:, 2, 2] = 1
+    rot_z[:, 3, 3] = 1
+    R = np.matmul(rot_z, rot_y)
+    if vp.shape[1] == 2:
+        return R
+    S = np.zeros((B, 4, 4), np.float32)
+    S[:, 0, 0] = S[:, 1, 1] = S[:, 2, 2] = vp[:, 2]
+    S[:, 3, 3] = 1
+    return R, S
+
+
+def inverse_sampling_matrix(transformation_matrix, Scale_matrix=None, size=64, new_size=128) -> np.ndarray:
+    """:579-602: M = T(+new/2).S.R.T(-size/2);  returns inverse(M)[:, :3, :] as fp32 [B,3,4]."""
+    R = _np32(transformation_matrix)
+    B = R.shape[0]
+    T = np.array([[1, 0, 0, -size * 0.5], [0, 1, 0, -size * 0.5], [0, 0, 1, -size * 0.5], [0, 0, 0, 1]], np.float32)
+    Tn = np.array([[1, 0, 0, new_size * 0.5], [0, 1, 0, new_size * 0.5], [0, 0, 1, new_size * 0.5], [0, 0, 0, 1]],
+                  np.float32)
+    T = np.tile(T[None], (B, 1, 1))
+    Tn = np.tile(Tn[None], (B, 1, 1))
+    if Scale_matrix is None:
+        M = np.matmul(np.matmul(Tn, R), T)
+    else:
+        M = np.matmul(np.matmul(np.matmul(Tn, _np32(Scale_matrix)), R), T)
+    return np.ascontiguousarray(np.linalg.inv(M).astype(np.float32)[:, 0:3, :])
+
+
+class ResampledGrid:
+    """Deferred result of tf_resampling so that a following tf_transform_voxel_to_match_image is fused."""
+
+    def __init__(self, voxel: torch.Tensor, minv: torch.Tensor, new_size: int):
+        self.voxel, self.minv, self.new_size = voxel, minv, new_size
+        B, _, _, _, C = voxel.shape
+        self.shape = (B, new_size, new_size, new_size, C)
+        self._value = None
+
+    def realize(self, transform: bool = False) -> torch.Tensor:
+        if transform:
+            return ops.resample(self.voxel, self.minv, self.new_size, True)
+        if self._value is None:
+            self._value = ops.resample(self.voxel, self.minv, self.new_size, False)
+        return self._value
+
+    def get_shape(self):
+        return list(self.shape)
+
+
+def _to_cuda_f32(x) -> torch.Tensor:
+    if not isinstance(x, torch.Tensor):
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32)))
+    return x.to(device="cuda", dtype=torch.float32).contiguous()
+
+
+def tf_resampling(voxel_array, transformation_matrix, params=None, Scale_matrix=None, size=64, new_size=128):
+    """:564-614.  `params` is vestigial in the reference (never read) and therefore optional here; the
+    shipped tf_rotation_resampling omits it and would raise TypeError (SURVEY finding 4)."""
+    minv = inverse_sampling_matrix(transformation_matrix, Scale_matrix, size, new_size)
+    return ResampledGrid(_to_cuda_f32(voxel_array), torch.from_numpy(minv).cuda(), new_size)
+
+
+def tf_rotation_resampling(voxel_array, view_params, size=64, new_size=128):
+    """:616-632."""
+    vp = _np32(view_params)
+    if vp.shape[1] == 2:
+        M = tf_rotation_around_grid_centroid(vp)
+        return tf_resampling(voxel_array, M, size=size, new_size=new_size)
+    M, S = tf_rotation_around_grid_centroid(vp)
+    return tf_resampling(voxel_array, M, Scale_matrix=S, size=size, new_size=new_size)
+
+
+tf_rotation_translation_resampling = tf_rotation_resampling   # :634-650 is a verbatim duplicate upstream
+
+
+def tf_voxel_meshgrid(height, width, depth, homogeneous=False):
+    """:488-513: rows (x=k, y=j, z=i[, 1]) for flat index n = i*H*W + j*W + k (host NumPy; the kernel
+    generates these coordinates on the fly and never materialises the grid)."""
+    z_t, y_t, x_t = np.meshgrid(np.arange(depth, dtype=np.float32), np.arange(height, dtype=np.float32),
+                                np.arange(width, dtype=np.float32), indexing='ij')
+    rows = [x_t.reshape(1, -1), y_t.reshape(1, -1), z_t.reshape(1, -1)]
+    if homogeneous:
+        rows.append(np.ones_like(rows[0]))
+    return np.concatenate(rows, axis=0)
