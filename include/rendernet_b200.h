@@ -82,6 +82,10 @@ typedef struct rn_conv_desc {
   long long o_base, o_b, o_y, o_x, o_z;
   int fmt;                  /* 0 fp16, 1 bf16 */
   int force_bn, force_kps, max_ctas; /* 0 = auto (tuning / tests) */
+  /* depth-folded ("banded") conv3d: x is [B,H,W,x_channels] with x_channels = D*C, Cin = K elements read per
+   * tap starting at channel a_c_base + n_tile*a_c_ntile (may run out of range: zero filled), and w_packed is one
+   * banded filter [ntaps*Cin/KB][force_bn][KB] shared by all N tiles.  All zero for ordinary convolutions. */
+  int x_channels, a_c_base, a_c_ntile, w_banded;
 } rn_conv_desc;
 int rn_conv_igemm(const rn_conv_desc* d, void* stream);
 
@@ -94,6 +98,20 @@ int rn_conv2d_same(const void* x, const void* w_packed, const float* bias, const
 int rn_conv3d_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
                    const void* residual, int residual_is_f32, void* out16, float* out32, int B, int H, int W,
                    int D, int Cin, int Cout, int cout_pad, int k, int fmt, void* stream);
+/* layer_util.conv3d 3^3 SAME stride 1 (res_block_3d, tools/layer_util.py:60-88; RenderNet_Shader.py:45-64) as a
+ * depth-folded 2-D convolution: the D axis is part of the GEMM's N (128 = (128/Cout) output depths x Cout) and K
+ * ((128/Cout + 2) input depths x Cin, padded to 64-element blocks), so TMA moves full 128-byte rows and each
+ * activation byte is fetched from L2 9x instead of 27x.  w_banded from rn_pack_conv3d_banded
+ * ([9][kblocks][128][64] 16-bit, bytes = rn_conv3d_banded_bytes); bias/alpha are per Cout (length Cout) and are
+ * expanded over depth internally via bias_full/alpha_full scratch [D*Cout] fp32 supplied by the caller
+ * (fill them with rn_expand_channels).  x, residual, out: [B,H,W,D,C*] 16-bit. */
+long long rn_conv3d_banded_bytes(int Cin, int Cout);
+int rn_pack_conv3d_banded(const float* w, void* packed, int Cin, int Cout, int fmt, void* stream);
+int rn_expand_channels(const float* v, float* v_full, int C, int D, void* stream);
+int rn_conv3d_banded_same(const void* x, const void* w_banded, const float* bias_full, const float* alpha_full,
+                          int act, const void* residual, int residual_is_f32, void* out16, float* out32, int B,
+                          int H, int W, int D, int Cin, int Cout, int fmt, void* stream);
+
 /* slim.conv2d_transpose / layer_util.conv2d_transpose (layer_util.py:186; RenderNet_Shader.py:106-129),
  * SAME, out = in*stride.  w_packed holds the stride^2 phase filters back to back, as produced by
  * rn_pack_conv2d_transpose_weights: [phase = ay*s+ax][taps_of_phase][cout_pad][Cin]. */

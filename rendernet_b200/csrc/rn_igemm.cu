@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile, BN);
+        const int a_c0 = p.a_c_base + (t.n0 / BN) * p.a_c_ntile;
         for (int it = 0; it < total_k;) {
           const int n_here = min(p.kps, total_k - it);
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -206,9 +207,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             uint8_t* a_dst = sbase + j * sub_bytes;
             uint8_t* b_dst = a_dst + p.a_sub_bytes;
             const int cx = t.x0 + p.tap[tap][0], cy = t.y0 + p.tap[tap][1], cz = t.z0 + p.tap[tap][2];
-            if (p.rank == 4) tma_load_4d(a_dst, &p.tmA, &full_bar[stage], kb * kb_elems, cx, cy, t.b);
-            else tma_load_5d(a_dst, &p.tmA, &full_bar[stage], kb * kb_elems, cz, cx, cy, t.b);
-            tma_load_3d(b_dst, &p.tmB, &full_bar[stage], kb * kb_elems, t.n0, tap);
+            const int ac = a_c0 + kb * kb_elems;
+            if (p.rank == 4) tma_load_4d(a_dst, &p.tmA, &full_bar[stage], ac, cx, cy, t.b);
+            else tma_load_5d(a_dst, &p.tmA, &full_bar[stage], ac, cz, cx, cy, t.b);
+            if (p.b_banded) tma_load_3d(b_dst, &p.tmB, &full_bar[stage], 0, 0, kit);
+            else tma_load_3d(b_dst, &p.tmB, &full_bar[stage], kb * kb_elems, t.n0, tap);
           }
           it += n_here;
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -403,24 +406,31 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   const CUtensorMapDataType dt = d->fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r;
+  const cuuint64_t Cx = d->x_channels > 0 ? d->x_channels : d->Cin;  // channel extent of x (>= K per tap)
+  if (Cx % 8 != 0) return -11;
+  p.a_c_base = d->a_c_base; p.a_c_ntile = d->a_c_ntile; p.b_banded = d->w_banded;
+  if (d->w_banded && (d->force_bn <= 0)) return -12;
   if (p.rank == 4) {
-    const cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
-    const cuuint64_t strides[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * d->W,
-                                   (cuuint64_t)d->Cin * 2 * d->W * d->H};
+    const cuuint64_t dims[4] = {Cx, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    const cuuint64_t strides[3] = {Cx * 2, Cx * 2 * d->W, Cx * 2 * d->W * d->H};
     const cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
     r = enc(&p.tmA, dt, 4, const_cast<void*>(d->x), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
-    const cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)D, (cuuint64_t)d->W, (cuuint64_t)d->H,
-                                (cuuint64_t)d->B};
-    const cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * D,
-                                   (cuuint64_t)d->Cin * 2 * D * d->W, (cuuint64_t)d->Cin * 2 * D * d->W * d->H};
+    const cuuint64_t dims[5] = {Cx, (cuuint64_t)D, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    const cuuint64_t strides[4] = {Cx * 2, Cx * 2 * D, Cx * 2 * D * d->W, Cx * 2 * D * d->W * d->H};
     const cuuint32_t box[5] = {(cuuint32_t)KB, (cuuint32_t)p.BD, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
     r = enc(&p.tmA, dt, 5, const_cast<void*>(d->x), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) return 1000 + static_cast<int>(r);
-  {
+  if (d->w_banded) {  // [ntaps*kblocks][BN][KB], identical for every N tile
+    const cuuint64_t dims[3] = {(cuuint64_t)KB, (cuuint64_t)BN, (cuuint64_t)d->ntaps * p.kblocks};
+    const cuuint64_t strides[2] = {(cuuint64_t)KB * 2, (cuuint64_t)KB * 2 * BN};
+    const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)BN, 1};
+    r = enc(&p.tmB, dt, 3, const_cast<void*>(d->w_packed), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
     const cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->cout_pad, (cuuint64_t)d->ntaps};
     const cuuint64_t strides[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * d->cout_pad};
     const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)BN, 1};

@@ -145,6 +145,33 @@ __global__ void cast_16_to_f32_kernel(const uint16_t* __restrict__ s, float* __r
 }
 
 
+
+// ------------------------------------------------------------------------------------------ banded conv3d filter
+// Wb[tap=(ky,kx)][kb][n = zo_l*Cout + co][k = zi_l*Cin + ci],  zi = z0 - 1 + kb*(64/Cin) + zi_l, zo = z0 + zo_l
+// -> w[ky][kx][zi - zo + 1][ci][co] when |zi - zo| <= 1, else 0.   (BN = 128, KB = 64)
+__global__ void pack_banded_kernel(const float* __restrict__ w, uint16_t* __restrict__ packed, int Cin, int Cout,
+                                   int kblocks, int fmt) {
+  const long long total = 9LL * kblocks * 128 * 64;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % 64);
+    const int n = static_cast<int>((i / 64) % 128);
+    const int kb = static_cast<int>((i / (64 * 128)) % kblocks);
+    const int tap = static_cast<int>(i / (64LL * 128 * kblocks));
+    const int zi_l = k / Cin, ci = k % Cin, zo_l = n / Cout, co = n % Cout;
+    const int dz = kb * (64 / Cin) + zi_l - 1 - zo_l;
+    float v = 0.f;
+    if (dz >= -1 && dz <= 1) v = w[((static_cast<long long>(tap) * 3 + (dz + 1)) * Cin + ci) * Cout + co];
+    if (fmt == 0) { __half h = __float2half_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
+    else { __nv_bfloat16 h = __float2bfloat16_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
+  }
+}
+
+__global__ void expand_channels_kernel(const float* __restrict__ v, float* __restrict__ out, int C, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v[i % C];
+}
+
 // ------------------------------------------------------------------------------------------ elementwise
 // y = act(x + bias[c]) + residual, 16-bit in/out, channel = innermost axis (standalone prelu / tf.add /
 // sigmoid when they cannot be fused into a convolution epilogue; tools/layer_util.py:27-45,73,105).
@@ -496,6 +523,62 @@ extern "C" int rn_conv2d_transpose_same(const void* x, const void* w_packed, con
       off += static_cast<size_t>(pt.n) * cout_pad * Cin;
     }
   return 0;
+}
+
+
+// ---------------------------------------------------------------------------------- depth-folded conv3d
+static int banded_kblocks(int Cin, int Cout) {
+  const int span = (128 / Cout + 2) * Cin;  // input depths needed by one N tile, in elements
+  return (span + 63) / 64;
+}
+
+extern "C" long long rn_conv3d_banded_bytes(int Cin, int Cout) {
+  if (Cin < 8 || Cout < 8 || 64 % Cin != 0 || 128 % Cout != 0) return -1;
+  return 9LL * banded_kblocks(Cin, Cout) * 128 * 64 * 2;
+}
+
+extern "C" int rn_pack_conv3d_banded(const float* w, void* packed, int Cin, int Cout, int fmt, void* stream) {
+  if (!w || !packed || rn_conv3d_banded_bytes(Cin, Cout) < 0) return -1;
+  const int kb = banded_kblocks(Cin, Cout);
+  pack_banded_kernel<<<grid_for(9LL * kb * 128 * 64, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<uint16_t*>(packed), Cin, Cout, kb, fmt);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_expand_channels(const float* v, float* v_full, int C, int D, void* stream) {
+  if (!v || !v_full || C < 1 || D < 1) return -1;
+  const int n = C * D;
+  expand_channels_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, v_full, C, n);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_conv3d_banded_same(const void* x, const void* w_banded, const float* bias_full,
+                                     const float* alpha_full, int act, const void* residual, int residual_is_f32,
+                                     void* out16, float* out32, int B, int H, int W, int D, int Cin, int Cout,
+                                     int fmt, void* stream) {
+  if (rn_conv3d_banded_bytes(Cin, Cout) < 0) return -30;
+  const long long Fi = static_cast<long long>(D) * Cin, Fo = static_cast<long long>(D) * Cout;
+  if (Fo % 128 != 0 || Fi % 8 != 0) return -31;
+  int8_t taps[27];
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      int8_t* t = taps + 3 * (ky * 3 + kx);
+      t[0] = static_cast<int8_t>(kx - 1); t[1] = static_cast<int8_t>(ky - 1); t[2] = 0;
+    }
+  rn_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.ndim = 2; d.B = B; d.H = H; d.W = W; d.D = 1;
+  d.Cin = banded_kblocks(Cin, Cout) * 64;          // K elements per (ky,kx) tap
+  d.Cout = static_cast<int>(Fo); d.cout_pad = static_cast<int>(Fo);
+  d.ntaps = 9; d.taps = taps; d.x = x; d.w_packed = w_banded; d.bias = bias_full; d.alpha = alpha_full; d.act = act;
+  d.residual = residual; d.residual_is_f32 = residual_is_f32; d.out16 = out16; d.out32 = out32;
+  d.o_base = 0; d.o_x = Fo; d.o_y = static_cast<long long>(W) * Fo; d.o_b = static_cast<long long>(H) * W * Fo;
+  d.fmt = fmt; d.force_bn = 128;
+  d.x_channels = static_cast<int>(Fi);
+  d.a_c_base = -Cin;                                // first input depth of N tile 0 is z = -1 (zero filled)
+  d.a_c_ntile = (128 / Cout) * Cin;                 // each N tile advances 128/Cout depths
+  d.w_banded = 1;
+  return rn_conv_igemm(&d, stream);
 }
 
 // ---------------------------------------------------------------------------------- thin conv3d

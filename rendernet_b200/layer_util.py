@@ -18,6 +18,8 @@ from . import ops
 from . import tfcompat as tf
 from .tfcompat import Deferred, realize
 
+USE_BANDED_CONV3D = True   # depth-folded tensor-core path for 3^3 convs (falls back to the 5-D TMA path)
+
 _XAVIER = tf.xavier_initializer
 _RANDN002 = lambda: tf.random_normal_initializer(stddev=0.02)  # noqa: E731  (layer_util.py:149 default)
 
@@ -301,12 +303,23 @@ def _deferred_conv(kind, x, w, b, stride):
 
     def run(act, alpha, residual, want32):
         xt = _as16(xin)
-        L = _packed(w, b, kind, stride)
-        a = _alpha_arg(alpha, L.cout_pad)
+        banded = (kind == "conv3d" and USE_BANDED_CONV3D and tuple(w.shape[:3]) == (3, 3, 3)
+                  and ops.BandedConv3d.eligible(int(w.shape[3]), int(w.shape[4]), int(xt.shape[3])))
+        L = None if banded else _packed(w, b, kind, stride)
+        a = _alpha_arg(alpha, ops.round_up(int(w.shape[-1]), 16) if banded else L.cout_pad)
         want16 = not want32
         if kind == "conv2d":
             return ops.conv2d(xt, L, act=act, residual=residual, want16=want16, want32=want32, alpha=a)
         if kind == "conv3d":
+            D = xt.shape[3]
+            if (USE_BANDED_CONV3D and tuple(w.shape[:3]) == (3, 3, 3)
+                    and ops.BandedConv3d.eligible(int(w.shape[3]), int(w.shape[4]), D)):
+                Lb = _store().packed.get(("banded", w._rn_name))
+                if Lb is None:
+                    Lb = ops.BandedConv3d(w, b, dtype=tf.COMPUTE_DTYPE, device=_store().device)
+                    _store().packed[("banded", w._rn_name)] = Lb
+                return ops.conv3d_banded(xt, Lb, act=act, residual=residual, alpha=a,
+                                         alpha_tag=getattr(alpha, "_rn_name", None), want16=want16, want32=want32)
             return ops.conv3d(xt, L, act=act, residual=residual, want16=want16, want32=want32, alpha=a)
         if residual is not None:
             y = ops.conv2d_transpose(xt, L, act=act, alpha=a)

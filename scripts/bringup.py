@@ -136,6 +136,23 @@ def t_conv3d():
         report(f"conv3d 3^3 B{B} {H}x{W}x{D} {Cin}->{Cout} +res", y, orc.conv3d(x, w, b) + torch.from_numpy(res), 3e-3)
 
 
+def t_conv3d_banded():
+    rng = np.random.default_rng(21)
+    for (B, H, W, D, Cin, Cout) in [(1, 8, 8, 32, 32, 32), (1, 8, 16, 32, 16, 32), (2, 4, 8, 16, 16, 16), (1, 6, 5, 8, 32, 32),
+                                     (1, 16, 16, 4, 32, 32)]:
+        x = q16(rng.standard_normal((B, H, W, D, Cin)))
+        w = q16(rng.standard_normal((3, 3, 3, Cin, Cout)) / np.sqrt(27 * Cin))
+        b = rng.standard_normal(Cout).astype(np.float32) * 0.1
+        a = rng.uniform(0, 0.3, Cout).astype(np.float32)
+        res = q16(rng.standard_normal((B, H, W, D, Cout)))
+        L = ops.BandedConv3d(torch.from_numpy(w), torch.from_numpy(b))
+        xt = torch.from_numpy(x).to(dev).half()
+        y = ops.conv3d_banded(xt, L, act="prelu", alpha=torch.from_numpy(a).to(dev))
+        report(f"conv3d banded B{B} {H}x{W}x{D} {Cin}->{Cout} prelu", y, orc.prelu(orc.conv3d(x, w, b), a), 3e-3)
+        y = ops.conv3d_banded(xt, L, act=None, residual=torch.from_numpy(res).to(dev).half())
+        report(f"conv3d banded B{B} {H}x{W}x{D} {Cin}->{Cout} +res", y, orc.conv3d(x, w, b) + torch.from_numpy(res), 3e-3)
+
+
 def t_conv2d_transpose():
     rng = np.random.default_rng(12)
     for (B, H, W, Cin, Cout, s) in [(1, 16, 16, 64, 32, 2), (1, 16, 16, 64, 64, 1), (2, 8, 8, 256, 128, 2),
@@ -219,6 +236,10 @@ def t_big_layers():
     out = torch.empty_like(x)
     ms = timeit(lambda: ops.conv3d(x, L, act="prelu", out16=out))
     print(f"[perf] res1 3^3 32->32: {ms:.3f} ms  {2.0 * B * 64 * 64 * 32 * 27 * 32 * 32 / ms / 1e9:.1f} TFLOP/s", flush=True)
+    Lb = ops.BandedConv3d(w, torch.zeros(32))
+    al = torch.rand(32, device=dev) * 0.3
+    ms = timeit(lambda: ops.conv3d_banded(x, Lb, act="prelu", alpha=al, out16=out))
+    print(f"[perf] res1 3^3 32->32 banded: {ms:.3f} ms  {2.0 * B * 64 * 64 * 32 * 27 * 32 * 32 / ms / 1e9:.1f} TFLOP/s (useful)", flush=True)
     vox = (torch.rand(B, 64, 64, 64, 1, device=dev) < 0.1).float()
     minv = torch.eye(4, device=dev)[:3].repeat(B, 1, 1).contiguous()
     minv[:, :, 3] = -32
@@ -237,7 +258,7 @@ def t_big_layers():
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
     t0 = time.time()
-    for fn in (t_resample, t_phong, t_conv3d_direct, t_gemm_1x1, t_conv2d_3x3, t_conv2d_4x4, t_conv3d, t_conv2d_transpose):
+    for fn in (t_resample, t_phong, t_conv3d_direct, t_gemm_1x1, t_conv2d_3x3, t_conv2d_4x4, t_conv3d, t_conv3d_banded, t_conv2d_transpose):
         case(fn)
     if "--quick" not in sys.argv:
         case(t_big_layers)
