@@ -29,6 +29,8 @@ extern "C" {
 
 int rn_version(void);
 const char* rn_error_string(int code);
+/* number of kernels this library has launched in this process (host-side counter) */
+long long rn_launch_count(void);
 
 /* ---- resampler ----------------------------------------------------------------------------------
  * Replaces tf_resampling + tf_interpolate + tf_voxel_meshgrid (tools/resampling_voxel_grid.py:381-614)

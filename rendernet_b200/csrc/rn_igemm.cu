@@ -16,6 +16,7 @@
 //   * Persistent: grid = #SMs, static round-robin tile schedule with N fastest so concurrently running
 //     CTAs share the same activation rows in L2.
 #include <cstdio>
+#include <atomic>
 #include <cstring>
 #include <cuda_bf16.h>
 
@@ -313,6 +314,7 @@ static CUtensorMapSwizzle swizzle_of(int row_bytes) {
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+std::atomic<long long> g_launch_count{0};   // kernels launched by this library (bench.py's gpu_launches)
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -332,12 +334,15 @@ static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaSt
     attr_set = true;
   }
   igemm_kernel<BN><<<grid, kNumThreads, smem, stream>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
 
 }  // namespace rn
 
 #include "../../include/rendernet_b200.h"
+
+extern "C" long long rn_launch_count(void) { return rn::g_launch_count.load(std::memory_order_relaxed); }
 
 extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   using namespace rn;

@@ -14,7 +14,10 @@
 
 #include "../../include/rendernet_b200.h"
 
+#include <atomic>
 namespace rn {
+extern std::atomic<long long> g_launch_count;
+#define RN_COUNT_LAUNCH() rn::g_launch_count.fetch_add(1, std::memory_order_relaxed)
 
 // ------------------------------------------------------------------------------------------ resampler
 // One warp per output row (innermost output axis); each lane owns 4 consecutive points per iteration so
@@ -359,6 +362,7 @@ extern "C" int rn_resample_f32(const float* vox, const float* minv, float* out, 
     case 4: resample_kernel<4><<<grid, block, 0, st>>>(vox, minv, out, B, size, new_size, transform); break;
     default: return -2;
   }
+  RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -381,6 +385,7 @@ extern "C" int rn_pack_conv_weights(const float* w, void* packed, int ntaps_tota
   const long long total = static_cast<long long>(sel.n) * cout_pad * Cin;
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, static_cast<uint16_t*>(packed), Cin, Cout, cout_pad, transposed, sel, fmt);
+  RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -389,6 +394,7 @@ extern "C" int rn_cast_f32_to_16(const float* src, void* dst, long long n, long 
   if (n_pad == 0) return 0;
   cast_f32_to_16_kernel<<<grid_for(n_pad, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<uint16_t*>(dst), n, n_pad, fmt);
+  RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -397,6 +403,7 @@ extern "C" int rn_cast_16_to_f32(const void* src, float* dst, long long n, int f
   if (n == 0) return 0;
   cast_16_to_f32_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint16_t*>(src), dst, n, fmt);
+  RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -408,6 +415,7 @@ extern "C" int rn_bias_act_16(const void* x, const float* bias, const float* alp
   bias_act_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint16_t*>(x), bias, alpha, act, static_cast<const uint16_t*>(residual),
       static_cast<uint16_t*>(out16), out32, n, C, fmt);
+  RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -542,6 +550,7 @@ extern "C" int rn_pack_conv3d_banded(const float* w, void* packed, int Cin, int 
   const int kb = banded_kblocks(Cin, Cout);
   pack_banded_kernel<<<grid_for(9LL * kb * 128 * 64, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, static_cast<uint16_t*>(packed), Cin, Cout, kb, fmt);
+  RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -549,6 +558,7 @@ extern "C" int rn_expand_channels(const float* v, float* v_full, int C, int D, v
   if (!v || !v_full || C < 1 || D < 1) return -1;
   const int n = C * D;
   expand_channels_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, v_full, C, n);
+  RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -605,6 +615,7 @@ extern "C" int rn_conv3d_direct(const void* x, int x_is_f32, const float* w, con
   else if (Cin == 2 && Cout == 8 && k == 3 && x_is_f32) RN_LAUNCH_DIRECT(2, 8, 3, true);
   else return -2;
 #undef RN_LAUNCH_DIRECT
+  RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -617,5 +628,6 @@ extern "C" int rn_phong_composite(const float* img, const float* light_dir, cons
   const int block = 256;
   phong_kernel<<<static_cast<int>((total + block - 1) / block), block, 0, static_cast<cudaStream_t>(stream)>>>(
       img, light_dir, light_col, ambient, k_diffuse, background_white, with_mask, out_f32, out_u8, B, npix);
+  RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }

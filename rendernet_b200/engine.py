@@ -31,6 +31,7 @@ class RenderEngine:
         self.is_greyscale = is_greyscale
         self.device = device
         tf.reset_default_graph(seed)
+        tf.get_store().device = device
         if weights is not None:
             tf.load_weight_dict(weights)
         self.vox = torch.zeros((batch, size, size, size, 1), device=device, dtype=torch.float32)
@@ -46,15 +47,18 @@ class RenderEngine:
         self.out_u8 = None
         self.launches_per_step = None
         # warm-up (packs weights, sets kernel attributes, sizes the allocator), then capture
+        from ._lib import lib
         self._forward()
         torch.cuda.synchronize()
+        n0 = lib.rn_launch_count()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._forward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.launches_per_step = int(lib.rn_launch_count() - n0)   # kernels of one steady-state step
         if use_graph:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                self._forward()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._forward()
