@@ -1,0 +1,266 @@
+"""GPU parity tests: every CUDA kernel, called through the C ABI (ctypes), against the CPU oracle on the same
+seeded inputs.  Tolerances (floating point, stated per test):
+  * resampler / Phong (fp32 kernels): absolute 2e-4 / 1e-4;
+  * tensor-core convs: operands are rounded to fp16 for BOTH sides, so the fp32-output error is pure
+    accumulation-order noise (<= 1e-5 relative) and the fp16-output error is one fp16 rounding (<= 2^-10 relative).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rendernet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def _ops():
+    from rendernet_b200 import ops
+    return ops
+
+
+def q16(a):
+    return torch.from_numpy(np.asarray(a, np.float32)).half().float().numpy()
+
+
+def close(got, want, rel=None, abs_=None):
+    got = got.float().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    want = want.float().cpu().numpy() if isinstance(want, torch.Tensor) else np.asarray(want)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    err = float(np.abs(got - want).max())
+    bound = abs_ if abs_ is not None else rel * max(float(np.abs(want).max()), 1e-6)
+    assert err <= bound, f"max abs err {err:.3e} > {bound:.3e}"
+    return err
+
+
+# ----------------------------------------------------------------------------------------- resampler
+def test_resample_golden_small_and_chair(golden_dir):
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, "resample.npz"))
+    R, S = orc.rotation_around_grid_centroid(g["small_pose"])
+    minv = torch.from_numpy(orc.inverse_total_matrix(R, S, 16, 32)).to(dev)
+    vox = torch.from_numpy(g["small_vox"]).to(dev)
+    close(ops.resample(vox, minv, 32, False), g["small_out"], abs_=2e-4)
+    close(ops.resample(vox, minv, 32, True), g["small_net_in"], abs_=2e-4)
+    bv = np.load(os.path.join(golden_dir, "binvox.npz"))
+    chair = np.unpackbits(bv["chair_bits"]).reshape(1, 64, 64, 64, 1).astype(np.float32)
+    R, S = orc.rotation_around_grid_centroid(g["chair_pose"])
+    minv = torch.from_numpy(orc.inverse_total_matrix(R, S, 64, 128)).to(dev)
+    out = ops.resample(torch.from_numpy(chair).to(dev), minv, 128, True)
+    ref = np.zeros(128 ** 3, np.float32)
+    ref[g["chair_nz_idx"]] = g["chair_nz_val"]
+    close(out.reshape(-1), ref, abs_=2e-4)
+    assert abs(float(out.double().sum()) - float(g["chair_sum"])) < 0.05
+
+
+def test_resample_properties_full_size():
+    """Size-independent properties at BASELINE's full size (B=24, 64^3 -> 128^3): linearity in the voxel values,
+    range preservation, and identity pose reproducing the grid at the embedded offset."""
+    ops = _ops()
+    rng = np.random.default_rng(0)
+    B = 24
+    vox = torch.from_numpy((rng.random((B, 64, 64, 64, 1)) < 0.1).astype(np.float32)).to(dev)
+    poses = np.stack([rng.uniform(0, 2 * np.pi, B), (90 - rng.uniform(10, 170, B)) * np.pi / 180,
+                      3.3 / rng.uniform(2.5, 4.5, B)], axis=1).astype(np.float32)
+    R, S = orc.rotation_around_grid_centroid(poses)
+    minv = torch.from_numpy(orc.inverse_total_matrix(R, S, 64, 128)).to(dev)
+    a = ops.resample(vox, minv, 128, True)
+    assert float(a.min()) >= 0.0 and float(a.max()) <= 1.0 + 1e-6
+    b = ops.resample(vox * 0.25, minv, 128, True)
+    close(b, a * 0.25, abs_=1e-6)                                                     # linearity
+    eye = torch.eye(4)[:3].repeat(B, 1, 1).contiguous()
+    eye[:, :, 3] = -32.0                                                              # p_src = p_dst - 32
+    t = ops.resample(vox, eye.to(dev), 128, False)
+    assert torch.equal(t[:, 32:95, 32:95, 32:95], vox[:, :63, :63, :63])              # interior copied exactly
+    assert float(t[:, :32].abs().max()) == 0.0 and float(t[:, 96:].abs().max()) == 0.0
+
+
+def test_resample_axis_aligned_knife_edges(golden_dir):
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, "resample.npz"))
+    R, S = orc.rotation_around_grid_centroid(g["axis_pose"])
+    minv = orc.inverse_total_matrix(R, S, 16, 32)
+    out = ops.resample(torch.from_numpy(g["axis_vox"]).to(dev), torch.from_numpy(minv).to(dev), 32, False).cpu().numpy()
+    diff = np.abs(out - g["axis_out"])
+    # points whose source coordinate is within 1e-4 of 0 or 15 sit on the clamp discontinuity
+    grid = orc.voxel_meshgrid(32, 32, 32)
+    pts = np.matmul(minv, grid[None])
+    edge = (np.minimum(np.abs(pts), np.abs(pts - 15.0)).min(axis=1) < 1e-4).reshape(out.shape[:4])
+    assert diff[~edge].max() < 2e-4
+    assert edge.mean() < 0.2
+
+
+# ----------------------------------------------------------------------------------------- Phong
+def test_phong_matches_reference(golden_dir):
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, "phong.npz"))
+    lc = torch.ones(2, 3)
+    out, u8 = ops.phong_composite(torch.from_numpy(g["normal_map"]).to(dev), torch.from_numpy(g["light"]).float(), lc,
+                                  0.1, 0.9, want_u8=True)
+    close(out, g["composite"].astype(np.float32), abs_=1e-4)
+    assert np.abs(u8[0].cpu().numpy().astype(int) - g["uint8_first"].astype(int)).max() <= 1
+    out = ops.phong_composite(torch.from_numpy(g["normal_map"]).to(dev), torch.from_numpy(g["light"]).float(), lc,
+                              0.1, 0.9, background_white=True)
+    close(out, g["composite_white"].astype(np.float32), abs_=1e-4)
+
+
+# ----------------------------------------------------------------------------------------- tensor-core convs
+CONV2D = [  # B,H,W,Cin,Cout,k,act,res,res32
+    (1, 16, 16, 64, 64, 1, None, False, False), (1, 16, 16, 128, 256, 1, None, False, False),
+    (1, 16, 16, 16, 16, 1, None, False, False), (1, 16, 16, 32, 32, 1, None, False, False),
+    (1, 16, 16, 256, 512, 1, "prelu", False, False), (1, 16, 16, 64, 3, 1, None, False, False),
+    (1, 16, 16, 64, 24, 1, None, False, False),
+    (2, 16, 16, 64, 64, 3, "prelu", False, False), (1, 16, 16, 128, 128, 3, None, True, False),
+    (1, 16, 16, 128, 128, 3, None, True, True), (1, 64, 64, 64, 256, 3, "prelu", False, False),
+    (1, 24, 20, 32, 64, 3, "prelu", False, False),      # ragged tiles (H, W not multiples of the M box)
+    (1, 8, 8, 64, 64, 3, "sigmoid", False, False),      # M box taller than the image
+    (1, 5, 7, 16, 16, 3, None, True, False),            # tiny, everything ragged
+    (1, 128, 128, 32, 16, 3, "prelu", False, False), (1, 256, 256, 16, 16, 3, None, False, False),
+    (1, 16, 16, 64, 128, 4, "prelu", False, False), (2, 32, 32, 128, 64, 4, None, False, False),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,act,with_res,res32", CONV2D)
+def test_conv2d_same(B, H, W, Cin, Cout, k, act, with_res, res32):
+    ops = _ops()
+    rng = np.random.default_rng(Cin * 7 + Cout + k)
+    x = q16(rng.standard_normal((B, H, W, Cin)))
+    w = q16(rng.standard_normal((k, k, Cin, Cout)) / np.sqrt(k * k * Cin))
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    a = rng.uniform(0, 0.3, Cout).astype(np.float32)
+    res = q16(rng.standard_normal((B, H, W, Cout))) if with_res else None
+    L = ops.pack_conv("conv2d", torch.from_numpy(w), torch.from_numpy(b), torch.from_numpy(a))
+    rt = None
+    if with_res:
+        rt = torch.from_numpy(res).to(dev)
+        rt = rt if res32 else rt.half()
+    y16, y32 = ops.conv2d(torch.from_numpy(x).to(dev).half(), L, act=act, residual=rt, want16=True, want32=True)
+    ref = orc.conv2d(x, w, b)
+    if act == "prelu":
+        ref = orc.prelu(ref, a)
+    elif act == "sigmoid":
+        ref = torch.sigmoid(ref)
+    if with_res:
+        ref = ref + torch.from_numpy(res)
+    close(y32, ref, rel=2e-5)
+    close(y16, ref, rel=1.2e-3)
+
+
+@pytest.mark.parametrize("B,H,W,D,Cin,Cout", [(1, 8, 8, 32, 32, 32), (1, 8, 8, 32, 16, 32), (2, 4, 8, 16, 16, 16),
+                                               (1, 6, 5, 32, 32, 32), (1, 16, 16, 4, 32, 32), (1, 3, 3, 3, 16, 16)])
+@pytest.mark.parametrize("path", ["tma5d", "banded"])
+def test_conv3d_same(B, H, W, D, Cin, Cout, path):
+    ops = _ops()
+    if path == "banded" and not ops.BandedConv3d.eligible(Cin, Cout, D):
+        pytest.skip("shape not eligible for the depth-folded path")
+    rng = np.random.default_rng(D + Cin + Cout)
+    x = q16(rng.standard_normal((B, H, W, D, Cin)))
+    w = q16(rng.standard_normal((3, 3, 3, Cin, Cout)) / np.sqrt(27 * Cin))
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    a = rng.uniform(0, 0.3, Cout).astype(np.float32)
+    res = q16(rng.standard_normal((B, H, W, D, Cout)))
+    xt = torch.from_numpy(x).to(dev).half()
+    rt = torch.from_numpy(res).to(dev).half()
+    if path == "tma5d":
+        L = ops.pack_conv("conv3d", torch.from_numpy(w), torch.from_numpy(b), torch.from_numpy(a))
+        y1 = ops.conv3d(xt, L, act="prelu", want16=False, want32=True)
+        y2 = ops.conv3d(xt, L, act=None, residual=rt)
+    else:
+        L = ops.BandedConv3d(torch.from_numpy(w), torch.from_numpy(b))
+        y1 = ops.conv3d_banded(xt, L, act="prelu", alpha=torch.from_numpy(a).to(dev), want16=False, want32=True)
+        y2 = ops.conv3d_banded(xt, L, act=None, residual=rt)
+    close(y1, orc.prelu(orc.conv3d(x, w, b), a), rel=2e-5)
+    close(y2, orc.conv3d(x, w, b) + torch.from_numpy(res), rel=1.2e-3)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,s", [(1, 16, 16, 64, 32, 2), (1, 16, 16, 64, 64, 1), (2, 8, 8, 256, 128, 2),
+                                               (1, 32, 32, 32, 16, 1), (1, 32, 32, 16, 3, 1), (1, 64, 64, 64, 32, 2),
+                                               (1, 7, 9, 16, 16, 2)])
+def test_conv2d_transpose_same(B, H, W, Cin, Cout, s):
+    ops = _ops()
+    rng = np.random.default_rng(Cin + Cout + s)
+    x = q16(rng.standard_normal((B, H, W, Cin)))
+    w = q16(rng.standard_normal((4, 4, Cout, Cin)) / np.sqrt(16 * Cin / (s * s)))
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    a = rng.uniform(0, 0.3, Cout).astype(np.float32)
+    L = ops.pack_conv("conv2d_transpose", torch.from_numpy(w), torch.from_numpy(b), torch.from_numpy(a), stride=s)
+    y16, y32 = ops.conv2d_transpose(torch.from_numpy(x).to(dev).half(), L, act="prelu", want32=True)
+    ref = orc.prelu(orc.conv2d_transpose(x, w, b, (s, s)), a)
+    close(y32, ref, rel=2e-5)
+    close(y16, ref, rel=1.2e-3)
+
+
+def test_conv_bf16_variant():
+    ops = _ops()
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.standard_normal((1, 16, 16, 64)).astype(np.float32)).bfloat16()
+    w = torch.from_numpy((rng.standard_normal((3, 3, 64, 64)) / 24).astype(np.float32)).bfloat16().float()
+    L = ops.pack_conv("conv2d", w, torch.zeros(64), None, dtype=torch.bfloat16)
+    y = ops.conv2d(x.to(dev), L, want16=False, want32=True)
+    close(y, orc.conv2d(x.float().numpy(), w.numpy(), None), rel=2e-5)
+
+
+def test_conv_linearity_and_tile_schedule_full_size():
+    """BASELINE-size layer (B=24, 64x64, 1024->1024, 3x3): linearity f(2x) = 2 f(x) (exact in fp16: power of two),
+    independence from the persistent-CTA count, and agreement with a cuDNN fp32 conv on a slice."""
+    ops = _ops()
+    torch.manual_seed(0)
+    B = 24
+    x = torch.randn(B, 64, 64, 1024, device=dev).half()
+    w = torch.randn(3, 3, 1024, 1024, device=dev) / 96.0
+    L = ops.pack_conv("conv2d", w, torch.zeros(1024), None)
+    y = ops.conv2d(x, L)
+    y2 = ops.conv2d(x * 2, L)
+    assert torch.equal(y2, y * 2)
+    # same work on 37 CTAs instead of 148: different tile->CTA assignment, identical result
+    taps = [(kx - 1, ky - 1, 0) for ky in range(3) for kx in range(3)]
+    y3 = torch.empty_like(y)
+    ops.conv_igemm_raw(x, L.w, L.bias, taps, 2, B, 64, 64, 1, 1024, 1024, 1024, out16=y3, max_ctas=37)
+    assert torch.equal(y3, y)
+    ref = torch.nn.functional.conv2d(x[:1].permute(0, 3, 1, 2).float(), w.half().float().permute(3, 2, 0, 1),
+                                     padding=1).permute(0, 2, 3, 1)
+    close(y[:1], ref, rel=1.5e-3)
+
+
+# ----------------------------------------------------------------------------------------- thin conv3d / misc
+def test_conv3d_direct_first_layers():
+    ops = _ops()
+    rng = np.random.default_rng(13)
+    x = rng.random((1, 16, 16, 32, 1)).astype(np.float32)
+    w = (rng.standard_normal((5, 5, 5, 1, 8)) / np.sqrt(125)).astype(np.float32)
+    b = (rng.standard_normal(8) * 0.1).astype(np.float32)
+    a = rng.uniform(0, 0.3, 8).astype(np.float32)
+    t = lambda v: torch.from_numpy(v).to(dev)
+    y = ops.conv3d_direct(t(x), t(w), t(b), t(a), (2, 2, 2))
+    close(y, orc.prelu(orc.conv3d(x, w, b, (2, 2, 2)), a), rel=1.2e-3)
+    x = q16(rng.standard_normal((1, 8, 8, 32, 8)))
+    w = (rng.standard_normal((3, 3, 3, 8, 16)) / np.sqrt(27 * 8)).astype(np.float32)
+    b = (rng.standard_normal(16) * 0.1).astype(np.float32)
+    a = rng.uniform(0, 0.3, 16).astype(np.float32)
+    y = ops.conv3d_direct(t(x).half(), t(w), t(b), t(a), (1, 1, 2))
+    close(y, orc.prelu(orc.conv3d(x, w, b, (1, 1, 2)), a), rel=1.2e-3)
+
+
+def test_bias_act_and_casts():
+    ops = _ops()
+    rng = np.random.default_rng(5)
+    x = q16(rng.standard_normal((2, 5, 7, 24)))
+    r = q16(rng.standard_normal((2, 5, 7, 24)))
+    a = rng.uniform(0, 0.3, 24).astype(np.float32)
+    y = ops.bias_act(torch.from_numpy(x).to(dev).half(), None, torch.from_numpy(a).to(dev), "prelu",
+                     residual=torch.from_numpy(r).to(dev).half())
+    close(y, orc.prelu(x, a) + torch.from_numpy(r), rel=1.2e-3)
+    z = ops.cast_to_f32(ops.cast_to_16(torch.from_numpy(x).to(dev)))
+    assert torch.equal(z.cpu(), torch.from_numpy(x))
+
+
+def test_invalid_arguments_raise():
+    ops = _ops()
+    from rendernet_b200._lib import RenderNetCudaError
+    x = torch.zeros(1, 8, 8, 24, device=dev, dtype=torch.float16)     # Cin not a multiple of 16
+    with pytest.raises(RenderNetCudaError):
+        ops.conv_igemm_raw(x, x, torch.zeros(16, device=dev), [(0, 0, 0)], 2, 1, 8, 8, 1, 24, 16, 16, out16=x)
+    with pytest.raises(RuntimeError):
+        ops.resample(torch.zeros(1, 4, 4, 4, 1), torch.zeros(1, 3, 4), 8, True)     # CPU tensors are rejected

@@ -1,0 +1,185 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every symbol include/rendernet_b200.h
+declares (no compute calls without a GPU), the reference-mirroring host functions agree with the oracle / golden
+fixtures, and the batch-sharding + all-gather logic under a 2-process gloo group."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rendernet_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rendernet_b200._lib import SIGNATURES, lib
+    hdr = open(os.path.join(ROOT, "include", "rendernet_b200.h")).read()
+    declared = set(re.findall(r"\b(rn_[a-z0-9_]+)\s*\(", hdr)) - {"rn_conv_desc"}
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in SIGNATURES, f"{name} has no ctypes signature"
+    assert set(SIGNATURES) == declared
+    assert lib.rn_version() >= 100
+    assert b"invalid" in lib.rn_error_string(-1)
+
+
+def test_conv_desc_struct_matches_header_field_order():
+    from rendernet_b200._lib import rn_conv_desc
+    hdr = open(os.path.join(ROOT, "include", "rendernet_b200.h")).read()
+    body = hdr[hdr.index("typedef struct rn_conv_desc {"):hdr.index("} rn_conv_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(int8_t|void|float|int|long long)\s*\**\s*", "", decl)
+        names += [n.strip().lstrip("*") for n in decl.split(",")]
+    assert names == [f[0] for f in rn_conv_desc._fields_]
+
+
+def test_no_cpu_fallback():
+    from rendernet_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.resample(torch.zeros(1, 4, 4, 4, 1), torch.zeros(1, 3, 4), 8, True)
+    with pytest.raises(RuntimeError):
+        ops.cast_to_16(torch.zeros(4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "rendernet_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_pose_matrices_match_oracle_and_golden(golden_dir):
+    from rendernet_b200.resampling_voxel_grid import (inverse_sampling_matrix, tf_rotation_around_grid_centroid,
+                                                      tf_voxel_meshgrid)
+    g = np.load(os.path.join(golden_dir, "resample.npz"))
+    R, S = tf_rotation_around_grid_centroid(g["chair_pose"])
+    assert np.array_equal(R, g["chair_R"]) and np.array_equal(S, g["chair_S"])
+    rng = np.random.default_rng(0)
+    vp = np.stack([rng.uniform(0, 2 * np.pi, 8), rng.uniform(-1.4, 1.4, 8), rng.uniform(0.7, 1.4, 8)], 1).astype(np.float32)
+    R, S = tf_rotation_around_grid_centroid(vp)
+    Ro, So = orc.rotation_around_grid_centroid(vp)
+    assert np.array_equal(R, Ro) and np.array_equal(S, So)
+    assert np.array_equal(inverse_sampling_matrix(R, S, 64, 128), orc.inverse_total_matrix(Ro, So, 64, 128))
+    assert np.array_equal(tf_voxel_meshgrid(4, 5, 6, True), orc.voxel_meshgrid(4, 5, 6))
+    assert tf_rotation_around_grid_centroid(vp[:, :2]).shape == (8, 4, 4)       # 2-parameter form returns R only
+
+
+def test_demo_helpers(golden_dir, tmp_path):
+    from rendernet_b200 import Phong_shading, binvox_rw
+    from rendernet_b200.RenderNet_demo import Session, compute_pose_param, load_graph
+    g = np.load(os.path.join(golden_dir, "pose.npz"))
+    assert np.array_equal(compute_pose_param(250.0, 60.0, 3.3), g["pose_250_60_33"])
+    assert np.array_equal(Phong_shading.generate_light_pos(60.0, 250.0), g["light_60_250"])
+    bv = np.load(os.path.join(golden_dir, "binvox.npz"))
+    grid = np.unpackbits(bv["teapot_bits"]).reshape(64, 64, 64).astype(bool)
+    flat = np.transpose(grid, (0, 2, 1)).reshape(-1).astype(np.uint8)
+    rle = bytearray()
+    i = 0
+    while i < flat.size:
+        j = i
+        while j < flat.size and flat[j] == flat[i] and j - i < 255:
+            j += 1
+        rle += bytes([int(flat[i]), j - i])
+        i = j
+    p = tmp_path / "teapot.binvox"
+    p.write_bytes(b"#binvox 1\ndim 64 64 64\ntranslate 0 0 0\nscale 1\ndata\n" + bytes(rle))
+    with open(p, "rb") as f:
+        v = binvox_rw.read_as_3d_array(f)
+    assert v.data.dtype == bool and np.array_equal(v.data, grid) and int(v.data.sum()) == 27933
+    with pytest.raises(KeyError):
+        Session(load_graph(None)).run("encoder/nope:0", {})
+    with pytest.raises(NotImplementedError):
+        load_graph("model/3d2d_renderer.pb")
+
+
+def test_variable_store_names_and_npz_spelling():
+    from rendernet_b200 import tfcompat as tf
+    tf.reset_default_graph(seed=3)
+    with tf.variable_scope("encoder"):
+        with tf.variable_scope("res1_skip"):
+            with tf.variable_scope("con1_3X3"):
+                w = tf.get_variable("weights", [3, 3, 3, 32, 32], initializer=tf.xavier_initializer())
+                b = tf.get_variable("biases", [32], initializer=tf.constant_initializer(0.001))
+    assert w._rn_name == "encoder/res1_skip/con1_3X3/weights" and tuple(w.shape) == (3, 3, 3, 32, 32)
+    lim = np.sqrt(6.0 / (27 * 32 + 27 * 32))
+    assert float(w.abs().max()) <= lim + 1e-7 and float(w.abs().max()) > 0.9 * lim
+    assert torch.all(b == 0.001)
+    tf.reset_default_graph()
+    tf.load_weight_dict({"res1_skip_con1_3X3_biases": np.full(32, 0.5, np.float32),      # npz-dir spelling
+                         "encoder/e_conv1/alpha:0": np.full(8, 0.25, np.float32)})       # TF spelling with :0
+    with tf.variable_scope("encoder"):
+        with tf.variable_scope("res1_skip"):
+            with tf.variable_scope("con1_3X3"):
+                b = tf.get_variable("biases", [32], initializer=tf.constant_initializer(0.001))
+        with tf.variable_scope("e_conv1"):
+            a = tf.get_variable("alpha", [8], initializer=tf.constant_initializer(0.0))
+            with pytest.raises(ValueError):
+                tf.get_variable("alpha", [9])
+    assert torch.all(b == 0.5) and torch.all(a == 0.25)
+    tf.reset_default_graph()
+
+
+def test_shard_bounds_partition():
+    from rendernet_b200.parallel import shard_bounds, turntable_poses
+    for n, w in [(192, 8), (360, 8), (24, 1), (7, 3), (2, 4)]:
+        cover = []
+        for r in range(w):
+            lo, hi = shard_bounds(n, w, r)
+            assert 0 <= lo <= hi <= n
+            cover += list(range(lo, hi))
+        assert cover == list(range(n))
+    assert shard_bounds(192, 8, 3) == (72, 96) and shard_bounds(360, 8, 7) == (315, 360)
+    p = turntable_poses(72, 60.0, 3.3)
+    assert p.shape == (72, 3) and abs(p[1, 0] - np.deg2rad(5.0)) < 1e-6 and abs(p[0, 1] - np.deg2rad(30)) < 1e-6
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gloo_worker(rank, world, port, n_total, q):
+    import torch.distributed as dist
+    from rendernet_b200.parallel import all_gather_images, broadcast_weight_dict, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(n_total * 2 * 3 * 3, dtype=torch.float32).reshape(n_total, 2, 3, 3)   # the "rendered" batch
+    lo, hi = shard_bounds(n_total, world, rank)
+    got = all_gather_images(full[lo:hi].clone(), n_total)
+    W = {"a/weights": np.arange(6, dtype=np.float32).reshape(2, 3), "b": np.ones(4, np.float32)} if rank == 0 else None
+    Wb = broadcast_weight_dict(W, src=0)
+    ok = torch.equal(got, full) and np.array_equal(Wb["a/weights"], np.arange(6, dtype=np.float32).reshape(2, 3)) \
+        and np.array_equal(Wb["b"], np.ones(4, np.float32))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [8, 5])
+def test_batch_sharding_allgather_world2_gloo(n_total):
+    """world_size=2 on CPU/gloo: shard the batch, 'render', all-gather -> identical to the unsharded batch
+    (even and ragged shard sizes), and the weight broadcast replicates rank 0's dict."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
