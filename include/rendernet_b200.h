@@ -31,6 +31,8 @@ int rn_version(void);
 const char* rn_error_string(int code);
 /* number of kernels this library has launched in this process (host-side counter) */
 long long rn_launch_count(void);
+/* default cluster size (1, 2, 4) used by descriptors that leave `cluster` at 0; returns the previous value */
+int rn_set_default_cluster(int cluster);
 
 /* ---- resampler ----------------------------------------------------------------------------------
  * Replaces tf_resampling + tf_interpolate + tf_voxel_meshgrid (tools/resampling_voxel_grid.py:381-614)
@@ -88,6 +90,7 @@ typedef struct rn_conv_desc {
    * tap starting at channel a_c_base + n_tile*a_c_ntile (may run out of range: zero filled), and w_packed is one
    * banded filter [ntaps*Cin/KB][force_bn][KB] shared by all N tiles.  All zero for ordinary convolutions. */
   int x_channels, a_c_base, a_c_ntile, w_banded;
+  int cluster;              /* thread-block-cluster size for the weight-tile TMA multicast: 0 auto, 1, 2 or 4 */
 } rn_conv_desc;
 int rn_conv_igemm(const rn_conv_desc* d, void* stream);
 

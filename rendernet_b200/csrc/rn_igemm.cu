@@ -147,7 +147,11 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
   }
 }
 
-template <int BN>
+// CL = thread-block-cluster size (1, 2 or 4).  The CL CTAs of a cluster work on CL consecutive M tiles of the SAME
+// N tile; each loads 1/CL of every weight (B) tile and TMA-multicasts it to all of them, so B is fetched from L2
+// once per cluster instead of once per CTA.  A smem stage may only be refilled when every CTA of the cluster has
+// released it (empty barrier count = CL; each MMA warp commits to all CTAs' empty barriers).
+template <int BN, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   constexpr int CW = (BN >= 32) ? 32 : 16;                     // epilogue column chunk
   constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // double-buffered accumulator
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -180,8 +184,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
   if (warp == 1) tmem_alloc<1>(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync();   // peers' barriers are initialised before any multicast / remote commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int cta_rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  // tile walk: cluster c handles "cluster tiles" c, c+nclusters, ...; cluster tile ct -> tiles (mg*CL + rank, n)
+  const int ncl = static_cast<int>(gridDim.x) / CL;
+  const int cl_id = static_cast<int>(blockIdx.x) / CL;
+  const int num_ct = p.num_tiles / CL;
+  auto tile_of = [&](int ct) { return ((ct / p.n_tiles) * CL + cta_rank) * p.n_tiles + (ct % p.n_tiles); };
 
   const int total_k = p.ntaps * p.kblocks;
   const int kb_elems = p.row_bytes >> 1;
@@ -193,7 +204,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
+      constexpr int kBRows = BN / CL;               // rows of the B tile this CTA fetches (and multicasts)
+      for (int ct = cl_id; ct < num_ct; ct += ncl) {
+        const int tile = tile_of(ct);
         const TileCoord t = decode_tile(p, tile, BN);
         const int a_c0 = p.a_c_base + (t.n0 / BN) * p.a_c_ntile;
         for (int it = 0; it < total_k;) {
@@ -211,8 +225,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             const int ac = a_c0 + kb * kb_elems;
             if (p.rank == 4) tma_load_4d(a_dst, &p.tmA, &full_bar[stage], ac, cx, cy, t.b);
             else tma_load_5d(a_dst, &p.tmA, &full_bar[stage], ac, cz, cx, cy, t.b);
-            if (p.b_banded) tma_load_3d(b_dst, &p.tmB, &full_bar[stage], 0, 0, kit);
-            else tma_load_3d(b_dst, &p.tmB, &full_bar[stage], kb * kb_elems, t.n0, tap);
+            if constexpr (CL == 1) {
+              if (p.b_banded) tma_load_3d(b_dst, &p.tmB, &full_bar[stage], 0, 0, kit);
+              else tma_load_3d(b_dst, &p.tmB, &full_bar[stage], kb * kb_elems, t.n0, tap);
+            } else {
+              uint8_t* b_part = b_dst + cta_rank * kBRows * p.row_bytes;
+              if (p.b_banded) tma_load_3d_mc(b_part, &p.tmB, &full_bar[stage], kMask, 0, cta_rank * kBRows, kit);
+              else tma_load_3d_mc(b_part, &p.tmB, &full_bar[stage], kMask, kb * kb_elems, t.n0 + cta_rank * kBRows, tap);
+            }
           }
           it += n_here;
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -228,7 +248,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int ct = cl_id; ct < num_ct; ct += ncl) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -243,7 +263,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             for (int k = 0; k < mma_per_kit; ++k)
               umma_f16<1>(d_tmem, da + 2 * k, db + 2 * k, idesc, (it + j > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit<1>(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in every CTA of the cluster: their multicasts write into ours) once these MMAs retire
+          if constexpr (CL == 1) umma_commit<1>(&empty_bar[stage]);
+          else umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>((1u << CL) - 1u));
           it += n_here;
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -261,8 +283,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     const int yl = m / (p.BD * p.BW);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile, BN);
+    for (int ct = cl_id; ct < num_ct; ct += ncl) {
+      const TileCoord t = decode_tile(p, tile_of(ct), BN);
       const int x = t.x0 + xl, y = t.y0 + yl, z = t.z0 + zl;
       const bool row_valid = (x < p.W) && (y < p.H) && (z < p.D);
       const long long off = p.o_base + t.b * p.o_b + y * p.o_y + x * p.o_x + z * p.o_z;
@@ -289,6 +311,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync();   // no CTA exits while a peer may still multicast into / commit to it
   if (warp == 1) tmem_dealloc<1>(tmem_base, kTmemCols);
 }
 
@@ -314,6 +337,7 @@ static CUtensorMapSwizzle swizzle_of(int row_bytes) {
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+int g_default_cluster = 2;                   // B-multicast cluster size used when the descriptor says 0 (auto)
 std::atomic<long long> g_launch_count{0};   // kernels launched by this library (bench.py's gpu_launches)
 static int g_num_sms = 0;
 static int num_sms() {
@@ -325,22 +349,45 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN>
+template <int BN, int CL>
 static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  igemm_kernel<BN><<<grid, kNumThreads, smem, stream>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  return cudaGetLastError();
+  if constexpr (CL == 1) {
+    igemm_kernel<BN, 1><<<grid, kNumThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, igemm_kernel<BN, CL>, p);
+  }
 }
 
 }  // namespace rn
 
 #include "../../include/rendernet_b200.h"
+
+extern "C" int rn_set_default_cluster(int c) {
+  const int prev = rn::g_default_cluster;
+  if (c == 1 || c == 2 || c == 4) rn::g_default_cluster = c;
+  return prev;
+}
 
 extern "C" long long rn_launch_count(void) { return rn::g_launch_count.load(std::memory_order_relaxed); }
 
@@ -408,6 +455,19 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   if (p.stages < 2) return -10;
   const size_t smem = static_cast<size_t>(p.stages) * p.kps * sub + 1024 + 256;
 
+  int grid = num_sms();
+  if (d->max_ctas > 0 && d->max_ctas < grid) grid = d->max_ctas;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  // cluster size for the B multicast: CL consecutive M tiles share an N tile
+  const int m_tiles = p.num_tiles / p.n_tiles;
+  int CL = 1;
+  if (BN >= 128) {
+    const int want = d->cluster > 0 ? d->cluster : g_default_cluster;
+    if (want >= 4 && m_tiles % 4 == 0 && grid >= 4) CL = 4;
+    else if (want >= 2 && m_tiles % 2 == 0 && grid >= 2) CL = 2;
+  }
+  grid -= grid % CL;
+
   const CUtensorMapDataType dt = d->fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r;
@@ -432,13 +492,13 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   if (d->w_banded) {  // [ntaps*kblocks][BN][KB], identical for every N tile
     const cuuint64_t dims[3] = {(cuuint64_t)KB, (cuuint64_t)BN, (cuuint64_t)d->ntaps * p.kblocks};
     const cuuint64_t strides[2] = {(cuuint64_t)KB * 2, (cuuint64_t)KB * 2 * BN};
-    const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)BN, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)(BN / CL), 1};
     r = enc(&p.tmB, dt, 3, const_cast<void*>(d->w_packed), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     const cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->cout_pad, (cuuint64_t)d->ntaps};
     const cuuint64_t strides[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * d->cout_pad};
-    const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)BN, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)(BN / CL), 1};
     r = enc(&p.tmB, dt, 3, const_cast<void*>(d->w_packed), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
@@ -452,16 +512,17 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_ok = strides8 && al16(d->out16) && al16(d->out32) && al16(d->residual) ? 1 : 0;
 
-  int grid = num_sms();
-  if (d->max_ctas > 0 && d->max_ctas < grid) grid = d->max_ctas;
-  if (grid > p.num_tiles) grid = p.num_tiles;
   cudaError_t e;
-  switch (BN) {
-    case 256: e = launch_bn<256>(p, grid, smem, stream); break;
-    case 128: e = launch_bn<128>(p, grid, smem, stream); break;
-    case 64: e = launch_bn<64>(p, grid, smem, stream); break;
-    case 32: e = launch_bn<32>(p, grid, smem, stream); break;
-    default: e = launch_bn<16>(p, grid, smem, stream); break;
+  switch (BN * 8 + CL) {
+    case 256 * 8 + 1: e = launch_bn<256, 1>(p, grid, smem, stream); break;
+    case 256 * 8 + 2: e = launch_bn<256, 2>(p, grid, smem, stream); break;
+    case 256 * 8 + 4: e = launch_bn<256, 4>(p, grid, smem, stream); break;
+    case 128 * 8 + 1: e = launch_bn<128, 1>(p, grid, smem, stream); break;
+    case 128 * 8 + 2: e = launch_bn<128, 2>(p, grid, smem, stream); break;
+    case 128 * 8 + 4: e = launch_bn<128, 4>(p, grid, smem, stream); break;
+    case 64 * 8 + 1: e = launch_bn<64, 1>(p, grid, smem, stream); break;
+    case 32 * 8 + 1: e = launch_bn<32, 1>(p, grid, smem, stream); break;
+    default: e = launch_bn<16, 1>(p, grid, smem, stream); break;
   }
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }

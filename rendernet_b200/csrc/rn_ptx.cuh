@@ -102,6 +102,16 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// multicast: the box is written to the same CTA-relative smem offset of every CTA in `mask`, and the byte count is
+// signalled on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, uint16_t mask, int c0,
+                                               int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, "
+      "%5, %6}], [%2], %3;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // cta_group::2 flavours: data lands in THIS CTA's smem, completion bytes are signalled on the barrier at
 // the same offset in the pair's leader CTA (address with the peer bit cleared).
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
@@ -198,6 +208,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
         "h"(mask)
         : "memory");
   }
+}
+
+// cta_group::1 commit that arrives on the barrier at the same smem offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
 }
 
 // 32 lanes x 32b, 32 consecutive columns: thread i of the warp receives TMEM lane (base_lane + i).

@@ -224,6 +224,26 @@ def test_conv_linearity_and_tile_schedule_full_size():
     close(y[:1], ref, rel=1.5e-3)
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("bn", [256, 128])
+def test_conv_cluster_multicast_bit_identical(cluster, bn):
+    """The weight-tile TMA multicast across a 2/4-CTA cluster must not change a single bit."""
+    ops = _ops()
+    torch.manual_seed(1)
+    B, H, W, Cin, Cout = 3, 32, 32, 128, 256                    # 24 M tiles: divisible by 4
+    x = torch.randn(B, H, W, Cin, device=dev).half()
+    w = torch.randn(3, 3, Cin, Cout, device=dev) / (9 * Cin) ** 0.5
+    L = ops.pack_conv("conv2d", w, torch.randn(Cout) * 0.1, torch.rand(Cout) * 0.3)
+    taps = [(kx - 1, ky - 1, 0) for ky in range(3) for kx in range(3)]
+    ref = ops.conv2d(x, L, act="prelu")
+    close(ref, orc.prelu(orc.conv2d(x.float().cpu().numpy(), w.half().float().cpu().numpy(), L.bias[:Cout].cpu().numpy()),
+                         L.alpha[:Cout].cpu().numpy()), rel=1.2e-3)
+    out = torch.empty_like(ref)
+    ops.conv_igemm_raw(x, L.w, L.bias, taps, 2, B, H, W, 1, Cin, Cout, L.cout_pad, out16=out, alpha=L.alpha, act=1,
+                       force_bn=bn, cluster=cluster)
+    assert torch.equal(out, ref)
+
+
 # ----------------------------------------------------------------------------------------- thin conv3d / misc
 def test_conv3d_direct_first_layers():
     ops = _ops()
