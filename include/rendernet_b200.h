@@ -33,6 +33,7 @@ const char* rn_error_string(int code);
 long long rn_launch_count(void);
 /* default cluster size (1, 2, 4) used by descriptors that leave `cluster` at 0; returns the previous value */
 int rn_set_default_cluster(int cluster);
+int rn_set_default_cta_group(int cta_group);
 
 /* ---- resampler ----------------------------------------------------------------------------------
  * Replaces tf_resampling + tf_interpolate + tf_voxel_meshgrid (tools/resampling_voxel_grid.py:381-614)
@@ -91,6 +92,7 @@ typedef struct rn_conv_desc {
    * banded filter [ntaps*Cin/KB][force_bn][KB] shared by all N tiles.  All zero for ordinary convolutions. */
   int x_channels, a_c_base, a_c_ntile, w_banded;
   int cluster;              /* thread-block-cluster size for the weight-tile TMA multicast: 0 auto, 1, 2 or 4 */
+  int cta_group;            /* 0 auto, 1 = single-CTA MMA, 2 = paired tcgen05.mma.cta_group::2 (M = 256) */
 } rn_conv_desc;
 int rn_conv_igemm(const rn_conv_desc* d, void* stream);
 

@@ -151,8 +151,16 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
 // N tile; each loads 1/CL of every weight (B) tile and TMA-multicasts it to all of them, so B is fetched from L2
 // once per cluster instead of once per CTA.  A smem stage may only be refilled when every CTA of the cluster has
 // released it (empty barrier count = CL; each MMA warp commits to all CTAs' empty barriers).
-template <int BN, int CL>
+//
+// CG = 2 (implies CL = 2): the pair issues ONE tcgen05.mma.cta_group::2 per k-step with M = 256: each CTA stages its
+// own 128 A rows and only HALF of the B tile (BN/2 rows); the tensor cores of both SMs read both halves.  Per SM
+// this cuts the operand bytes per MMA cycle from 48 KB to 32 KB per k-block (BN = 256), which matters because the
+// 1-CTA kernel is bound by the ~64 B/clk an SM can ingest from L2.  Only the leader CTA (rank 0) issues MMAs; its
+// full barrier collects the TMA bytes of both CTAs; commits are multicast to both CTAs' barriers; the peer's
+// epilogue warps release the accumulator on the leader's barrier with a remote arrive.
+template <int BN, int CL, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  static_assert(CG == 1 || (CG == 2 && CL == 2), "cta_group::2 runs on a 2-CTA cluster");
   constexpr int CW = (BN >= 32) ? 32 : 16;                     // epilogue column chunk
   constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // double-buffered accumulator
   extern __shared__ uint8_t smem_raw[];
@@ -173,15 +181,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);
+      mbar_init(&empty_bar[s], CG == 2 ? 1 : CL);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], CG == 2 ? 8 : 4);   // 4 epilogue warps (x2 CTAs feeding the leader's barrier)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<1>(tmem_slot, kTmemCols);
+  if (warp == 1) tmem_alloc<CG>(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync();   // peers' barriers are initialised before any multicast / remote commit
@@ -197,7 +205,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
   const int total_k = p.ntaps * p.kblocks;
   const int kb_elems = p.row_bytes >> 1;
   const uint32_t a_tx = kTileM * p.row_bytes;
-  const uint32_t b_tx = BN * p.row_bytes;
+  const uint32_t b_tx = (CG == 2 ? BN / 2 : BN) * p.row_bytes;   // B bytes that land in THIS CTA's smem
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -213,7 +221,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
         for (int it = 0; it < total_k;) {
           const int n_here = min(p.kps, total_k - it);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], n_here * (a_tx + b_tx));
+          if constexpr (CG == 2) {   // the leader's barrier counts the bytes of both CTAs
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2u * n_here * (a_tx + b_tx));
+          } else {
+            mbar_expect_tx(&full_bar[stage], n_here * (a_tx + b_tx));
+          }
           uint8_t* sbase = smem + static_cast<size_t>(stage) * stage_bytes;
           for (int j = 0; j < n_here; ++j) {
             const int kit = it + j;
@@ -223,6 +235,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             uint8_t* b_dst = a_dst + p.a_sub_bytes;
             const int cx = t.x0 + p.tap[tap][0], cy = t.y0 + p.tap[tap][1], cz = t.z0 + p.tap[tap][2];
             const int ac = a_c0 + kb * kb_elems;
+            if constexpr (CG == 2) {
+              if (p.rank == 4) tma_load_4d_2sm(a_dst, &p.tmA, &full_bar[stage], ac, cx, cy, t.b);
+              else tma_load_5d_2sm(a_dst, &p.tmA, &full_bar[stage], ac, cz, cx, cy, t.b);
+              if (p.b_banded) tma_load_3d_2sm(b_dst, &p.tmB, &full_bar[stage], 0, cta_rank * (BN / 2), kit);
+              else tma_load_3d_2sm(b_dst, &p.tmB, &full_bar[stage], kb * kb_elems, t.n0 + cta_rank * (BN / 2), tap);
+              continue;
+            }
             if (p.rank == 4) tma_load_4d(a_dst, &p.tmA, &full_bar[stage], ac, cx, cy, t.b);
             else tma_load_5d(a_dst, &p.tmA, &full_bar[stage], ac, cz, cx, cy, t.b);
             if constexpr (CL == 1) {
@@ -240,9 +259,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (one thread)
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_f16(kTileM, BN, p.ab_fmt);
+    // ------------------------------------------------------------ MMA issuer (one thread; leader CTA only for CG=2)
+    if ((CG == 1 || cta_rank == 0) && elect_one()) {
+      const uint32_t idesc = make_idesc_f16(CG * kTileM, BN, p.ab_fmt);
       const int mma_per_kit = p.row_bytes >> 5;  // 32 B (= 16 elements, UMMA_K) per instruction
       int stage = 0;
       uint32_t phase = 0;
@@ -261,15 +280,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             const uint64_t da = make_smem_desc(sbase + j * sub_bytes, p.row_bytes);
             const uint64_t db = make_smem_desc(sbase + j * sub_bytes + p.a_sub_bytes, p.row_bytes);
             for (int k = 0; k < mma_per_kit; ++k)
-              umma_f16<1>(d_tmem, da + 2 * k, db + 2 * k, idesc, (it + j > 0 || k > 0) ? 1u : 0u);
+              umma_f16<CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (it + j > 0 || k > 0) ? 1u : 0u);
           }
           // frees the smem slot (in every CTA of the cluster: their multicasts write into ours) once these MMAs retire
-          if constexpr (CL == 1) umma_commit<1>(&empty_bar[stage]);
+          if constexpr (CG == 2) umma_commit<2>(&empty_bar[stage]);
+          else if constexpr (CL == 1) umma_commit<1>(&empty_bar[stage]);
           else umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>((1u << CL) - 1u));
           it += n_here;
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit<1>(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        umma_commit<CG>(&tfull_bar[acc]);     // accumulator complete -> epilogue (of both CTAs for CG=2)
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -300,7 +320,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
         if (c + CW >= BN) {  // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) {
+            if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // leader owns the barrier
+            else mbar_arrive(&tempty_bar[acc]);
+          }
         }
         epilogue_chunk<CW>(p, r, t.n0 + c, off, row_valid);
       }
@@ -312,7 +335,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync();   // no CTA exits while a peer may still multicast into / commit to it
-  if (warp == 1) tmem_dealloc<1>(tmem_base, kTmemCols);
+  if (warp == 1) tmem_dealloc<CG>(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -337,6 +360,7 @@ static CUtensorMapSwizzle swizzle_of(int row_bytes) {
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+int g_default_cta_group = 2;                 // 2: paired tcgen05.mma.cta_group::2 tiles where the shape allows
 int g_default_cluster = 2;                   // B-multicast cluster size used when the descriptor says 0 (auto)
 std::atomic<long long> g_launch_count{0};   // kernels launched by this library (bench.py's gpu_launches)
 static int g_num_sms = 0;
@@ -349,17 +373,17 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int CL>
+template <int BN, int CL, int CG = 1>
 static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, CL, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if constexpr (CL == 1) {
-    igemm_kernel<BN, 1><<<grid, kNumThreads, smem, stream>>>(p);
+    igemm_kernel<BN, 1, 1><<<grid, kNumThreads, smem, stream>>>(p);
     return cudaGetLastError();
   } else {
     cudaLaunchConfig_t cfg;
@@ -375,7 +399,7 @@ static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaSt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, igemm_kernel<BN, CL>, p);
+    return cudaLaunchKernelEx(&cfg, igemm_kernel<BN, CL, CG>, p);
   }
 }
 
@@ -386,6 +410,12 @@ static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaSt
 extern "C" int rn_set_default_cluster(int c) {
   const int prev = rn::g_default_cluster;
   if (c == 1 || c == 2 || c == 4) rn::g_default_cluster = c;
+  return prev;
+}
+
+extern "C" int rn_set_default_cta_group(int g) {
+  const int prev = rn::g_default_cta_group;
+  if (g == 1 || g == 2) rn::g_default_cta_group = g;
   return prev;
 }
 
@@ -441,8 +471,22 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
     p.tap[t][2] = d->taps[3 * t + 2];
   }
   p.ab_fmt = d->fmt;
+  // launch shape: persistent grid, cluster size CL for the B multicast, CG = 2 for the paired (cta_group::2) MMA
+  int grid = num_sms();
+  if (d->max_ctas > 0 && d->max_ctas < grid) grid = d->max_ctas;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  const int m_tiles = p.num_tiles / p.n_tiles;
+  int CL = 1, CG = 1;
+  if (BN >= 128) {
+    const int want = d->cluster > 0 ? d->cluster : g_default_cluster;
+    const int want_cg = d->cta_group > 0 ? d->cta_group : g_default_cta_group;
+    if (want_cg == 2 && m_tiles % 2 == 0 && grid >= 2) { CL = 2; CG = 2; }
+    else if (want >= 4 && m_tiles % 4 == 0 && grid >= 4) CL = 4;
+    else if (want >= 2 && m_tiles % 2 == 0 && grid >= 2) CL = 2;
+  }
+  grid -= grid % CL;
   p.a_sub_bytes = kTileM * p.row_bytes;
-  p.b_sub_bytes = ((BN * p.row_bytes + 1023) / 1024) * 1024;
+  p.b_sub_bytes = (((BN / CG) * p.row_bytes + 1023) / 1024) * 1024;
   const int sub = p.a_sub_bytes + p.b_sub_bytes;
   const int total_k = p.ntaps * p.kblocks;
   p.kps = 32768 / sub;
@@ -455,18 +499,6 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   if (p.stages < 2) return -10;
   const size_t smem = static_cast<size_t>(p.stages) * p.kps * sub + 1024 + 256;
 
-  int grid = num_sms();
-  if (d->max_ctas > 0 && d->max_ctas < grid) grid = d->max_ctas;
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  // cluster size for the B multicast: CL consecutive M tiles share an N tile
-  const int m_tiles = p.num_tiles / p.n_tiles;
-  int CL = 1;
-  if (BN >= 128) {
-    const int want = d->cluster > 0 ? d->cluster : g_default_cluster;
-    if (want >= 4 && m_tiles % 4 == 0 && grid >= 4) CL = 4;
-    else if (want >= 2 && m_tiles % 2 == 0 && grid >= 2) CL = 2;
-  }
-  grid -= grid % CL;
 
   const CUtensorMapDataType dt = d->fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
@@ -492,13 +524,13 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   if (d->w_banded) {  // [ntaps*kblocks][BN][KB], identical for every N tile
     const cuuint64_t dims[3] = {(cuuint64_t)KB, (cuuint64_t)BN, (cuuint64_t)d->ntaps * p.kblocks};
     const cuuint64_t strides[2] = {(cuuint64_t)KB * 2, (cuuint64_t)KB * 2 * BN};
-    const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)(BN / CL), 1};
+    const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)(BN / CL), 1};  // CL == 2 also for the paired MMA
     r = enc(&p.tmB, dt, 3, const_cast<void*>(d->w_packed), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     const cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->cout_pad, (cuuint64_t)d->ntaps};
     const cuuint64_t strides[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * d->cout_pad};
-    const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)(BN / CL), 1};
+    const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)(BN / CL), 1};  // CL == 2 also for the paired MMA
     r = enc(&p.tmB, dt, 3, const_cast<void*>(d->w_packed), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
@@ -513,6 +545,10 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   p.vec_ok = strides8 && al16(d->out16) && al16(d->out32) && al16(d->residual) ? 1 : 0;
 
   cudaError_t e;
+  if (CG == 2) {
+    e = (BN == 256) ? launch_bn<256, 2, 2>(p, grid, smem, stream) : launch_bn<128, 2, 2>(p, grid, smem, stream);
+    return e == cudaSuccess ? 0 : static_cast<int>(e);
+  }
   switch (BN * 8 + CL) {
     case 256 * 8 + 1: e = launch_bn<256, 1>(p, grid, smem, stream); break;
     case 256 * 8 + 2: e = launch_bn<256, 2>(p, grid, smem, stream); break;

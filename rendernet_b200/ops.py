@@ -236,7 +236,7 @@ def conv2d_transpose(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, 
 
 def conv_igemm_raw(x, w_packed, bias, taps, ndim, B, H, W, D, Cin, Cout, cout_pad, out16=None, out32=None,
                    alpha=None, act=ACT_NONE, residual=None, o=None, fmt=0, force_bn=0, force_kps=0, max_ctas=0,
-                   cluster=0):
+                   cluster=0, cta_group=0):
     """Direct access to rn_conv_igemm for tests / tuning.  taps: list of (dx,dy,dz)."""
     n = len(taps)
     arr = (C.c_int8 * (3 * n))(*[v for t in taps for v in t])
@@ -257,6 +257,7 @@ def conv_igemm_raw(x, w_packed, bias, taps, ndim, B, H, W, D, Cin, Cout, cout_pa
     d.o_base, d.o_b, d.o_y, d.o_x, d.o_z = o
     d.fmt, d.force_bn, d.force_kps, d.max_ctas = fmt, force_bn, force_kps, max_ctas
     d.cluster = cluster
+    d.cta_group = cta_group
     check(lib.rn_conv_igemm(C.byref(d), _stream()), "rn_conv_igemm")
 
 

@@ -43,23 +43,23 @@ def main():
         for bn in (256, 128):
             if Cout % bn:
                 continue
-            for cl in (1, 2, 4):
+            for cl, cg in ((1, 1), (2, 1), (2, 2)):
                 for kps in (0, 2):
-                    if kps == 2 and bn == 256:
+                    if kps == 2 and bn == 256 and cg == 1:
                         continue
                     def run():
                         ops.conv_igemm_raw(x, L.w, L.bias, taps, 2, B, 64, 64, 1, Cin, Cout, L.cout_pad, out16=out,
-                                           alpha=L.alpha, act=1, force_bn=bn, force_kps=kps, cluster=cl)
+                                           alpha=L.alpha, act=1, force_bn=bn, force_kps=kps, cluster=cl, cta_group=cg)
                     try:
                         ms = timeit(run)
                     except Exception as e:
-                        print(f"[tune] {name} BN={bn} CL={cl} kps={kps}: FAILED {e}")
+                        print(f"[tune] {name} BN={bn} CL={cl} CG={cg} kps={kps}: FAILED {e}")
                         torch.cuda.synchronize()
                         continue
                     if ref is None:
                         ref = out.clone()
                     same = torch.equal(out, ref)
-                    print(f"[tune] {name} BN={bn} CL={cl} kps={kps or 'auto'}: {ms:.3f} ms {fl / ms / 1e9:7.1f} TFLOP/s same={same}",
+                    print(f"[tune] {name} BN={bn} CL={cl} CG={cg} kps={kps or 'auto'}: {ms:.3f} ms {fl / ms / 1e9:7.1f} TFLOP/s same={same}",
                           flush=True)
     # banded conv3d
     x = torch.randn(B, 64, 64, 32, 32, device=dev).half()
@@ -68,14 +68,16 @@ def main():
     al = torch.rand(32, device=dev) * 0.3
     out = torch.empty_like(x)
     ref = None
-    for cl in (1, 2, 4):
+    for cl, cg in ((1, 1), (2, 1), (2, 2)):
         lib.rn_set_default_cluster(cl)
+        lib.rn_set_default_cta_group(cg)
         ms = timeit(lambda: ops.conv3d_banded(x, Lb, act="prelu", alpha=al, out16=out))
         if ref is None:
             ref = out.clone()
-        print(f"[tune] res1 3^3 banded CL={cl}: {ms:.3f} ms {2.0 * B * 64 * 64 * 32 * 27 * 32 * 32 / ms / 1e9:.1f} TFLOP/s (useful) "
+        print(f"[tune] res1 3^3 banded CL={cl} CG={cg}: {ms:.3f} ms {2.0 * B * 64 * 64 * 32 * 27 * 32 * 32 / ms / 1e9:.1f} TFLOP/s (useful) "
               f"same={torch.equal(out, ref)}", flush=True)
     lib.rn_set_default_cluster(2)
+    lib.rn_set_default_cta_group(2)
 
 
 if __name__ == "__main__":

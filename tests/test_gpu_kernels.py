@@ -224,10 +224,11 @@ def test_conv_linearity_and_tile_schedule_full_size():
     close(y[:1], ref, rel=1.5e-3)
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("cluster,cta_group", [(1, 1), (2, 1), (4, 1), (2, 2)])
 @pytest.mark.parametrize("bn", [256, 128])
-def test_conv_cluster_multicast_bit_identical(cluster, bn):
-    """The weight-tile TMA multicast across a 2/4-CTA cluster must not change a single bit."""
+def test_conv_cluster_multicast_bit_identical(cluster, cta_group, bn):
+    """Neither the weight-tile TMA multicast across a 2/4-CTA cluster nor the paired cta_group::2 MMA (M = 256)
+    may change a single bit of the result."""
     ops = _ops()
     torch.manual_seed(1)
     B, H, W, Cin, Cout = 3, 32, 32, 128, 256                    # 24 M tiles: divisible by 4
@@ -240,7 +241,7 @@ def test_conv_cluster_multicast_bit_identical(cluster, bn):
                          L.alpha[:Cout].cpu().numpy()), rel=1.2e-3)
     out = torch.empty_like(ref)
     ops.conv_igemm_raw(x, L.w, L.bias, taps, 2, B, H, W, 1, Cin, Cout, L.cout_pad, out16=out, alpha=L.alpha, act=1,
-                       force_bn=bn, cluster=cluster)
+                       force_bn=bn, cluster=cluster, cta_group=cta_group)
     assert torch.equal(out, ref)
 
 
