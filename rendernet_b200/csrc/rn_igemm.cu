@@ -208,53 +208,54 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
   const uint32_t b_tx = (CG == 2 ? BN / 2 : BN) * p.row_bytes;   // B bytes that land in THIS CTA's smem
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (one thread).  The k loop is
+    // (tap, kblock)-nested so there is no division, and everything loop-invariant lives in registers: this
+    // thread's issue rate bounds the whole pipeline.
     if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
       constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
       constexpr int kBRows = BN / CL;               // rows of the B tile this CTA fetches (and multicasts)
+      const int kps = p.kps, kblocks = p.kblocks, ntaps = p.ntaps, stages = p.stages;
+      const bool rank5 = (p.rank == 5), banded = (p.b_banded != 0);
+      const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(full_bar);
+      const uint32_t a_sub = static_cast<uint32_t>(p.a_sub_bytes), sub_u = static_cast<uint32_t>(sub_bytes);
+      const uint32_t kit_tx = (CG == 2 ? 2u : 1u) * (a_tx + b_tx);
+      const uint32_t b_off = (CL > 1 && CG == 1) ? static_cast<uint32_t>(cta_rank * kBRows * p.row_bytes) : 0u;
+      const int b_row = (CG == 2) ? cta_rank * (BN / 2) : ((CL > 1) ? cta_rank * kBRows : 0);
+      const uint64_t mapA = reinterpret_cast<uint64_t>(&p.tmA), mapB = reinterpret_cast<uint64_t>(&p.tmB);
+      int stage = 0;
+      uint32_t phase = 0;
       for (int ct = cl_id; ct < num_ct; ct += ncl) {
-        const int tile = tile_of(ct);
-        const TileCoord t = decode_tile(p, tile, BN);
+        const TileCoord t = decode_tile(p, tile_of(ct), BN);
         const int a_c0 = p.a_c_base + (t.n0 / BN) * p.a_c_ntile;
-        for (int it = 0; it < total_k;) {
-          const int n_here = min(p.kps, total_k - it);
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if constexpr (CG == 2) {   // the leader's barrier counts the bytes of both CTAs
-            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2u * n_here * (a_tx + b_tx));
-          } else {
-            mbar_expect_tx(&full_bar[stage], n_here * (a_tx + b_tx));
-          }
-          uint8_t* sbase = smem + static_cast<size_t>(stage) * stage_bytes;
-          for (int j = 0; j < n_here; ++j) {
-            const int kit = it + j;
-            const int tap = kit / p.kblocks;
-            const int kb = kit - tap * p.kblocks;
-            uint8_t* a_dst = sbase + j * sub_bytes;
-            uint8_t* b_dst = a_dst + p.a_sub_bytes;
-            const int cx = t.x0 + p.tap[tap][0], cy = t.y0 + p.tap[tap][1], cz = t.z0 + p.tap[tap][2];
-            const int ac = a_c0 + kb * kb_elems;
-            if constexpr (CG == 2) {
-              if (p.rank == 4) tma_load_4d_2sm(a_dst, &p.tmA, &full_bar[stage], ac, cx, cy, t.b);
-              else tma_load_5d_2sm(a_dst, &p.tmA, &full_bar[stage], ac, cz, cx, cy, t.b);
-              if (p.b_banded) tma_load_3d_2sm(b_dst, &p.tmB, &full_bar[stage], 0, cta_rank * (BN / 2), kit);
-              else tma_load_3d_2sm(b_dst, &p.tmB, &full_bar[stage], kb * kb_elems, t.n0 + cta_rank * (BN / 2), tap);
-              continue;
+        const int bn0 = t.n0 + b_row;
+        int left = total_k, j = 0, n_here = 0, kit = 0;
+        uint32_t dst = 0, bar = 0;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          const int cx = t.x0 + p.tap[tap][0], cy = t.y0 + p.tap[tap][1], cz = t.z0 + p.tap[tap][2];
+          int ac = a_c0, bk = 0;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            if (j == 0) {
+              n_here = min(kps, left);
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              bar = full0 + 8u * stage;
+              if (CG == 1 || cta_rank == 0) mbar_expect_tx_a(bar, n_here * kit_tx);   // CG=2: leader counts both CTAs
+              dst = smem_base + static_cast<uint32_t>(stage) * stage_bytes;
             }
-            if (p.rank == 4) tma_load_4d(a_dst, &p.tmA, &full_bar[stage], ac, cx, cy, t.b);
-            else tma_load_5d(a_dst, &p.tmA, &full_bar[stage], ac, cz, cx, cy, t.b);
-            if constexpr (CL == 1) {
-              if (p.b_banded) tma_load_3d(b_dst, &p.tmB, &full_bar[stage], 0, 0, kit);
-              else tma_load_3d(b_dst, &p.tmB, &full_bar[stage], kb * kb_elems, t.n0, tap);
+            if (rank5) tma_a_5d<CG == 2>(dst, mapA, bar, ac, cz, cx, cy, t.b);
+            else tma_a_4d<CG == 2>(dst, mapA, bar, ac, cx, cy, t.b);
+            if constexpr (CL > 1 && CG == 1) {
+              if (banded) tma_a_3d_mc(dst + a_sub + b_off, mapB, bar, kMask, 0, b_row, kit);
+              else tma_a_3d_mc(dst + a_sub + b_off, mapB, bar, kMask, bk, bn0, tap);
             } else {
-              uint8_t* b_part = b_dst + cta_rank * kBRows * p.row_bytes;
-              if (p.b_banded) tma_load_3d_mc(b_part, &p.tmB, &full_bar[stage], kMask, 0, cta_rank * kBRows, kit);
-              else tma_load_3d_mc(b_part, &p.tmB, &full_bar[stage], kMask, kb * kb_elems, t.n0 + cta_rank * kBRows, tap);
+              if (banded) tma_a_3d<CG == 2>(dst + a_sub, mapB, bar, 0, b_row, kit);
+              else tma_a_3d<CG == 2>(dst + a_sub, mapB, bar, bk, bn0, tap);
+            }
+            ac += kb_elems; bk += kb_elems; ++kit; dst += sub_u;
+            if (++j == n_here) {
+              j = 0; left -= n_here;
+              if (++stage == stages) { stage = 0; phase ^= 1; }
             }
           }
-          it += n_here;
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -263,6 +264,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     if ((CG == 1 || cta_rank == 0) && elect_one()) {
       const uint32_t idesc = make_idesc_f16(CG * kTileM, BN, p.ab_fmt);
       const int mma_per_kit = p.row_bytes >> 5;  // 32 B (= 16 elements, UMMA_K) per instruction
+      const int kps = p.kps, stages = p.stages;
+      // descriptor = constant high part | (smem address >> 4); all operand buffers are 1024-byte aligned
+      const uint64_t desc_hi = make_smem_desc(0, p.row_bytes);
+      const uint32_t base16 = (smem_u32(smem) & 0x3FFFFu) >> 4;
+      const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4, sub16 = static_cast<uint32_t>(sub_bytes) >> 4;
+      const uint32_t a16 = static_cast<uint32_t>(p.a_sub_bytes) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -271,23 +278,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int it = 0; it < total_k;) {
-          const int n_here = min(p.kps, total_k - it);
+        uint32_t accum = 0;
+        for (int left = total_k; left > 0;) {
+          const int n_here = min(kps, left);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          uint64_t da = desc_hi | static_cast<uint64_t>(base16 + static_cast<uint32_t>(stage) * stage16);
           for (int j = 0; j < n_here; ++j) {
-            const uint64_t da = make_smem_desc(sbase + j * sub_bytes, p.row_bytes);
-            const uint64_t db = make_smem_desc(sbase + j * sub_bytes + p.a_sub_bytes, p.row_bytes);
-            for (int k = 0; k < mma_per_kit; ++k)
-              umma_f16<CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (it + j > 0 || k > 0) ? 1u : 0u);
+            const uint64_t db = da + a16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < mma_per_kit) {
+                umma_f16<CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                accum = 1;
+              }
+            }
+            da += sub16;
           }
           // frees the smem slot (in every CTA of the cluster: their multicasts write into ours) once these MMAs retire
           if constexpr (CG == 2) umma_commit<2>(&empty_bar[stage]);
           else if constexpr (CL == 1) umma_commit<1>(&empty_bar[stage]);
           else umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>((1u << CL) - 1u));
-          it += n_here;
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          left -= n_here;
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         umma_commit<CG>(&tfull_bar[acc]);     // accumulator complete -> epilogue (of both CTAs for CG=2)
         acc ^= 1;
