@@ -34,6 +34,7 @@ long long rn_launch_count(void);
 /* default cluster size (1, 2, 4) used by descriptors that leave `cluster` at 0; returns the previous value */
 int rn_set_default_cluster(int cluster);
 int rn_set_default_cta_group(int cta_group);
+int rn_set_default_kps(int kps); /* k-iterations per smem pipeline stage, 0 = heuristic (tuning aid) */
 
 /* ---- resampler ----------------------------------------------------------------------------------
  * Replaces tf_resampling + tf_interpolate + tf_voxel_meshgrid (tools/resampling_voxel_grid.py:381-614)

@@ -373,6 +373,7 @@ static CUtensorMapSwizzle swizzle_of(int row_bytes) {
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+int g_default_kps = 0;                       // k-iterations per pipeline stage override (0 = heuristic)
 int g_default_cta_group = 2;                 // 2: paired tcgen05.mma.cta_group::2 tiles where the shape allows
 int g_default_cluster = 2;                   // B-multicast cluster size used when the descriptor says 0 (auto)
 std::atomic<long long> g_launch_count{0};   // kernels launched by this library (bench.py's gpu_launches)
@@ -423,6 +424,12 @@ static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaSt
 extern "C" int rn_set_default_cluster(int c) {
   const int prev = rn::g_default_cluster;
   if (c == 1 || c == 2 || c == 4) rn::g_default_cluster = c;
+  return prev;
+}
+
+extern "C" int rn_set_default_kps(int k) {
+  const int prev = rn::g_default_kps;
+  if (k >= 0 && k <= 16) rn::g_default_kps = k;
   return prev;
 }
 
@@ -506,6 +513,7 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   if (p.kps < 1) p.kps = 1;
   if (p.kps > total_k) p.kps = total_k;
   if (d->force_kps > 0) p.kps = d->force_kps;
+  else if (g_default_kps > 0) p.kps = g_default_kps < total_k ? g_default_kps : total_k;
   const int budget = 232448 - 1024 - 256;
   p.stages = budget / (p.kps * sub);
   if (p.stages > 12) p.stages = 12;

@@ -41,11 +41,11 @@ def main():
         fl = 2.0 * B * 64 * 64 * Cin * Cout * k * k
         ref = None
         for bn in (256, 128):
-            if Cout % bn:
+            if Cout % bn or (bn == 128 and "--all" not in sys.argv):
                 continue
             for cl, cg in ((1, 1), (2, 1), (2, 2)):
-                for kps in (0, 2):
-                    if kps == 2 and bn == 256 and cg == 1:
+                for kps in (0, 2, 3):
+                    if (kps >= 2 and bn == 256 and cg == 1) or (kps == 3 and bn == 256):
                         continue
                     def run():
                         ops.conv_igemm_raw(x, L.w, L.bias, taps, 2, B, 64, 64, 1, Cin, Cout, L.cout_pad, out16=out,
@@ -68,16 +68,18 @@ def main():
     al = torch.rand(32, device=dev) * 0.3
     out = torch.empty_like(x)
     ref = None
-    for cl, cg in ((1, 1), (2, 1), (2, 2)):
+    for cl, cg, kps in ((1, 1, 0), (1, 1, 2), (1, 1, 3), (2, 1, 2), (2, 2, 0), (2, 2, 2), (2, 2, 3), (2, 2, 4)):
         lib.rn_set_default_cluster(cl)
         lib.rn_set_default_cta_group(cg)
+        lib.rn_set_default_kps(kps)
         ms = timeit(lambda: ops.conv3d_banded(x, Lb, act="prelu", alpha=al, out16=out))
         if ref is None:
             ref = out.clone()
-        print(f"[tune] res1 3^3 banded CL={cl} CG={cg}: {ms:.3f} ms {2.0 * B * 64 * 64 * 32 * 27 * 32 * 32 / ms / 1e9:.1f} TFLOP/s (useful) "
+        print(f"[tune] res1 3^3 banded CL={cl} CG={cg} kps={kps}: {ms:.3f} ms {2.0 * B * 64 * 64 * 32 * 27 * 32 * 32 / ms / 1e9:.1f} TFLOP/s (useful) "
               f"same={torch.equal(out, ref)}", flush=True)
     lib.rn_set_default_cluster(2)
     lib.rn_set_default_cta_group(2)
+    lib.rn_set_default_kps(0)
 
 
 if __name__ == "__main__":
