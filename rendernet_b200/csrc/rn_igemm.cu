@@ -509,14 +509,20 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   p.b_sub_bytes = (((BN / CG) * p.row_bytes + 1023) / 1024) * 1024;
   const int sub = p.a_sub_bytes + p.b_sub_bytes;
   const int total_k = p.ntaps * p.kblocks;
-  p.kps = 32768 / sub;
+  // k-iterations per stage: ~64 KB stages amortise the per-stage barrier round trips (measured: tune3/tune4 logs)
+  p.kps = (65536 + sub / 2) / sub;
   if (p.kps < 1) p.kps = 1;
+  if (p.kps > 8) p.kps = 8;
   if (p.kps > total_k) p.kps = total_k;
   if (d->force_kps > 0) p.kps = d->force_kps;
   else if (g_default_kps > 0) p.kps = g_default_kps < total_k ? g_default_kps : total_k;
   const int budget = 232448 - 1024 - 256;
   p.stages = budget / (p.kps * sub);
   if (p.stages > 12) p.stages = 12;
+  while (p.stages < 3 && p.kps > 1) {   // keep at least 3 stages in flight
+    --p.kps;
+    p.stages = budget / (p.kps * sub);
+  }
   if (p.stages < 2) return -10;
   const size_t smem = static_cast<size_t>(p.stages) * p.kps * sub + 1024 + 256;
 
