@@ -137,6 +137,19 @@ int rn_conv3d_direct(const void* x, int x_is_f32, const float* w, const float* b
                      void* out16, int B, int H, int W, int D, int Cin, int Cout, int k, int sy, int sx, int sz,
                      int fmt, void* stream);
 
+/* ---- texture decoder (BASELINE config 4; RenderNet_Texture_Face_Normal.py:34-46) ----------------------------
+ * fully_connected (tools/layer_util.py:311-343): y[B,N] = prelu(x[B,K] . w[K,N] + bias[N]; alpha[N]); fp32 in,
+ * 16-bit and/or fp32 out; B <= 32.  alpha NULL -> no activation. */
+int rn_fully_connected(const float* x, const float* w, const float* bias, const float* alpha, void* out16,
+                       float* out32, int B, int K, int N, int fmt, void* stream);
+/* conv3d / conv3d_transpose with <= 8 channels (layer_util.py:228-309), TF SAME, cubic kernel k, isotropic stride,
+ * + bias + PReLU.  w in TF layout: forward [k,k,k,Cin,Cout], transposed [k,k,k,Cout,Cin].  x [B,H,W,D,Cin]. */
+int rn_conv3d_small(const void* x, int x_is_f32, const float* w, const float* bias, const float* alpha, void* out16,
+                    float* out32, int B, int H, int W, int D, int Cin, int Cout, int k, int stride, int transposed,
+                    int fmt, void* stream);
+/* tf.concat([a, b], axis=4) of fp32 channel-last tensors with n points (RenderNet_Texture_Face_Normal.py:178) */
+int rn_concat_channels_f32(const float* a, const float* b, float* out, long long n, int Ca, int Cb, void* stream);
+
 /* ---- Phong composite (tools/Phong_shading.py:138-228, RenderNet_demo.py:54-58) -----------------------
  * img [B,H,W,3] fp32 normal map in [0,1]; light_dir [B,3]; light_col [B,3]; out_f32 [B,H,W,3] and/or
  * out_u8 = clip(255*out,0,255) as uint8.  background: 0 = "Black" (threshold 150), 1 = white (80). */

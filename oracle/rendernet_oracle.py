@@ -471,3 +471,148 @@ def np_phong_composite(images_in, light_dir, light_col, ambient_in, k_diffuse,
 def to_uint8(img_phong):
     """RenderNet_demo.py:58."""
     return np.clip(255.0 * img_phong, 0, 255).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------------
+# Texture + Normal network and texture decoder (BASELINE config 4)
+# RenderNet_Texture_Face_Normal.py:34-147, graph wiring :155-179
+# ----------------------------------------------------------------------------------
+def texture_layer_specs():
+    """(name, kind, filter shape, bias_init, alpha scope) of every variable group; scope quirks of the reference
+    (`e_conv7_1` block uses scope 'e_conv7_2', default 'conv2d_transpose' scopes) included."""
+    sp = []
+    te = "texture_encoder"
+    sp.append((f"{te}/e_tex_fc1/fully_connected", "fc", (199, 32 * 32 * 32 * 4), 0.001, f"{te}/e_tex_fc1"))
+    sp.append((f"{te}/e_tex_conv0/conv3d_transpose", "conv3d_transpose", (4, 4, 4, 4, 4), 0.001, f"{te}/e_tex_conv0"))
+    sp.append((f"{te}/e_tex_conv1/conv3d_transpose", "conv3d_transpose", (4, 4, 4, 8, 4), 0.001, f"{te}/e_tex_conv1"))
+    sp.append((f"{te}/e_tex_conv2/conv3d", "conv3d", (4, 4, 4, 8, 4), 0.001, f"{te}/e_tex_conv2"))
+    e = "encoder"
+    sp.append((f"{e}/e_conv1/e_conv1", "conv3d", (5, 5, 5, 5, 8), 0.001, f"{e}/e_conv1"))
+    sp.append((f"{e}/e_conv2/e_conv2", "conv3d", (3, 3, 3, 8, 16), 0.001, f"{e}/e_conv2"))
+    sp.append((f"{e}/e_conv3/e_conv3", "conv3d", (3, 3, 3, 16, 16), 0.001, f"{e}/e_conv3"))
+    for k in range(1, 11):
+        sp.append((f"{e}/res1_{k}/con1_3X3", "conv3d", (3, 3, 3, 16, 16), 0.001, f"{e}/res1_{k}"))
+        sp.append((f"{e}/res1_{k}/conv2_3x3", "conv3d", (3, 3, 3, 16, 16), 0.001, None))
+    sp.append((f"{e}/res1_skip/con1_3X3", "conv3d", (3, 3, 3, 16, 16), 0.001, None))
+    sp.append((f"{e}/projection_unit/Conv", "conv2d", (1, 1, 512, 512), 0.0, f"{e}/projection_unit"))
+    for k in range(1, 11):
+        sp.append((f"{e}/res2_{k}/con1_3X3", "conv2d", (3, 3, 512, 512), 0.0, f"{e}/res2_{k}"))
+        sp.append((f"{e}/res2_{k}/conv2_3x3", "conv2d", (3, 3, 512, 512), 0.0, None))
+    sp.append((f"{e}/res2_skip/con1_3X3", "conv2d", (3, 3, 512, 512), 0.001, None))          # layer_util.conv2d
+    sp.append((f"{e}/e_conv5/e_conv5", "conv2d", (4, 4, 512, 256), 0.001, f"{e}/e_conv5"))
+    for k in range(1, 6):
+        sp.append((f"{e}/res3_{k}/con1_3X3", "conv2d", (3, 3, 256, 256), 0.0, f"{e}/res3_{k}"))
+        sp.append((f"{e}/res3_{k}/conv2_3x3", "conv2d", (3, 3, 256, 256), 0.0, None))
+    sp.append((f"{e}/res3_skip/con1_3X3", "conv2d", (3, 3, 256, 256), 0.001, None))
+    for head, sfx in (("Image", "1"), ("Normal", "2")):
+        h = f"{e}/{head}"
+        sp.append((f"{h}/e_conv6_{sfx}/e_conv6_{sfx}", "conv2d", (4, 4, 256, 128), 0.001, f"{h}/e_conv6_{sfx}"))
+        if sfx == "1":   # Image head: scope quirks (:118-127)
+            sp.append((f"{h}/e_conv7_1/e_conv7_2", "conv2d_transpose", (4, 4, 64, 128), 0.001, f"{h}/e_conv7_1"))
+            sp.append((f"{h}/e_conv8_1/conv2d_transpose", "conv2d_transpose", (4, 4, 32, 64), 0.001, f"{h}/e_conv8_1"))
+            sp.append((f"{h}/e_conv9_1/conv2d_transpose", "conv2d_transpose", (4, 4, 16, 32), 0.001, f"{h}/e_conv9_1"))
+            sp.append((f"{h}/e_conv10_1/conv2d_transpose", "conv2d_transpose", (4, 4, 3, 16), 0.001, None))
+        else:
+            sp.append((f"{h}/e_conv7_2/e_conv7_2", "conv2d_transpose", (4, 4, 64, 128), 0.001, f"{h}/e_conv7_2"))
+            sp.append((f"{h}/e_conv8_2/e_conv8_2", "conv2d_transpose", (4, 4, 32, 64), 0.001, f"{h}/e_conv8_2"))
+            sp.append((f"{h}/e_conv9_2/e_conv9_2", "conv2d_transpose", (4, 4, 16, 32), 0.001, f"{h}/e_conv9_2"))
+            sp.append((f"{h}/e_conv10_2/e_conv10_2", "conv2d_transpose", (4, 4, 3, 16), 0.001, None))
+    return sp
+
+
+def init_texture_weights(seed: int = 0, alpha_range=(0.0, 0.0), gain: float = 1.0, bias_jitter: float = 0.0,
+                         decoder_std: float = 0.02) -> Dict[str, np.ndarray]:
+    """Seeded weights: xavier-uniform for the render net; N(0, 0.02) for the texture decoder (layer_util defaults)."""
+    rng = np.random.default_rng(seed)
+    W: Dict[str, np.ndarray] = {}
+    for name, kind, shape, bias0, alpha_scope in texture_layer_specs():
+        if name.startswith("texture_encoder"):
+            W[name + "/weights"] = (rng.standard_normal(shape) * decoder_std).astype(np.float32)
+        else:
+            fi, fo = _fans(kind, shape)
+            W[name + "/weights"] = xavier_uniform(rng, shape, fi, fo, gain)
+        nb = shape[-2] if kind in ("conv2d_transpose", "conv3d_transpose") else shape[-1]
+        bias = np.full((nb,), bias0, np.float32)
+        if bias_jitter > 0.0:
+            bias = bias + (rng.standard_normal(nb) * bias_jitter).astype(np.float32)
+        W[name + "/biases"] = bias
+        if alpha_scope is not None:
+            lo, hi = alpha_range
+            W[alpha_scope + "/alpha"] = (rng.uniform(lo, hi, size=nb).astype(np.float32)
+                                         if hi > lo else np.full((nb,), lo, np.float32))
+    return W
+
+
+def decoder_texture(z_in, W):
+    """RenderNet_Texture_Face_Normal.py:34-46: FC 199->32^3*4, T-conv 4^3 s1 4->4, T-conv 4^3 s2 4->8, conv 4^3 8->4."""
+    te = "texture_encoder"
+    g = lambda n: W[n]
+    z = _t(np.asarray(z_in, np.float32))
+    zP = prelu(fully_connected(z, g(f"{te}/e_tex_fc1/fully_connected/weights"), g(f"{te}/e_tex_fc1/fully_connected/biases")),
+               g(f"{te}/e_tex_fc1/alpha"))
+    x = zP.reshape(z.shape[0], 32, 32, 32, 4)
+    c0 = prelu(conv3d_transpose(x, g(f"{te}/e_tex_conv0/conv3d_transpose/weights"),
+                                g(f"{te}/e_tex_conv0/conv3d_transpose/biases"), (1, 1, 1)), g(f"{te}/e_tex_conv0/alpha"))
+    c1 = prelu(conv3d_transpose(c0, g(f"{te}/e_tex_conv1/conv3d_transpose/weights"),
+                                g(f"{te}/e_tex_conv1/conv3d_transpose/biases"), (2, 2, 2)), g(f"{te}/e_tex_conv1/alpha"))
+    c2 = prelu(conv3d(c1, g(f"{te}/e_tex_conv2/conv3d/weights"), g(f"{te}/e_tex_conv2/conv3d/biases"), (1, 1, 1)),
+               g(f"{te}/e_tex_conv2/alpha"))
+    return c2
+
+
+def rendernet_texture(models_in, W, return_stages: bool = False):
+    """RenderNet_Texture_Face_Normal.py:48-147 at inference.  models_in [B,H,W,128,5] -> (image, normal)."""
+    g = lambda n: W[n]
+    e = "encoder"
+    c3 = lambda x, s, st=(1, 1, 1): conv3d(x, g(s + "/weights"), g(s + "/biases"), st)
+    c2 = lambda x, s: conv2d(x, g(s + "/weights"), g(s + "/biases"))
+    ct = lambda x, s, k: conv2d_transpose(x, g(s + "/weights"), g(s + "/biases"), (k, k))
+    st = {}
+    x = _t(models_in).float()
+    enc1 = prelu(c3(x, f"{e}/e_conv1/e_conv1", (2, 2, 2)), g(f"{e}/e_conv1/alpha"))
+    enc2 = prelu(c3(enc1, f"{e}/e_conv2/e_conv2", (1, 1, 2)), g(f"{e}/e_conv2/alpha"))
+    enc3 = prelu(c3(enc2, f"{e}/e_conv3/e_conv3"), g(f"{e}/e_conv3/alpha"))
+    h = enc3
+    for k in range(1, 11):
+        t = prelu(c3(h, f"{e}/res1_{k}/con1_3X3"), g(f"{e}/res1_{k}/alpha"))
+        h = c3(t, f"{e}/res1_{k}/conv2_3x3") + h
+    enc3_skip = c3(h, f"{e}/res1_skip/con1_3X3") + enc3
+    enc4 = projection_unit(enc3_skip, g(f"{e}/projection_unit/Conv/weights"), g(f"{e}/projection_unit/Conv/biases"),
+                           g(f"{e}/projection_unit/alpha"))
+    h = enc4
+    for k in range(1, 11):
+        t = prelu(c2(h, f"{e}/res2_{k}/con1_3X3"), g(f"{e}/res2_{k}/alpha"))
+        h = c2(t, f"{e}/res2_{k}/conv2_3x3") + h
+    enc4_skip = c2(h, f"{e}/res2_skip/con1_3X3") + enc4
+    enc5 = prelu(c2(enc4_skip, f"{e}/e_conv5/e_conv5"), g(f"{e}/e_conv5/alpha"))
+    h = enc5
+    for k in range(1, 6):
+        t = prelu(c2(h, f"{e}/res3_{k}/con1_3X3"), g(f"{e}/res3_{k}/alpha"))
+        h = c2(t, f"{e}/res3_{k}/conv2_3x3") + h
+    enc5_skip = c2(h, f"{e}/res3_skip/con1_3X3") + enc5
+    st.update(enc3=enc3, enc3_skip=enc3_skip, enc4=enc4, enc4_skip=enc4_skip, enc5_skip=enc5_skip)
+    outs = []
+    for head, sfx, names in (("Image", "1", ("e_conv7_1/e_conv7_2", "e_conv8_1/conv2d_transpose", "e_conv9_1/conv2d_transpose",
+                                              "e_conv10_1/conv2d_transpose")),
+                             ("Normal", "2", ("e_conv7_2/e_conv7_2", "e_conv8_2/e_conv8_2", "e_conv9_2/e_conv9_2",
+                                              "e_conv10_2/e_conv10_2"))):
+        hh = f"{e}/{head}"
+        a6 = prelu(c2(enc5_skip, f"{hh}/e_conv6_{sfx}/e_conv6_{sfx}"), g(f"{hh}/e_conv6_{sfx}/alpha"))
+        a7 = prelu(ct(a6, f"{hh}/{names[0]}", 2), g(f"{hh}/e_conv7_{sfx}/alpha"))
+        a8 = prelu(ct(a7, f"{hh}/{names[1]}", 2), g(f"{hh}/e_conv8_{sfx}/alpha"))
+        a9 = prelu(ct(a8, f"{hh}/{names[2]}", 2), g(f"{hh}/e_conv9_{sfx}/alpha"))
+        logits = ct(a9, f"{hh}/{names[3]}", 1)
+        st[f"logits_{head}"] = logits
+        outs.append(torch.sigmoid(logits))
+    if return_stages:
+        return outs[0], outs[1], st
+    return outs[0], outs[1]
+
+
+def render_forward_texture(voxel, texture_in, view_params, W):
+    """Graph of RenderNet_Texture_Face_Normal.py:155-179 at inference."""
+    rot = transform_voxel_to_match_image(rotation_resampling(voxel, view_params))
+    tex = decoder_texture(texture_in, W).numpy()
+    tex_rot = transform_voxel_to_match_image(rotation_resampling(tex, view_params))
+    x = np.ascontiguousarray(np.concatenate([rot, tex_rot], axis=4))
+    return rendernet_texture(x, W)

@@ -291,6 +291,129 @@ __global__ void __launch_bounds__(256) conv3d_direct_kernel(const void* __restri
   for (int v = 0; v < COUT / 8; ++v) op[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
 }
 
+
+// ------------------------------------------------------------------------------------------ texture decoder (config 4)
+// fully_connected (tools/layer_util.py:311-343): y[b][n] = act(sum_k x[b][k] w[k][n] + bias[n]); w is TF [in,out].
+// One thread per output column, weights streamed once (coalesced across n), x staged in shared memory.
+template <int BMAX>
+__global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                 const float* __restrict__ bias, const float* __restrict__ alpha,
+                                                 uint16_t* __restrict__ out16, float* __restrict__ out32, int B, int K,
+                                                 int N, int fmt) {
+  extern __shared__ float xs[];  // [B][K]
+  for (int i = threadIdx.x; i < B * K; i += blockDim.x) xs[i] = x[i];
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc[BMAX];
+#pragma unroll
+  for (int b = 0; b < BMAX; ++b) acc[b] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float wv = __ldg(w + static_cast<size_t>(k) * N + n);
+#pragma unroll
+    for (int b = 0; b < BMAX; ++b)
+      if (b < B) acc[b] = fmaf(xs[b * K + k], wv, acc[b]);
+  }
+  const float bv = bias != nullptr ? __ldg(bias + n) : 0.f;
+  const float av = alpha != nullptr ? __ldg(alpha + n) : 1.f;
+#pragma unroll
+  for (int b = 0; b < BMAX; ++b) {
+    if (b < B) {
+      float v = acc[b] + bv;
+      if (alpha != nullptr) v = fmaxf(v, 0.f) + av * fminf(v, 0.f);
+      const size_t o = static_cast<size_t>(b) * N + n;
+      if (out32 != nullptr) out32[o] = v;
+      if (out16 != nullptr) {
+        if (fmt == 0) { __half h = __float2half_rn(v); out16[o] = *reinterpret_cast<uint16_t*>(&h); }
+        else { __nv_bfloat16 h = __float2bfloat16_rn(v); out16[o] = *reinterpret_cast<uint16_t*>(&h); }
+      }
+    }
+  }
+}
+
+// Thin 3-D (transposed) convolution with tiny channel counts (<= 8), TF SAME, + bias + PReLU; fp32 or 16-bit in,
+// 16-bit and/or fp32 out.  One thread per output voxel.  transposed: out[o] += x[i] w[k][co][ci], o = i*s + k - pb
+// (tools/layer_util.py:269-309); forward: out[o] = sum x[o*s + k - pb] w[k][ci][co] (:228-265).
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) conv3d_small_kernel(const void* __restrict__ xv, int x_is_f32,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           const float* __restrict__ alpha, uint16_t* __restrict__ out16,
+                                                           float* __restrict__ out32, int B, int H, int W, int D, int Ho,
+                                                           int Wo, int Do, int K, int s, int pb, int transposed, int fmt) {
+  extern __shared__ float wsm[];  // K^3 * CIN * COUT
+  const int nw = K * K * K * CIN * COUT;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  const long long total = static_cast<long long>(B) * Ho * Wo * Do;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int oz = static_cast<int>(idx % Do);
+  const int ox = static_cast<int>((idx / Do) % Wo);
+  const int oy = static_cast<int>((idx / (static_cast<long long>(Do) * Wo)) % Ho);
+  const int b = static_cast<int>(idx / (static_cast<long long>(Do) * Wo * Ho));
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  for (int ky = 0; ky < K; ++ky) {
+    int iy;
+    if (transposed) { const int n = oy + pb - ky; if (n < 0 || n % s != 0) continue; iy = n / s; }
+    else iy = oy * s + ky - pb;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < K; ++kx) {
+      int ix;
+      if (transposed) { const int n = ox + pb - kx; if (n < 0 || n % s != 0) continue; ix = n / s; }
+      else ix = ox * s + kx - pb;
+      if (ix < 0 || ix >= W) continue;
+      for (int kz = 0; kz < K; ++kz) {
+        int iz;
+        if (transposed) { const int n = oz + pb - kz; if (n < 0 || n % s != 0) continue; iz = n / s; }
+        else iz = oz * s + kz - pb;
+        if (iz < 0 || iz >= D) continue;
+        const size_t xi = (((static_cast<size_t>(b) * H + iy) * W + ix) * D + iz) * CIN;
+        float xin[CIN];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          if (x_is_f32) xin[ci] = __ldg(static_cast<const float*>(xv) + xi + ci);
+          else {
+            const uint16_t u = __ldg(static_cast<const uint16_t*>(xv) + xi + ci);
+            xin[ci] = fmt == 0 ? __half2float(*reinterpret_cast<const __half*>(&u))
+                               : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
+          }
+        }
+        const float* wt = wsm + ((ky * K + kx) * K + kz) * CIN * COUT;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+          for (int co = 0; co < COUT; ++co)
+            acc[co] = fmaf(xin[ci], transposed ? wt[co * CIN + ci] : wt[ci * COUT + co], acc[co]);
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) {
+    float v = acc[co] + (bias != nullptr ? __ldg(bias + co) : 0.f);
+    if (alpha != nullptr) v = fmaxf(v, 0.f) + __ldg(alpha + co) * fminf(v, 0.f);
+    const size_t o = static_cast<size_t>(idx) * COUT + co;
+    if (out32 != nullptr) out32[o] = v;
+    if (out16 != nullptr) {
+      if (fmt == 0) { __half h = __float2half_rn(v); out16[o] = *reinterpret_cast<uint16_t*>(&h); }
+      else { __nv_bfloat16 h = __float2bfloat16_rn(v); out16[o] = *reinterpret_cast<uint16_t*>(&h); }
+    }
+  }
+}
+
+// channel concat of two fp32 channel-last tensors: out[..., 0:Ca] = a, out[..., Ca:Ca+Cb] = b
+__global__ void concat_channels_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                       long long n, int Ca, int Cb) {
+  const int C = Ca + Cb;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n * C;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / C;
+    const int c = static_cast<int>(i % C);
+    out[i] = c < Ca ? a[p * Ca + c] : b[p * Cb + (c - Ca)];
+  }
+}
+
 // ------------------------------------------------------------------------------------------ Phong
 __global__ void phong_kernel(const float* __restrict__ img, const float* __restrict__ light_dir,
                              const float* __restrict__ light_col, float ambient, float k_diffuse, int white,
@@ -589,6 +712,67 @@ extern "C" int rn_conv3d_banded_same(const void* x, const void* w_banded, const 
   d.a_c_ntile = (128 / Cout) * Cin;                 // each N tile advances 128/Cout depths
   d.w_banded = 1;
   return rn_conv_igemm(&d, stream);
+}
+
+
+// ---------------------------------------------------------------------------------- texture decoder ops
+extern "C" int rn_fully_connected(const float* x, const float* w, const float* bias, const float* alpha, void* out16,
+                                  float* out32, int B, int K, int N, int fmt, void* stream) {
+  if (!x || !w || (!out16 && !out32) || B < 1 || K < 1 || N < 1) return -1;
+  if (B > 32) return -2;
+  const size_t smem = static_cast<size_t>(B) * K * sizeof(float);
+  if (smem > 48 * 1024) return -3;
+  const int grid = (N + 255) / 256;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint16_t* o16 = static_cast<uint16_t*>(out16);
+  if (B <= 8) fc_kernel<8><<<grid, 256, smem, st>>>(x, w, bias, alpha, o16, out32, B, K, N, fmt);
+  else fc_kernel<32><<<grid, 256, smem, st>>>(x, w, bias, alpha, o16, out32, B, K, N, fmt);
+  RN_COUNT_LAUNCH();
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_conv3d_small(const void* x, int x_is_f32, const float* w, const float* bias, const float* alpha,
+                               void* out16, float* out32, int B, int H, int W, int D, int Cin, int Cout, int k,
+                               int stride, int transposed, int fmt, void* stream) {
+  if (!x || !w || (!out16 && !out32) || k < 1 || stride < 1) return -1;
+  int Ho, Wo, Do, pb;
+  if (transposed) {
+    Ho = H * stride; Wo = W * stride; Do = D * stride;
+    pb = (k - stride > 0 ? k - stride : 0) / 2;
+  } else {
+    int p2, p3;
+    same_pad(H, k, stride, &Ho, &pb);
+    same_pad(W, k, stride, &Wo, &p2);
+    same_pad(D, k, stride, &Do, &p3);
+    if (p2 != pb || p3 != pb) return -2;  // cubic inputs only
+  }
+  const long long total = static_cast<long long>(B) * Ho * Wo * Do;
+  const int grid = static_cast<int>((total + 255) / 256);
+  const size_t smem = static_cast<size_t>(k) * k * k * Cin * Cout * sizeof(float);
+  if (smem > 48 * 1024) return -3;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint16_t* o16 = static_cast<uint16_t*>(out16);
+#define RN_SMALL(CI, CO)                                                                                            \
+  conv3d_small_kernel<CI, CO><<<grid, 256, smem, st>>>(x, x_is_f32, w, bias, alpha, o16, out32, B, H, W, D, Ho, Wo, \
+                                                        Do, k, stride, pb, transposed, fmt)
+  if (Cin == 4 && Cout == 4) RN_SMALL(4, 4);
+  else if (Cin == 4 && Cout == 8) RN_SMALL(4, 8);
+  else if (Cin == 8 && Cout == 4) RN_SMALL(8, 4);
+  else if (Cin == 2 && Cout == 3) RN_SMALL(2, 3);
+  else return -4;
+#undef RN_SMALL
+  RN_COUNT_LAUNCH();
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_concat_channels_f32(const float* a, const float* b, float* out, long long n, int Ca, int Cb,
+                                      void* stream) {
+  if (!a || !b || !out || n < 0 || Ca < 1 || Cb < 1) return -1;
+  if (n == 0) return 0;
+  concat_channels_kernel<<<grid_for(n * (Ca + Cb), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n, Ca,
+                                                                                                     Cb);
+  RN_COUNT_LAUNCH();
+  return static_cast<int>(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------------- thin conv3d

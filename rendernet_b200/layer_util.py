@@ -94,7 +94,7 @@ def lrelu(x, leak=0.2, name="lrelu"):
 
 def prelu(x, trainable=True, alpha=None):
     """layer_util.py:27-45: max(0,x) + alpha*min(0,x); `alpha` variable of shape [channels], init 0."""
-    nch = x.shape[-1]
+    nch = int(x.shape[-1])
     if alpha is None:
         alpha = tf.get_variable(name='alpha', shape=[nch], dtype=tf.float32,
                                 initializer=tf.constant_initializer(0.0), trainable=trainable)
@@ -242,14 +242,49 @@ def conv3d(input_, num_outputs, pad="SAME", reuse=False, kernel_size=[4, 4, 4], 
 def conv3d_transpose(x, num_output, kernel_size=(4, 4), stride=(1, 1), pad='SAME', if_bias=True, reuse=False,
                      scope="conv3d_transpose", trainable=True, weight_initializer=None, bias_initializer=None,
                      weight_initializer_type=None):
-    """layer_util.py:269-309 (texture decoder only, BASELINE config 4)."""
-    raise NotImplementedError("conv3d_transpose (texture decoder) is scheduled after the Shader path; see DESIGN.md")
+    """layer_util.py:269-309: tf.nn.conv3d_transpose SAME, out = in*stride, filter [k,k,k,Cout,Cin] (texture
+    decoder, BASELINE config 4).  Thin channels -> CUDA-core kernel, fp32 storage."""
+    _check_same(pad)
+    if len(set(stride)) != 1 or len(set(kernel_size)) != 1:
+        raise NotImplementedError("conv3d_transpose: cubic kernels / isotropic strides only")
+    cin = int(x.shape[-1])
+    with tf.variable_scope(scope, reuse=reuse):
+        w = _weights_var(list(kernel_size) + [int(num_output), cin], weight_initializer, weight_initializer_type,
+                         trainable)
+        b = None
+        if if_bias:
+            b = bias_variable([int(num_output)], trainable=trainable, bias_initializer=bias_initializer)
+    return _deferred_small3d(x, w, b, int(stride[0]), True)
 
 
 def fully_connected(input_, output_size, reuse=False, scope='fully_connected', if_bias=True, weight_initializer=None,
                     bias_initializer=None, trainable=True, weight_initializer_type=None):
-    """layer_util.py:311-343 (texture decoder only, BASELINE config 4)."""
-    raise NotImplementedError("fully_connected (texture decoder) is scheduled after the Shader path; see DESIGN.md")
+    """layer_util.py:311-343: input_ @ weights[in,out] + biases (texture decoder, BASELINE config 4)."""
+    xin = realize(input_)
+    if not isinstance(xin, torch.Tensor):
+        xin = torch.as_tensor(np.asarray(xin, np.float32))
+    k_in = int(xin.shape[1])
+    with tf.variable_scope(scope, reuse=reuse):
+        if weight_initializer is None:
+            matrix = tf.get_variable("weights", [k_in, int(output_size)],
+                                     initializer=weight_initializer_type or _RANDN002(), dtype=tf.float32,
+                                     trainable=trainable)
+        else:
+            matrix = tf.get_variable("weights", initializer=weight_initializer, dtype=tf.float32, trainable=trainable)
+        b = None
+        if if_bias:
+            b = bias_variable([int(output_size)], bias_initializer, trainable=trainable)
+
+    def run(act, alpha, residual, want32):
+        xt = xin.to(device=_store().device, dtype=torch.float32).contiguous()
+        wd = _dev_f32(matrix)
+        y = ops.fully_connected(xt, wd, _dev_vec(b) if b is not None else None,
+                                _alpha_arg(alpha, None) if act == "prelu" else None, want32=True)
+        if act not in (None, "prelu") or residual is not None:
+            raise NotImplementedError("fully_connected: only a fused PReLU epilogue is supported")
+        return y
+
+    return Deferred(run, (xin.shape[0], int(output_size)), torch.float32)
 
 
 # ------------------------------------------------------------------------------------------ slim look-alikes
@@ -329,7 +364,47 @@ def _deferred_conv(kind, x, w, b, stride):
     return Deferred(run, oshape, tf.COMPUTE_DTYPE)
 
 
+def _dev_f32(v: torch.Tensor) -> torch.Tensor:
+    st = _store()
+    key = ("w32", getattr(v, "_rn_name", id(v)))
+    d = st.packed.get(key)
+    if d is None:
+        d = v.to(device=st.device, dtype=torch.float32).contiguous()
+        st.packed[key] = d
+    return d
+
+
+def _deferred_small3d(x, w, b, stride, transposed):
+    """Thin-channel conv3d / conv3d_transpose (rn_conv3d_small), fp32 storage."""
+    xin = x
+    cout = int(w.shape[3] if transposed else w.shape[4])
+    if transposed:
+        oshape = (x.shape[0], x.shape[1] * stride, x.shape[2] * stride, x.shape[3] * stride, cout)
+    else:
+        oshape = (x.shape[0], -(-x.shape[1] // stride), -(-x.shape[2] // stride), -(-x.shape[3] // stride), cout)
+
+    def run(act, alpha, residual, want32):
+        xt = realize(xin)
+        if not xt.is_cuda:
+            xt = xt.to(_store().device)
+        y = ops.conv3d_small(xt.contiguous(), _dev_f32(w), _dev_vec(b) if b is not None else None,
+                             _alpha_arg(alpha, cout) if act == "prelu" else None, stride, transposed, want32=True)
+        if act not in (None, "prelu") or residual is not None:
+            raise NotImplementedError("thin conv3d: only a fused PReLU epilogue is supported")
+        return y
+
+    return Deferred(run, oshape, torch.float32)
+
+
+_DIRECT3D = {(1, 8, 5): True, (5, 8, 5): True, (2, 8, 3): True, (8, 16, 3): False, (8, 8, 3): False}  # needs fp32 input?
+
+
 def _deferred_direct3d(x, w, b, stride):
+    key = (int(w.shape[3]), int(w.shape[4]), int(w.shape[0]))
+    if key not in _DIRECT3D:
+        if len(set(stride)) != 1:
+            raise NotImplementedError(f"conv3d {key} with stride {stride} has no kernel")
+        return _deferred_small3d(x, w, b, int(stride[0]), False)
     xin = x
     oshape = (x.shape[0], -(-x.shape[1] // stride[0]), -(-x.shape[2] // stride[1]), -(-x.shape[3] // stride[2]),
               w.shape[-1])

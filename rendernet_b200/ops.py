@@ -337,3 +337,51 @@ def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], alpha: Optional[torc
     check(lib.rn_bias_act_16(x.data_ptr(), _ptr(bias), _ptr(alpha), a, _ptr(residual), _ptr(out16), _ptr(out32),
                              x.numel(), C_, fmt_of(x.dtype), _stream()), "rn_bias_act_16")
     return out32 if want32 else out16
+
+
+# --------------------------------------------------------------------------------------- texture decoder (config 4)
+def fully_connected(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], alpha: Optional[torch.Tensor],
+                    want32: bool = True, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """y = prelu(x @ w + bias; alpha).  x [B,K] fp32, w [K,N] fp32 (TF layout) -> [B,N] fp32 (or 16-bit)."""
+    x = _cuda(x, torch.float32)
+    w = _cuda(w, torch.float32)
+    B, K = x.shape
+    N = w.shape[1]
+    out = torch.empty((B, N), device=x.device, dtype=torch.float32 if want32 else dtype)
+    check(lib.rn_fully_connected(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(alpha), None if want32 else out.data_ptr(),
+                                 out.data_ptr() if want32 else None, B, K, N, fmt_of(dtype), _stream()),
+          "rn_fully_connected")
+    return out
+
+
+def conv3d_small(x: torch.Tensor, w_tf: torch.Tensor, bias: Optional[torch.Tensor], alpha: Optional[torch.Tensor],
+                 stride: int, transposed: bool, want32: bool = True, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """Thin (<= 8 channel) conv3d / conv3d_transpose, TF SAME, + bias + PReLU.  x [B,H,W,D,Cin] fp32 or 16-bit;
+    w_tf fp32 [k,k,k,Cin,Cout] (forward) or [k,k,k,Cout,Cin] (transposed)."""
+    x = _cuda(x)
+    w_tf = _cuda(w_tf, torch.float32)
+    B, H, W, D, Cin = x.shape
+    k = w_tf.shape[0]
+    Cout = w_tf.shape[3] if transposed else w_tf.shape[4]
+    if transposed:
+        oshape = (B, H * stride, W * stride, D * stride, Cout)
+    else:
+        oshape = (B, -(-H // stride), -(-W // stride), -(-D // stride), Cout)
+    out = torch.empty(oshape, device=x.device, dtype=torch.float32 if want32 else dtype)
+    check(lib.rn_conv3d_small(x.data_ptr(), 1 if x.dtype == torch.float32 else 0, w_tf.data_ptr(), _ptr(bias),
+                              _ptr(alpha), None if want32 else out.data_ptr(), out.data_ptr() if want32 else None,
+                              B, H, W, D, Cin, Cout, k, stride, 1 if transposed else 0,
+                              fmt_of(dtype if x.dtype == torch.float32 else x.dtype), _stream()), "rn_conv3d_small")
+    return out
+
+
+def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """tf.concat([a, b], axis=-1) for fp32 channel-last tensors."""
+    a = _cuda(a, torch.float32)
+    b = _cuda(b, torch.float32)
+    assert a.shape[:-1] == b.shape[:-1]
+    Ca, Cb = a.shape[-1], b.shape[-1]
+    out = torch.empty(tuple(a.shape[:-1]) + (Ca + Cb,), device=a.device, dtype=torch.float32)
+    check(lib.rn_concat_channels_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel() // Ca, Ca, Cb, _stream()),
+          "rn_concat_channels_f32")
+    return out

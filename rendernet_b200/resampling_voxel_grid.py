@@ -86,6 +86,8 @@ class ResampledGrid:
 
 
 def _to_cuda_f32(x) -> torch.Tensor:
+    if hasattr(x, "realize"):          # deferred conv output (texture decoder)
+        x = x.realize()
     if not isinstance(x, torch.Tensor):
         x = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32)))
     return x.to(device="cuda", dtype=torch.float32).contiguous()

@@ -147,6 +147,41 @@ def main():
                         var_names=names, var_shapes=shapes,
                         bias_init_names=np.array(sorted(biases0)), bias_init_vals=np.array([biases0[k] for k in sorted(biases0)]))
 
+    # ------------------------------------------------------------------ Texture + Normal net and texture decoder
+    tex_path = os.path.join(REF, "RenderNet_Texture_Face_Normal.py")
+    nst = dict(tf=tf, slim=sys.modules["tensorflow.contrib.slim"], is_training=tf.constant(False),
+               keep_prob=layer_util.keep_prob, conv3d=layer_util.conv3d, conv2d=layer_util.conv2d,
+               conv2d_transpose=layer_util.conv2d_transpose, conv3d_transpose=layer_util.conv3d_transpose,
+               fully_connected=layer_util.fully_connected, prelu=layer_util.prelu,
+               res_block_2d=layer_util.res_block_2d, res_block_3d=layer_util.res_block_3d,
+               projection_unit=layer_util.projection_unit)
+    decoder_texture = _lift_function(tex_path, "decoder_texture", nst)
+    RenderNetTex = _lift_function(tex_path, "RenderNet", nst)
+    Wt = orc.init_texture_weights(seed=4321, alpha_range=(0.05, 0.3), gain=1.0, bias_jitter=0.02)
+    z_in = np.random.default_rng(2).standard_normal((1, 199)).astype(np.float32)
+    stdout, sys.stdout = sys.stdout, devnull
+    try:
+        tf1_shim.reset(provided=Wt)
+        tex_dec = np.asarray(decoder_texture(tf.constant(z_in)))                       # [1,64,64,64,4]
+        # graph wiring of :155-179 on the chair grid: resample both, concat on the channel axis, crop a patch
+        _, _, _, tex_rot = ref_resample(tex_dec, pose, 64, 128)
+        x5 = np.concatenate([n, tex_rot], axis=4)
+        patch5 = np.ascontiguousarray(x5[:, 56:72, 56:72])
+        img_t, nrm_t = RenderNetTex(tf.constant(patch5), prob=0.75)
+        used_t = tf1_shim.created_variables()
+    finally:
+        sys.stdout = stdout
+    assert set(used_t) == set(Wt), sorted(set(used_t) ^ set(Wt))[:10]
+    np.savez_compressed(os.path.join(HERE, "texture_patch.npz"), weight_seed=np.int64(4321), alpha_range=np.array([0.05, 0.3]),
+                        gain=np.float64(1.0), bias_jitter=np.float64(0.02), z_in=z_in,
+                        decoder_sub=tex_dec[:, ::4, ::4, ::4].astype(np.float32),
+                        decoder_sum=np.float64(tex_dec.sum(dtype=np.float64)),
+                        decoder_abs_sum=np.float64(np.abs(tex_dec).sum(dtype=np.float64)),
+                        patch_slice=np.array([56, 72, 56, 72]),
+                        image=np.asarray(img_t, np.float32), normal=np.asarray(nrm_t, np.float32),
+                        var_names=np.array(sorted(used_t.keys())),
+                        var_shapes=np.array([";".join(map(str, used_t[k].shape)) for k in sorted(used_t.keys())]))
+
     # ------------------------------------------------------------------ Phong composite
     rng = np.random.default_rng(11)
     nm = rng.random((2, 16, 16, 3)).astype(np.float32)

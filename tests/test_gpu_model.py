@@ -43,3 +43,35 @@ def test_shader_patch_matches_reference_golden(golden_dir):
     e, s = _rel(logit, st["logits"])
     print("logits err", e, "scale", s)
     assert e < 2e-2 * s
+
+
+def test_texture_model_matches_reference_golden(golden_dir):
+    """BASELINE config 4 (reduced H,W): texture decoder + resample (C=1 and C=4) + concat + Texture/Normal RenderNet
+    through the CUDA path vs the fixture frozen from the reference's own Python.  Bar: 1e-3 max-abs on both images."""
+    from rendernet_b200 import ops, tfcompat as tf
+    from rendernet_b200.RenderNet_Texture_Face_Normal import RenderNet, decoder_texture
+    from rendernet_b200.model_util import tf_transform_voxel_to_match_image
+    from rendernet_b200.resampling_voxel_grid import tf_rotation_resampling
+    g = np.load(os.path.join(golden_dir, "texture_patch.npz"))
+    r = np.load(os.path.join(golden_dir, "resample.npz"))
+    bv = np.load(os.path.join(golden_dir, "binvox.npz"))
+    chair = np.unpackbits(bv["chair_bits"]).reshape(1, 64, 64, 64, 1).astype(np.float32)
+    W = orc.init_texture_weights(seed=int(g["weight_seed"]), alpha_range=tuple(g["alpha_range"]),
+                                 gain=float(g["gain"]), bias_jitter=float(g["bias_jitter"]))
+    tf.reset_default_graph()
+    tf.load_weight_dict(W)
+    tex = decoder_texture(torch.from_numpy(g["z_in"]).cuda())
+    tex_t = tf.realize(tex)
+    assert tuple(tex_t.shape) == (1, 64, 64, 64, 4)
+    err, _ = _rel(tex_t[:, ::4, ::4, ::4], g["decoder_sub"])
+    print("texture decoder max-abs err:", err)
+    assert err < 1e-5
+    pose = r["chair_pose"]
+    n = tf_transform_voxel_to_match_image(tf_rotation_resampling(chair, pose))
+    tr = tf_transform_voxel_to_match_image(tf_rotation_resampling(tex_t, pose))
+    x5 = ops.concat_channels(n, tr)
+    a, b, c, d = g["patch_slice"]
+    img, nrm = RenderNet(x5[:, a:b, c:d].contiguous())
+    e1, _ = _rel(img, g["image"]); e2, _ = _rel(nrm, g["normal"])
+    print("texture net image/normal max-abs err:", e1, e2)
+    assert e1 < 1e-3 and e2 < 1e-3

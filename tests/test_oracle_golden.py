@@ -260,3 +260,26 @@ def test_phong_composite_matches_reference(golden_dir):
     assert np.abs(comp - g["composite"]).max() < 1e-12
     assert np.abs(comp_w - g["composite_white"]).max() < 1e-12
     assert np.array_equal(orc.to_uint8(comp[0]), g["uint8_first"])
+
+
+# ----------------------------------------------------------------------------- Texture + Normal net (config 4)
+def test_texture_model_matches_reference_python(golden_dir):
+    """decoder_texture + RenderNet of RenderNet_Texture_Face_Normal.py:34-147 executed over the TF shim vs the oracle,
+    incl. the variable names the reference creates (scope quirks of :118-127)."""
+    g = _g(golden_dir, "texture_patch.npz"); r = _g(golden_dir, "resample.npz")
+    W = orc.init_texture_weights(seed=int(g["weight_seed"]), alpha_range=tuple(g["alpha_range"]),
+                                 gain=float(g["gain"]), bias_jitter=float(g["bias_jitter"]))
+    assert sorted(W) == g["var_names"].tolist()
+    shapes = {n: tuple(int(v) for v in s.split(";")) for n, s in zip(g["var_names"].tolist(), g["var_shapes"].tolist())}
+    assert all(tuple(W[k].shape) == shapes[k] for k in W)
+    tex = orc.decoder_texture(g["z_in"], W).numpy()
+    assert np.abs(tex[:, ::4, ::4, ::4] - g["decoder_sub"]).max() < 1e-6
+    assert abs(tex.sum(dtype=np.float64) - float(g["decoder_sum"])) < 1e-2 * max(1.0, float(g["decoder_abs_sum"]) * 1e-3)
+    pose = r["chair_pose"]
+    n = orc.transform_voxel_to_match_image(orc.rotation_resampling(_chair(golden_dir), pose))
+    tr = orc.transform_voxel_to_match_image(orc.rotation_resampling(tex, pose))
+    a, b, c, d = g["patch_slice"]
+    x5 = np.ascontiguousarray(np.concatenate([n, tr], axis=4)[:, a:b, c:d])
+    img, nrm = orc.rendernet_texture(x5, W)
+    assert np.abs(img.numpy() - g["image"]).max() < 5e-6
+    assert np.abs(nrm.numpy() - g["normal"]).max() < 5e-6
