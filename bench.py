@@ -130,6 +130,10 @@ def run_ours(args, rank, world, local_rank):
     from rendernet_b200._lib import lib
     from rendernet_b200.engine import RenderEngine
 
+    # Keep stdout clean for the single JSON line: NCCL / torchrun banners go to stderr.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -271,7 +275,10 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roofline,
             "projection_unit": {"ms_per_launch": p_ms, "tflops": p_tf, "frac_of_burst_peak": p_tf / peaks["burst"]},
             "cpu_baseline": cpu}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
