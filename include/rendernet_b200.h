@@ -129,6 +129,17 @@ int rn_conv2d_transpose_same(const void* x, const void* w_packed, const float* b
                              void* out16, float* out32, int B, int H, int W, int Cin, int Cout, int cout_pad,
                              int kh, int kw, int stride, int fmt, void* stream);
 
+/* Thin-channel stride-1 transposed conv (e_conv10 32->16, e_conv11 16->3 at 512^2; RenderNet_Shader.py:122-129) with
+ * F = 64/Cin adjacent x-pixels folded into the channel axis: rows of the implicit GEMM are pixel groups, K = F*Cin
+ * (= one 128-byte TMA row), N = F*Cout, and the kw x-taps collapse into 3 group offsets.  rn_xfold_factor returns F
+ * (1 = not applicable).  bias_x / alpha_x: per-Cout vectors tiled F times, zero padded to cout_pad >= F*Cout. */
+int rn_xfold_factor(int Cin, int W);
+int rn_pack_conv2d_transpose_xfold(const float* w, void* packed, int kh, int kw, int Cin, int Cout, int F, int cout_pad,
+                                   int fmt, void* stream);
+int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, const float* bias_x, const float* alpha_x, int act,
+                                 void* out16, float* out32, int B, int H, int W, int Cin, int Cout, int kh, int kw, int F,
+                                 int cout_pad, int fmt, void* stream);
+
 /* ---- thin 3-D convolutions on CUDA cores (too few channels for the tensor pipe) ---------------------
  * tf.nn.conv3d SAME + bias + PReLU (layer_util.py:228-265, RenderNet_Shader.py:36-43): e_conv1 (Cin=1,
  * 5^3, stride 2) and e_conv2 (Cin=8, 3^3, stride (1,1,2)).  x fp32 or 16-bit, w fp32 TF layout

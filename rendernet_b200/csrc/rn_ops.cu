@@ -414,6 +414,33 @@ __global__ void concat_channels_kernel(const float* __restrict__ a, const float*
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ x-folded thin transposed conv
+// Stride-1 SAME transposed conv (o = i + k - pb) with few channels, re-expressed over F-pixel groups:
+// x = F*q + r, x' = F*q' + p.  Rows of the GEMM are pixel groups q, K = (p, ci) = F*Cin, N = (r, co) = F*Cout, taps are
+// (ky, dq) with dq in {-1,0,1}:  Wf[ky][dq+1][r*Cout+co][p*Cin+ci] = w[ky][kx][co][ci], kx = pb - (F*dq + p - r), or 0
+// when kx is outside the filter.  TMA then moves 128-byte rows and kw taps collapse into 3.
+__global__ void pack_xfold_kernel(const float* __restrict__ w, uint16_t* __restrict__ packed, int kh, int kw, int Cin,
+                                  int Cout, int F, int cout_pad, int fmt) {
+  const int K = F * Cin, N = F * Cout, pb = (kw - 1) / 2;
+  const long long total = static_cast<long long>(kh) * 3 * cout_pad * K;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const int n = static_cast<int>((i / K) % cout_pad);
+    const int t = static_cast<int>(i / (static_cast<long long>(K) * cout_pad));
+    const int ky = t / 3, dq = t % 3 - 1;
+    float v = 0.f;
+    if (n < N) {
+      const int p = k / Cin, ci = k % Cin, r = n / Cout, co = n % Cout;
+      const int kx = pb - (F * dq + p - r);
+      if (kx >= 0 && kx < kw) v = w[((static_cast<long long>(ky) * kw + kx) * Cout + co) * Cin + ci];
+    }
+    if (fmt == 0) { __half h = __float2half_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
+    else { __nv_bfloat16 h = __float2bfloat16_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ Phong
 __global__ void phong_kernel(const float* __restrict__ img, const float* __restrict__ light_dir,
                              const float* __restrict__ light_col, float ambient, float k_diffuse, int white,
@@ -773,6 +800,47 @@ extern "C" int rn_concat_channels_f32(const float* a, const float* b, float* out
                                                                                                      Cb);
   RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
+}
+
+
+// ---------------------------------------------------------------------------------- x-folded thin transposed conv
+extern "C" int rn_xfold_factor(int Cin, int W) {
+  if (Cin >= 64 || Cin < 8 || 64 % Cin != 0) return 1;
+  const int F = 64 / Cin;
+  return (W % F == 0) ? F : 1;
+}
+
+extern "C" int rn_pack_conv2d_transpose_xfold(const float* w, void* packed, int kh, int kw, int Cin, int Cout, int F,
+                                              int cout_pad, int fmt, void* stream) {
+  if (!w || !packed || F < 2 || kw > 2 * F || cout_pad < F * Cout || kh * 3 > 28) return -1;
+  const long long total = static_cast<long long>(kh) * 3 * cout_pad * F * Cin;
+  pack_xfold_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<uint16_t*>(packed), kh, kw, Cin, Cout, F, cout_pad, fmt);
+  RN_COUNT_LAUNCH();
+  return static_cast<int>(cudaGetLastError());
+}
+
+// x [B,H,W,Cin] 16-bit; w_xfold from rn_pack_conv2d_transpose_xfold ([kh*3][cout_pad][F*Cin]); bias_x / alpha_x are the
+// per-Cout vectors tiled F times and zero padded to cout_pad (rn_expand_channels + padding by the caller).
+extern "C" int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, const float* bias_x, const float* alpha_x,
+                                            int act, void* out16, float* out32, int B, int H, int W, int Cin, int Cout,
+                                            int kh, int kw, int F, int cout_pad, int fmt, void* stream) {
+  if (F < 2 || W % F != 0 || kh * 3 > 28) return -20;
+  int8_t taps[28 * 3];
+  const int pby = (kh - 1) / 2;                     // SAME stride-1 transposed: dy = pb - ky
+  for (int ky = 0; ky < kh; ++ky)
+    for (int j = 0; j < 3; ++j) {
+      int8_t* t = taps + 3 * (ky * 3 + j);
+      t[0] = static_cast<int8_t>(j - 1); t[1] = static_cast<int8_t>(pby - ky); t[2] = 0;
+    }
+  rn_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.ndim = 2; d.B = B; d.H = H; d.W = W / F; d.D = 1; d.Cin = F * Cin; d.Cout = F * Cout; d.cout_pad = cout_pad;
+  d.ntaps = kh * 3; d.taps = taps; d.x = x; d.w_packed = w_xfold; d.bias = bias_x; d.alpha = alpha_x; d.act = act;
+  d.out16 = out16; d.out32 = out32;
+  d.o_base = 0; d.o_x = static_cast<long long>(F) * Cout; d.o_y = static_cast<long long>(W) * Cout;
+  d.o_b = static_cast<long long>(H) * W * Cout; d.fmt = fmt;
+  return rn_conv_igemm(&d, stream);
 }
 
 // ---------------------------------------------------------------------------------- thin conv3d

@@ -18,6 +18,7 @@ from . import ops
 from . import tfcompat as tf
 from .tfcompat import Deferred, realize
 
+USE_XFOLD = True           # fold x-pixels into channels for thin stride-1 transposed convs (e_conv10/11)
 USE_BANDED_CONV3D = True   # depth-folded tensor-core path for 3^3 convs (falls back to the 5-D TMA path)
 
 _XAVIER = tf.xavier_initializer
@@ -340,8 +341,12 @@ def _deferred_conv(kind, x, w, b, stride):
         xt = _as16(xin)
         banded = (kind == "conv3d" and USE_BANDED_CONV3D and tuple(w.shape[:3]) == (3, 3, 3)
                   and ops.BandedConv3d.eligible(int(w.shape[3]), int(w.shape[4]), int(xt.shape[3])))
-        L = None if banded else _packed(w, b, kind, stride)
-        a = _alpha_arg(alpha, ops.round_up(int(w.shape[-1]), 16) if banded else L.cout_pad)
+        xfold = 1
+        if (kind == "conv2d_transpose" and USE_XFOLD and stride == 1 and residual is None
+                and tuple(w.shape[:2]) == (4, 4)):
+            xfold = ops.XFoldConvT.factor(int(w.shape[3]), int(xt.shape[2]))
+        L = None if (banded or xfold > 1) else _packed(w, b, kind, stride)
+        a = None if xfold > 1 else _alpha_arg(alpha, ops.round_up(int(w.shape[-1]), 16) if banded else L.cout_pad)
         want16 = not want32
         if kind == "conv2d":
             return ops.conv2d(xt, L, act=act, residual=residual, want16=want16, want32=want32, alpha=a)
@@ -356,6 +361,17 @@ def _deferred_conv(kind, x, w, b, stride):
                 return ops.conv3d_banded(xt, Lb, act=act, residual=residual, alpha=a,
                                          alpha_tag=getattr(alpha, "_rn_name", None), want16=want16, want32=want32)
             return ops.conv3d(xt, L, act=act, residual=residual, want16=want16, want32=want32, alpha=a)
+        if xfold > 1:
+            F = xfold
+            Lx = _store().packed.get(("xfold", w._rn_name, F))
+            if Lx is None:
+                Lx = ops.XFoldConvT(w, b, F, dtype=tf.COMPUTE_DTYPE, device=_store().device)
+                _store().packed[("xfold", w._rn_name, F)] = Lx
+            al = None
+            if act == "prelu":
+                al = _dev_vec(alpha) if not isinstance(alpha, str) else torch.zeros(int(w.shape[2]), device=xt.device)
+            return ops.conv2d_transpose_xfold(xt, Lx, act=act, alpha=al, alpha_tag=getattr(alpha, "_rn_name", None),
+                                              want16=want16, want32=want32)
         if residual is not None:
             y = ops.conv2d_transpose(xt, L, act=act, alpha=a)
             return ops.bias_act(y, None, None, None, residual=residual, want32=want32)

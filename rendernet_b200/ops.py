@@ -234,6 +234,51 @@ def conv2d_transpose(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, 
     return out16 if not want32 else ((out16, out32) if want16 else out32)
 
 
+class XFoldConvT:
+    """Stride-1 transposed conv with thin channels, x-folded (rn_conv2d_transpose_s1_xfold)."""
+
+    def __init__(self, w_tf: torch.Tensor, bias: Optional[torch.Tensor], F: int, dtype=torch.float16, device="cuda"):
+        w_tf = torch.as_tensor(w_tf, dtype=torch.float32).to(device).contiguous()
+        self.kh, self.kw, self.cout, self.cin = (int(v) for v in w_tf.shape)
+        self.F, self.dtype = F, dtype
+        self.cout_pad = round_up(F * self.cout, 16)
+        self.w = torch.empty((self.kh * 3, self.cout_pad, F * self.cin), device=device, dtype=dtype)
+        check(lib.rn_pack_conv2d_transpose_xfold(w_tf.data_ptr(), self.w.data_ptr(), self.kh, self.kw, self.cin, self.cout,
+                                                 F, self.cout_pad, fmt_of(dtype), _stream()), "pack xfold")
+        b = bias if bias is not None else torch.zeros(self.cout)
+        self.bias = self.tiled(b, device)
+        self._alpha = {}
+
+    def tiled(self, v: torch.Tensor, device) -> torch.Tensor:
+        out = torch.zeros(self.cout_pad, device=device, dtype=torch.float32)
+        out[: self.F * self.cout] = v.to(device=device, dtype=torch.float32).reshape(-1)[: self.cout].repeat(self.F)
+        return out
+
+    @staticmethod
+    def factor(cin: int, W: int) -> int:
+        return int(lib.rn_xfold_factor(cin, W))
+
+
+def conv2d_transpose_xfold(x: torch.Tensor, L: XFoldConvT, act: Optional[str] = None, alpha: Optional[torch.Tensor] = None,
+                           alpha_tag=None, want16: bool = True, want32: bool = False, out16=None, out32=None):
+    x = _cuda(x, L.dtype)
+    B, H, W, Cin = x.shape
+    assert Cin == L.cin and W % L.F == 0
+    out16, out32 = _out_buffers((B, H, W, L.cout), L.dtype, x.device, want16, want32, out16, out32)
+    a = _ACT[act]
+    alpha_x = None
+    if a == ACT_PRELU:
+        key = alpha_tag if alpha_tag is not None else alpha.data_ptr()
+        alpha_x = L._alpha.get(key)
+        if alpha_x is None:
+            alpha_x = L.tiled(alpha, x.device)
+            L._alpha[key] = alpha_x
+    check(lib.rn_conv2d_transpose_s1_xfold(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(), _ptr(alpha_x), a, _ptr(out16),
+                                           _ptr(out32), B, H, W, Cin, L.cout, L.kh, L.kw, L.F, L.cout_pad, fmt_of(L.dtype),
+                                           _stream()), "rn_conv2d_transpose_s1_xfold")
+    return out16 if not want32 else ((out16, out32) if want16 else out32)
+
+
 def conv_igemm_raw(x, w_packed, bias, taps, ndim, B, H, W, D, Cin, Cout, cout_pad, out16=None, out32=None,
                    alpha=None, act=ACT_NONE, residual=None, o=None, fmt=0, force_bn=0, force_kps=0, max_ctas=0,
                    cluster=0, cta_group=0):

@@ -192,6 +192,27 @@ def test_conv2d_transpose_same(B, H, W, Cin, Cout, s):
     close(y16, ref, rel=1.2e-3)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 16, 32, 32, 16), (2, 8, 64, 16, 3), (1, 5, 8, 16, 16), (1, 32, 32, 32, 32)])
+def test_conv2d_transpose_s1_xfold(B, H, W, Cin, Cout):
+    """x-folded formulation of the thin stride-1 transposed convs (e_conv10 / e_conv11 shapes) vs the oracle."""
+    ops = _ops()
+    rng = np.random.default_rng(Cin + Cout + W)
+    x = q16(rng.standard_normal((B, H, W, Cin)))
+    w = q16(rng.standard_normal((4, 4, Cout, Cin)) / np.sqrt(16 * Cin))
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    a = rng.uniform(0, 0.3, Cout).astype(np.float32)
+    F = ops.XFoldConvT.factor(Cin, W)
+    assert F == 64 // Cin
+    L = ops.XFoldConvT(torch.from_numpy(w), torch.from_numpy(b), F)
+    xt = torch.from_numpy(x).to(dev).half()
+    y16, y32 = ops.conv2d_transpose_xfold(xt, L, act="prelu", alpha=torch.from_numpy(a).to(dev), want32=True)
+    ref = orc.prelu(orc.conv2d_transpose(x, w, b, (1, 1)), a)
+    close(y32, ref, rel=2e-5)
+    close(y16, ref, rel=1.2e-3)
+    y = ops.conv2d_transpose_xfold(xt, L, act="sigmoid", want16=False, want32=True)
+    close(y, torch.sigmoid(orc.conv2d_transpose(x, w, b, (1, 1))), abs_=2e-6)
+
+
 def test_conv_bf16_variant():
     ops = _ops()
     rng = np.random.default_rng(3)
