@@ -112,3 +112,76 @@ class RenderEngine:
             self.out_u8_host.copy_(self.out_u8, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.out_host if self.phong is None else (self.out_host, self.out_u8_host)
+
+
+class TextureRenderEngine:
+    """BASELINE config 4: voxels + 199-d texture vector + pose -> (albedo image, normal map), as one CUDA graph
+    (texture decoder -> two resamplings (C=1, C=4) -> concat -> Texture/Normal RenderNet;
+    RenderNet_Texture_Face_Normal.py:155-179)."""
+
+    def __init__(self, weights: Optional[Dict[str, np.ndarray]], batch: int, size: int = 64, new_size: int = 128,
+                 use_graph: bool = True, seed: int = 0, device: str = "cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("TextureRenderEngine needs a CUDA device (no CPU fallback)")
+        from ._lib import lib
+        self.B, self.size, self.new_size, self.device = batch, size, new_size, device
+        tf.reset_default_graph(seed)
+        tf.get_store().device = device
+        if weights is not None:
+            tf.load_weight_dict(weights)
+        self.vox = torch.zeros((batch, size, size, size, 1), device=device, dtype=torch.float32)
+        self.tex = torch.zeros((batch, 199), device=device, dtype=torch.float32)
+        self.minv = torch.zeros((batch, 3, 4), device=device, dtype=torch.float32)
+        self.vox_host = torch.zeros(self.vox.shape, dtype=torch.float32).pin_memory()
+        self.tex_host = torch.zeros(self.tex.shape, dtype=torch.float32).pin_memory()
+        self.minv_host = torch.zeros(self.minv.shape, dtype=torch.float32).pin_memory()
+        self.graph = None
+        self.out = None
+        self._forward()
+        torch.cuda.synchronize()
+        n0 = lib.rn_launch_count()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._forward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.launches_per_step = int(lib.rn_launch_count() - n0)
+        if use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._forward()
+            torch.cuda.synchronize()
+        self.out_host = tuple(torch.zeros(tuple(o.shape), dtype=torch.float32).pin_memory() for o in self.out)
+
+    def _forward(self):
+        from .RenderNet_Texture_Face_Normal import RenderNet as RenderNetTexture, decoder_texture
+        grid = ops.resample(self.vox, self.minv, self.new_size, True)
+        tex3d = tf.realize(decoder_texture(self.tex))
+        tex_rot = ops.resample(tex3d, self.minv, self.new_size, True)
+        x5 = ops.concat_channels(grid, tex_rot)
+        self.out = RenderNetTexture(x5, is_training=False)
+        return self.out
+
+    def upload(self, voxels, texture, view_params):
+        self.vox_host.copy_(torch.as_tensor(np.asarray(voxels, np.float32)).reshape(self.vox_host.shape))
+        self.tex_host.copy_(torch.as_tensor(np.asarray(texture, np.float32)).reshape(self.tex_host.shape))
+        self.minv_host.copy_(torch.from_numpy(RenderEngine.pose_to_matrix(view_params, self.size, self.new_size)))
+        self.vox.copy_(self.vox_host, non_blocking=True)
+        self.tex.copy_(self.tex_host, non_blocking=True)
+        self.minv.copy_(self.minv_host, non_blocking=True)
+
+    def step_device(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._forward()
+        return self.out
+
+    def render(self, voxels, texture, view_params):
+        self.upload(voxels, texture, view_params)
+        out = self.step_device()
+        for h, d in zip(self.out_host, out):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.out_host
