@@ -100,6 +100,70 @@ class RenderEngine:
         self.vox.copy_(self.vox_host, non_blocking=non_blocking)
         self.minv.copy_(self.minv_host, non_blocking=non_blocking)
 
+    # ------------------------------------------------------------------------------------------- pipelined API
+    def _init_pipeline(self):
+        if getattr(self, "_pipe", None) is not None:
+            return
+        dev = self.vox.device
+        P = {}
+        P["s_in"], P["s_out"] = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        P["vox_host"] = [torch.zeros(self.vox.shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+        P["minv_host"] = [torch.zeros(self.minv.shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+        P["vox_stage"] = [torch.zeros_like(self.vox) for _ in range(2)]
+        P["minv_stage"] = [torch.zeros_like(self.minv) for _ in range(2)]
+        src = self.out if self.phong is None else self.out_u8
+        P["out_stage"] = [torch.zeros_like(src) for _ in range(2)]
+        P["out_host"] = [torch.zeros(tuple(src.shape), dtype=src.dtype).pin_memory() for _ in range(2)]
+        for k in ("h2d_done", "stage_free", "out_ready", "d2h_done"):
+            P[k] = [torch.cuda.Event() for _ in range(2)]
+            for e in P[k]:
+                e.record(torch.cuda.current_stream())
+        P["n"] = 0
+        torch.cuda.synchronize()
+        self._pipe = P
+
+    def submit(self, voxels, view_params) -> int:
+        """Asynchronously enqueue one step: pinned-host staging -> H2D (copy stream) -> graph replay (compute
+        stream) -> D2H (copy stream).  Uploads of step i+1 and downloads of step i-1 overlap the compute of step i.
+        Returns a ticket for `result()`."""
+        self._init_pipeline()
+        P = self._pipe
+        i = P["n"]
+        s = i % 2
+        P["n"] = i + 1
+        P["h2d_done"][s].synchronize()                       # the pinned input slot is no longer being read
+        v = voxels if isinstance(voxels, torch.Tensor) else torch.as_tensor(np.asarray(voxels, np.float32))
+        P["vox_host"][s].copy_(v.reshape(P["vox_host"][s].shape))
+        P["minv_host"][s].copy_(torch.from_numpy(self.pose_to_matrix(view_params, self.size, self.new_size)))
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(P["s_in"]):
+            P["s_in"].wait_event(P["stage_free"][s])
+            P["vox_stage"][s].copy_(P["vox_host"][s], non_blocking=True)
+            P["minv_stage"][s].copy_(P["minv_host"][s], non_blocking=True)
+            P["h2d_done"][s].record(P["s_in"])
+        cur.wait_event(P["h2d_done"][s])
+        self.vox.copy_(P["vox_stage"][s])
+        self.minv.copy_(P["minv_stage"][s])
+        P["stage_free"][s].record(cur)
+        self.step_device()
+        cur.wait_event(P["d2h_done"][s])                     # the output staging slot has been drained
+        P["out_stage"][s].copy_(self.out if self.phong is None else self.out_u8)
+        P["out_ready"][s].record(cur)
+        with torch.cuda.stream(P["s_out"]):
+            P["s_out"].wait_event(P["out_ready"][s])
+            P["out_host"][s].copy_(P["out_stage"][s], non_blocking=True)
+            P["d2h_done"][s].record(P["s_out"])
+        return i
+
+    def result(self, ticket: int) -> torch.Tensor:
+        """Block until the step `ticket` (one of the last two submitted) has landed in pinned host memory."""
+        P = self._pipe
+        if ticket < P["n"] - 2:
+            raise RuntimeError("result() of a step whose host slot has been reused (keep at most 2 steps in flight)")
+        s = ticket % 2
+        P["d2h_done"][s].synchronize()
+        return P["out_host"][s]
+
     def render(self, voxels, view_params, to_host: bool = True):
         """voxels [B,64,64,64,1] float32 (host), view_params [B,3] -> image [B,512,512,3|1] float32
         (and uint8 Phong image when configured).  Includes H2D and D2H."""
