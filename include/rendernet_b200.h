@@ -34,6 +34,7 @@ long long rn_launch_count(void);
 /* default cluster size (1, 2, 4) used by descriptors that leave `cluster` at 0; returns the previous value */
 int rn_set_default_cluster(int cluster);
 int rn_set_default_cta_group(int cta_group);
+int rn_set_yhalo(int on);         /* y-halo sharing in rn_conv2d_same (3x3) / rn_conv3d_banded_same; default on */
 int rn_set_default_kps(int kps); /* k-iterations per smem pipeline stage, 0 = heuristic (tuning aid) */
 
 /* ---- resampler ----------------------------------------------------------------------------------
@@ -94,6 +95,9 @@ typedef struct rn_conv_desc {
   int x_channels, a_c_base, a_c_ntile, w_banded;
   int cluster;              /* thread-block-cluster size for the weight-tile TMA multicast: 0 auto, 1, 2 or 4 */
   int cta_group;            /* 0 auto, 1 = single-CTA MMA, 2 = paired tcgen05.mma.cta_group::2 (M = 256) */
+  /* y-halo sharing (2-D only): taps ordered tap = ky*nx + kx with dy(ky) = dy(0) + ky; the ny taps of a filter column
+   * then share one activation load of BH+ny-1 image rows.  0/1 = off.  tile_w: M-tile width override (0 = 16). */
+  int ny, tile_w;
 } rn_conv_desc;
 int rn_conv_igemm(const rn_conv_desc* d, void* stream);
 

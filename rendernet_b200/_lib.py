@@ -23,7 +23,7 @@ class rn_conv_desc(C.Structure):
         ("o_z", C.c_longlong), ("fmt", C.c_int), ("force_bn", C.c_int), ("force_kps", C.c_int),
         ("max_ctas", C.c_int),
         ("x_channels", C.c_int), ("a_c_base", C.c_int), ("a_c_ntile", C.c_int), ("w_banded", C.c_int),
-        ("cluster", C.c_int), ("cta_group", C.c_int),
+        ("cluster", C.c_int), ("cta_group", C.c_int), ("ny", C.c_int), ("tile_w", C.c_int),
     ]
 
 
@@ -37,6 +37,7 @@ SIGNATURES = {
     "rn_set_default_cluster": (_i, [_i]),
     "rn_set_default_cta_group": (_i, [_i]),
     "rn_set_default_kps": (_i, [_i]),
+    "rn_set_yhalo": (_i, [_i]),
     "rn_resample_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rn_pack_conv_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "rn_cast_f32_to_16": (_i, [_vp, _vp, _ll, _ll, _i, _vp]),

@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int sub_bytes = p.a_sub_bytes + p.b_sub_bytes;
+  const int ny = p.ny;                                        // B tiles (ky taps) per A (halo) load
+  const int sub_bytes = p.a_sub_bytes + ny * p.b_sub_bytes;   // one "group": A halo + ny weight tiles
   const int stage_bytes = p.kps * sub_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
@@ -202,9 +203,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
   const int num_ct = p.num_tiles / CL;
   auto tile_of = [&](int ct) { return ((ct / p.n_tiles) * CL + cta_rank) * p.n_tiles + (ct % p.n_tiles); };
 
-  const int total_k = p.ntaps * p.kblocks;
+  const int nx = p.ntaps / ny;
+  const int total_k = nx * p.kblocks;                          // groups per tile (each = ny k-iterations of MMAs)
   const int kb_elems = p.row_bytes >> 1;
-  const uint32_t a_tx = kTileM * p.row_bytes;
+  const uint32_t a_tx = static_cast<uint32_t>(p.BD * p.BW * (p.BH + ny - 1)) * p.row_bytes;
   const uint32_t b_tx = (CG == 2 ? BN / 2 : BN) * p.row_bytes;   // B bytes that land in THIS CTA's smem
 
   if (warp == 0) {
@@ -218,7 +220,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       const bool rank5 = (p.rank == 5), banded = (p.b_banded != 0);
       const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(full_bar);
       const uint32_t a_sub = static_cast<uint32_t>(p.a_sub_bytes), sub_u = static_cast<uint32_t>(sub_bytes);
-      const uint32_t kit_tx = (CG == 2 ? 2u : 1u) * (a_tx + b_tx);
+      const uint32_t b_sub = static_cast<uint32_t>(p.b_sub_bytes);
+      const uint32_t kit_tx = (CG == 2 ? 2u : 1u) * (a_tx + static_cast<uint32_t>(ny) * b_tx);
       const uint32_t b_off = (CL > 1 && CG == 1) ? static_cast<uint32_t>(cta_rank * kBRows * p.row_bytes) : 0u;
       const int b_row = (CG == 2) ? cta_rank * (BN / 2) : ((CL > 1) ? cta_rank * kBRows : 0);
       const uint64_t mapA = reinterpret_cast<uint64_t>(&p.tmA), mapB = reinterpret_cast<uint64_t>(&p.tmB);
@@ -228,10 +231,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
         const TileCoord t = decode_tile(p, tile_of(ct), BN);
         const int a_c0 = p.a_c_base + (t.n0 / BN) * p.a_c_ntile;
         const int bn0 = t.n0 + b_row;
-        int left = total_k, j = 0, n_here = 0, kit = 0;
+        int left = total_k, j = 0, n_here = 0;
         uint32_t dst = 0, bar = 0;
-        for (int tap = 0; tap < ntaps; ++tap) {
-          const int cx = t.x0 + p.tap[tap][0], cy = t.y0 + p.tap[tap][1], cz = t.z0 + p.tap[tap][2];
+        for (int kx = 0; kx < nx; ++kx) {      // tap(ky, kx) = ky*nx + kx; entry kx holds (dx, dy of ky = 0, dz)
+          const int cx = t.x0 + p.tap[kx][0], cy = t.y0 + p.tap[kx][1], cz = t.z0 + p.tap[kx][2];
           int ac = a_c0, bk = 0;
           for (int kb = 0; kb < kblocks; ++kb) {
             if (j == 0) {
@@ -243,14 +246,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             }
             if (rank5) tma_a_5d<CG == 2>(dst, mapA, bar, ac, cz, cx, cy, t.b);
             else tma_a_4d<CG == 2>(dst, mapA, bar, ac, cx, cy, t.b);
-            if constexpr (CL > 1 && CG == 1) {
-              if (banded) tma_a_3d_mc(dst + a_sub + b_off, mapB, bar, kMask, 0, b_row, kit);
-              else tma_a_3d_mc(dst + a_sub + b_off, mapB, bar, kMask, bk, bn0, tap);
-            } else {
-              if (banded) tma_a_3d<CG == 2>(dst + a_sub, mapB, bar, 0, b_row, kit);
-              else tma_a_3d<CG == 2>(dst + a_sub, mapB, bar, bk, bn0, tap);
+            uint32_t bdst = dst + a_sub;
+            for (int ky = 0; ky < ny; ++ky) {
+              const int tap = ky * nx + kx;
+              if constexpr (CL > 1 && CG == 1) {
+                if (banded) tma_a_3d_mc(bdst + b_off, mapB, bar, kMask, 0, b_row, tap * kblocks + kb);
+                else tma_a_3d_mc(bdst + b_off, mapB, bar, kMask, bk, bn0, tap);
+              } else {
+                if (banded) tma_a_3d<CG == 2>(bdst, mapB, bar, 0, b_row, tap * kblocks + kb);
+                else tma_a_3d<CG == 2>(bdst, mapB, bar, bk, bn0, tap);
+              }
+              bdst += b_sub;
             }
-            ac += kb_elems; bk += kb_elems; ++kit; dst += sub_u;
+            ac += kb_elems; bk += kb_elems; dst += sub_u;
             if (++j == n_here) {
               j = 0; left -= n_here;
               if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -269,7 +277,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       const uint64_t desc_hi = make_smem_desc(0, p.row_bytes);
       const uint32_t base16 = (smem_u32(smem) & 0x3FFFFu) >> 4;
       const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4, sub16 = static_cast<uint32_t>(sub_bytes) >> 4;
-      const uint32_t a16 = static_cast<uint32_t>(p.a_sub_bytes) >> 4;
+      const uint32_t a16 = static_cast<uint32_t>(p.a_sub_bytes) >> 4, b16 = static_cast<uint32_t>(p.b_sub_bytes) >> 4;
+      const uint32_t ady16 = static_cast<uint32_t>(p.BD * p.BW * p.row_bytes) >> 4;   // one image row of the A halo
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -285,13 +294,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
           tc_fence_after();
           uint64_t da = desc_hi | static_cast<uint64_t>(base16 + static_cast<uint32_t>(stage) * stage16);
           for (int j = 0; j < n_here; ++j) {
-            const uint64_t db = da + a16;
+            uint64_t dak = da, dbk = da + a16;
+            for (int ky = 0; ky < ny; ++ky) {       // operand ky = the halo shifted down by ky image rows
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < mma_per_kit) {
-                umma_f16<CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
-                accum = 1;
+              for (int k = 0; k < 4; ++k) {
+                if (k < mma_per_kit) {
+                  umma_f16<CG>(d_tmem, dak + 2 * k, dbk + 2 * k, idesc, accum);
+                  accum = 1;
+                }
               }
+              dak += ady16;
+              dbk += b16;
             }
             da += sub16;
           }
@@ -471,12 +484,30 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
     BN = d->force_bn;
   }
   p.n_tiles = d->cout_pad / BN;
+  // y-halo sharing of the A operand between the ny taps of a filter column (3x3 convs, banded 3^3)
+  p.ny = 1;
+  if (d->ny > 1) {
+    if (d->ndim != 2 || d->ntaps % d->ny != 0) return -13;
+    const int nxh = d->ntaps / d->ny;
+    for (int kx = 0; kx < nxh; ++kx)
+      for (int ky = 0; ky < d->ny; ++ky) {
+        const int8_t* t0 = d->taps + 3 * kx;
+        const int8_t* t1 = d->taps + 3 * (ky * nxh + kx);
+        if (t1[0] != t0[0] || t1[1] != t0[1] + ky || t1[2] != t0[2]) return -14;
+      }
+    p.ny = d->ny;
+  }
   // M tile box: BD x BW x BH == 128, innermost spatial dim first
   auto pow2_le = [](int v, int cap) { int r = 1; while (r * 2 <= cap && r < v) r *= 2; return r; };
   int rem = kTileM;
   p.BD = d->ndim == 3 ? pow2_le(D, rem) : 1;
   rem /= p.BD;
   p.BW = pow2_le(d->W, rem);
+  if (p.ny > 1) {   // tall tiles keep the halo overhead low: (BH+ny-1)/BH
+    const int tw = d->tile_w > 0 ? d->tile_w : 16;
+    if (p.BW > tw) p.BW = tw;
+    if (p.BW < 8 || (p.BW * p.row_bytes) % 1024 != 0) p.ny = 1;   // operand ky must start on a swizzle-atom boundary
+  }
   rem /= p.BW;
   p.BH = rem;
   p.rank = d->ndim == 3 ? 5 : 4;
@@ -505,10 +536,10 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
     else if (want >= 2 && m_tiles % 2 == 0 && grid >= 2) CL = 2;
   }
   grid -= grid % CL;
-  p.a_sub_bytes = kTileM * p.row_bytes;
+  p.a_sub_bytes = ((p.BD * p.BW * (p.BH + p.ny - 1) * p.row_bytes + 1023) / 1024) * 1024;
   p.b_sub_bytes = (((BN / CG) * p.row_bytes + 1023) / 1024) * 1024;
-  const int sub = p.a_sub_bytes + p.b_sub_bytes;
-  const int total_k = p.ntaps * p.kblocks;
+  const int sub = p.a_sub_bytes + p.ny * p.b_sub_bytes;       // one group: A (halo) + ny weight tiles
+  const int total_k = (p.ntaps / p.ny) * p.kblocks;
   // k-iterations per stage: ~64 KB stages amortise the per-stage barrier round trips (measured: tune3/tune4 logs)
   p.kps = (65536 + sub / 2) / sub;
   if (p.kps < 1) p.kps = 1;
@@ -537,7 +568,7 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   if (p.rank == 4) {
     const cuuint64_t dims[4] = {Cx, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     const cuuint64_t strides[3] = {Cx * 2, Cx * 2 * d->W, Cx * 2 * d->W * d->H};
-    const cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)p.BW, (cuuint32_t)(p.BH + p.ny - 1), 1};
     r = enc(&p.tmA, dt, 4, const_cast<void*>(d->x), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {

@@ -27,6 +27,8 @@ struct alignas(64) IgemmParams {
   int ab_fmt;                     // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
   int a_c_base, a_c_ntile;        // A channel coordinate = a_c_base + n_tile*a_c_ntile + kb*KB (depth-folded conv3d)
   int b_banded;                   // 1: B box = (0, 0, tap*kblocks+kb) -- one banded filter shared by all N tiles
+  int ny;                         // y-halo sharing: taps are ordered tap = ky*nx + kx with dy consecutive; the ny taps of a
+                                  // column share ONE A load of BH+ny-1 image rows (operand ky starts ky*BW rows into it)
   int8_t tap[kMaxTaps][4];        // (dx, dy, dz, _) input offset of each filter tap
   // fused epilogue: v = acc + bias; v = act(v); v += residual; store
   void* out16;                    // 16-bit output or nullptr

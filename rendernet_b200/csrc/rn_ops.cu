@@ -18,6 +18,7 @@
 namespace rn {
 extern std::atomic<long long> g_launch_count;
 #define RN_COUNT_LAUNCH() rn::g_launch_count.fetch_add(1, std::memory_order_relaxed)
+int g_yhalo = 1;   // share one activation halo load between the 3 ky taps of 3x3 / banded 3^3 convs
 
 // ------------------------------------------------------------------------------------------ resampler
 // One warp per output row (innermost output axis); each lane owns 4 consecutive points per iteration so
@@ -491,6 +492,12 @@ using namespace rn;
 
 extern "C" int rn_version(void) { return 100; }
 
+extern "C" int rn_set_yhalo(int on) {
+  const int prev = rn::g_yhalo;
+  rn::g_yhalo = on ? 1 : 0;
+  return prev;
+}
+
 extern "C" const char* rn_error_string(int code) {
   if (code == 0) return "ok";
   if (code < 0) return "rendernet_b200: invalid argument";
@@ -588,6 +595,7 @@ extern "C" int rn_conv2d_same(const void* x, const void* w_packed, const float* 
   d.residual = residual; d.residual_is_f32 = residual_is_f32; d.out16 = out16; d.out32 = out32;
   d.o_base = 0; d.o_x = Cout; d.o_y = static_cast<long long>(W) * Cout; d.o_b = static_cast<long long>(H) * W * Cout;
   d.o_z = 0; d.fmt = fmt;
+  if (kh == 3 && Cin % 64 == 0 && g_yhalo) d.ny = 3;   // taps are already ordered ky*kw + kx with dy = ky - 1
   return rn_conv_igemm(&d, stream);
 }
 
@@ -738,6 +746,7 @@ extern "C" int rn_conv3d_banded_same(const void* x, const void* w_banded, const 
   d.a_c_base = -Cin;                                // first input depth of N tile 0 is z = -1 (zero filled)
   d.a_c_ntile = (128 / Cout) * Cin;                 // each N tile advances 128/Cout depths
   d.w_banded = 1;
+  if (g_yhalo) d.ny = 3;
   return rn_conv_igemm(&d, stream);
 }
 

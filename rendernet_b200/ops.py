@@ -281,7 +281,7 @@ def conv2d_transpose_xfold(x: torch.Tensor, L: XFoldConvT, act: Optional[str] = 
 
 def conv_igemm_raw(x, w_packed, bias, taps, ndim, B, H, W, D, Cin, Cout, cout_pad, out16=None, out32=None,
                    alpha=None, act=ACT_NONE, residual=None, o=None, fmt=0, force_bn=0, force_kps=0, max_ctas=0,
-                   cluster=0, cta_group=0):
+                   cluster=0, cta_group=0, ny=0, tile_w=0):
     """Direct access to rn_conv_igemm for tests / tuning.  taps: list of (dx,dy,dz)."""
     n = len(taps)
     arr = (C.c_int8 * (3 * n))(*[v for t in taps for v in t])
@@ -303,6 +303,7 @@ def conv_igemm_raw(x, w_packed, bias, taps, ndim, B, H, W, D, Cin, Cout, cout_pa
     d.fmt, d.force_bn, d.force_kps, d.max_ctas = fmt, force_bn, force_kps, max_ctas
     d.cluster = cluster
     d.cta_group = cta_group
+    d.ny, d.tile_w = ny, tile_w
     check(lib.rn_conv_igemm(C.byref(d), _stream()), "rn_conv_igemm")
 
 
