@@ -213,6 +213,24 @@ def test_conv2d_transpose_s1_xfold(B, H, W, Cin, Cout):
     close(y, torch.sigmoid(orc.conv2d_transpose(x, w, b, (1, 1))), abs_=2e-6)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,tw", [(1, 16, 16, 64, 64, 0), (2, 24, 20, 128, 256, 16), (1, 8, 8, 64, 16, 8),
+                                                 (1, 64, 64, 64, 128, 32), (1, 5, 9, 64, 32, 0)])
+def test_conv2d_yhalo_sharing(B, H, W, Cin, Cout, tw):
+    """The 3 ky taps of a 3x3 conv sharing one activation halo load (A box of BH+2 rows, operands at row offsets)
+    vs the oracle, incl. ragged tiles and image borders inside the halo."""
+    ops = _ops()
+    rng = np.random.default_rng(H * W + Cin)
+    x = q16(rng.standard_normal((B, H, W, Cin)))
+    w = q16(rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin))
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    L = ops.pack_conv("conv2d", torch.from_numpy(w), torch.from_numpy(b), None)
+    taps = [(kx - 1, ky - 1, 0) for ky in range(3) for kx in range(3)]
+    y = torch.empty(B, H, W, Cout, device=dev, dtype=torch.float32)
+    ops.conv_igemm_raw(torch.from_numpy(x).to(dev).half(), L.w, L.bias, taps, 2, B, H, W, 1, Cin, Cout, L.cout_pad,
+                       out32=y, ny=3, tile_w=tw)
+    close(y, orc.conv2d(x, w, b), rel=2e-5)
+
+
 def test_conv_bf16_variant():
     ops = _ops()
     rng = np.random.default_rng(3)
@@ -238,8 +256,10 @@ def test_conv_linearity_and_tile_schedule_full_size():
     # same work on 37 CTAs instead of 148: different tile->CTA assignment, identical result
     taps = [(kx - 1, ky - 1, 0) for ky in range(3) for kx in range(3)]
     y3 = torch.empty_like(y)
-    ops.conv_igemm_raw(x, L.w, L.bias, taps, 2, B, 64, 64, 1, 1024, 1024, 1024, out16=y3, max_ctas=37)
-    assert torch.equal(y3, y)
+    ops.conv_igemm_raw(x, L.w, L.bias, taps, 2, B, 64, 64, 1, 1024, 1024, 1024, out16=y3, max_ctas=37, ny=3)
+    assert torch.equal(y3, y)                 # same accumulation order (y-halo sharing on, as in conv2d), other CTA count
+    ops.conv_igemm_raw(x, L.w, L.bias, taps, 2, B, 64, 64, 1, 1024, 1024, 1024, out16=y3, ny=0)
+    close(y3, y, rel=2e-3)                    # tap-major order without halo sharing: same result up to fp16 rounding
     ref = torch.nn.functional.conv2d(x[:1].permute(0, 3, 1, 2).float(), w.half().float().permute(3, 2, 0, 1),
                                      padding=1).permute(0, 2, 3, 1)
     close(y[:1], ref, rel=1.5e-3)
@@ -257,7 +277,9 @@ def test_conv_cluster_multicast_bit_identical(cluster, cta_group, bn):
     w = torch.randn(3, 3, Cin, Cout, device=dev) / (9 * Cin) ** 0.5
     L = ops.pack_conv("conv2d", w, torch.randn(Cout) * 0.1, torch.rand(Cout) * 0.3)
     taps = [(kx - 1, ky - 1, 0) for ky in range(3) for kx in range(3)]
-    ref = ops.conv2d(x, L, act="prelu")
+    ref = torch.empty(B, H, W, Cout, device=dev, dtype=torch.float16)
+    ops.conv_igemm_raw(x, L.w, L.bias, taps, 2, B, H, W, 1, Cin, Cout, L.cout_pad, out16=ref, alpha=L.alpha, act=1,
+                       cluster=1, cta_group=1)
     close(ref, orc.prelu(orc.conv2d(x.float().cpu().numpy(), w.half().float().cpu().numpy(), L.bias[:Cout].cpu().numpy()),
                          L.alpha[:Cout].cpu().numpy()), rel=1.2e-3)
     out = torch.empty_like(ref)
