@@ -497,62 +497,70 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
       }
     p.ny = d->ny;
   }
-  // M tile box: BD x BW x BH == 128, innermost spatial dim first
+  // M tile box (BD x BW x BH == 128, innermost spatial dim first), launch shape and pipeline sizing.  If the y-halo
+  // variant cannot keep >= 3 stages in flight (tiny images -> no CTA pairing -> 3 full-width B tiles per group),
+  // fall back to one A load per tap.
   auto pow2_le = [](int v, int cap) { int r = 1; while (r * 2 <= cap && r < v) r *= 2; return r; };
-  int rem = kTileM;
-  p.BD = d->ndim == 3 ? pow2_le(D, rem) : 1;
-  rem /= p.BD;
-  p.BW = pow2_le(d->W, rem);
-  if (p.ny > 1) {   // tall tiles keep the halo overhead low: (BH+ny-1)/BH
-    const int tw = d->tile_w > 0 ? d->tile_w : 16;
-    if (p.BW > tw) p.BW = tw;
-    if (p.BW < 8 || (p.BW * p.row_bytes) % 1024 != 0) p.ny = 1;   // operand ky must start on a swizzle-atom boundary
-  }
-  rem /= p.BW;
-  p.BH = rem;
-  p.rank = d->ndim == 3 ? 5 : 4;
-  p.W = d->W; p.H = d->H; p.D = D; p.B = d->B;
-  p.tiles_x = (d->W + p.BW - 1) / p.BW;
-  p.tiles_y = (d->H + p.BH - 1) / p.BH;
-  p.tiles_z = (D + p.BD - 1) / p.BD;
-  p.num_tiles = d->B * p.tiles_x * p.tiles_y * p.tiles_z * p.n_tiles;
   for (int t = 0; t < d->ntaps; ++t) {
     p.tap[t][0] = d->taps[3 * t + 0];
     p.tap[t][1] = d->taps[3 * t + 1];
     p.tap[t][2] = d->taps[3 * t + 2];
   }
   p.ab_fmt = d->fmt;
-  // launch shape: persistent grid, cluster size CL for the B multicast, CG = 2 for the paired (cta_group::2) MMA
-  int grid = num_sms();
-  if (d->max_ctas > 0 && d->max_ctas < grid) grid = d->max_ctas;
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  const int m_tiles = p.num_tiles / p.n_tiles;
-  int CL = 1, CG = 1;
-  if (BN >= 128) {
-    const int want = d->cluster > 0 ? d->cluster : g_default_cluster;
-    const int want_cg = d->cta_group > 0 ? d->cta_group : g_default_cta_group;
-    if (want_cg == 2 && m_tiles % 2 == 0 && grid >= 2) { CL = 2; CG = 2; }
-    else if (want >= 4 && m_tiles % 4 == 0 && grid >= 4) CL = 4;
-    else if (want >= 2 && m_tiles % 2 == 0 && grid >= 2) CL = 2;
-  }
-  grid -= grid % CL;
-  p.a_sub_bytes = ((p.BD * p.BW * (p.BH + p.ny - 1) * p.row_bytes + 1023) / 1024) * 1024;
-  p.b_sub_bytes = (((BN / CG) * p.row_bytes + 1023) / 1024) * 1024;
-  const int sub = p.a_sub_bytes + p.ny * p.b_sub_bytes;       // one group: A (halo) + ny weight tiles
-  const int total_k = (p.ntaps / p.ny) * p.kblocks;
-  // k-iterations per stage: ~64 KB stages amortise the per-stage barrier round trips (measured: tune3/tune4 logs)
-  p.kps = (65536 + sub / 2) / sub;
-  if (p.kps < 1) p.kps = 1;
-  if (p.kps > 8) p.kps = 8;
-  if (p.kps > total_k) p.kps = total_k;
-  if (d->force_kps > 0) p.kps = d->force_kps;
-  else if (g_default_kps > 0) p.kps = g_default_kps < total_k ? g_default_kps : total_k;
+  p.rank = d->ndim == 3 ? 5 : 4;
+  p.W = d->W; p.H = d->H; p.D = D; p.B = d->B;
   const int budget = 232448 - 1024 - 256;
-  p.stages = budget / (p.kps * sub);
-  if (p.stages > 12) p.stages = 12;
-  while (p.stages < 3 && p.kps > 1) {   // keep at least 3 stages in flight
-    --p.kps;
+  int grid = 0, CL = 1, CG = 1, sub = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    int rem = kTileM;
+    p.BD = d->ndim == 3 ? pow2_le(D, rem) : 1;
+    rem /= p.BD;
+    p.BW = pow2_le(d->W, rem);
+    if (p.ny > 1) {   // tall tiles keep the halo overhead low: (BH+ny-1)/BH
+      const int tw = d->tile_w > 0 ? d->tile_w : 16;
+      if (p.BW > tw) p.BW = tw;
+      if (p.BW < 8 || (p.BW * p.row_bytes) % 1024 != 0) p.ny = 1;   // operand ky must start on a swizzle-atom boundary
+      if (p.ny == 1) p.BW = pow2_le(d->W, rem);
+    }
+    rem /= p.BW;
+    p.BH = rem;
+    p.tiles_x = (d->W + p.BW - 1) / p.BW;
+    p.tiles_y = (d->H + p.BH - 1) / p.BH;
+    p.tiles_z = (D + p.BD - 1) / p.BD;
+    p.num_tiles = d->B * p.tiles_x * p.tiles_y * p.tiles_z * p.n_tiles;
+    // persistent grid, cluster size CL for the B multicast, CG = 2 for the paired (cta_group::2) MMA
+    grid = num_sms();
+    if (d->max_ctas > 0 && d->max_ctas < grid) grid = d->max_ctas;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    const int m_tiles = p.num_tiles / p.n_tiles;
+    CL = 1; CG = 1;
+    if (BN >= 128) {
+      const int want = d->cluster > 0 ? d->cluster : g_default_cluster;
+      const int want_cg = d->cta_group > 0 ? d->cta_group : g_default_cta_group;
+      if (want_cg == 2 && m_tiles % 2 == 0 && grid >= 2) { CL = 2; CG = 2; }
+      else if (want >= 4 && m_tiles % 4 == 0 && grid >= 4) CL = 4;
+      else if (want >= 2 && m_tiles % 2 == 0 && grid >= 2) CL = 2;
+    }
+    grid -= grid % CL;
+    p.a_sub_bytes = ((p.BD * p.BW * (p.BH + p.ny - 1) * p.row_bytes + 1023) / 1024) * 1024;
+    p.b_sub_bytes = (((BN / CG) * p.row_bytes + 1023) / 1024) * 1024;
+    sub = p.a_sub_bytes + p.ny * p.b_sub_bytes;       // one group: A (halo) + ny weight tiles
+    const int total_k = (p.ntaps / p.ny) * p.kblocks;
+    // groups per stage: ~64 KB stages amortise the per-stage barrier round trips (measured: tune3/tune4 logs)
+    p.kps = (65536 + sub / 2) / sub;
+    if (p.kps < 1) p.kps = 1;
+    if (p.kps > 8) p.kps = 8;
+    if (p.kps > total_k) p.kps = total_k;
+    if (d->force_kps > 0) p.kps = d->force_kps;
+    else if (g_default_kps > 0) p.kps = g_default_kps < total_k ? g_default_kps : total_k;
     p.stages = budget / (p.kps * sub);
+    if (p.stages > 12) p.stages = 12;
+    while (p.stages < 3 && p.kps > 1) {   // keep at least 3 stages in flight
+      --p.kps;
+      p.stages = budget / (p.kps * sub);
+    }
+    if (p.stages >= 3 || p.ny == 1) break;
+    p.ny = 1;                               // retry without halo sharing
   }
   if (p.stages < 2) return -10;
   const size_t smem = static_cast<size_t>(p.stages) * p.kps * sub + 1024 + 256;

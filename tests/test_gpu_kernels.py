@@ -117,6 +117,7 @@ CONV2D = [  # B,H,W,Cin,Cout,k,act,res,res32
     (1, 24, 20, 32, 64, 3, "prelu", False, False),      # ragged tiles (H, W not multiples of the M box)
     (1, 8, 8, 64, 64, 3, "sigmoid", False, False),      # M box taller than the image
     (1, 5, 7, 16, 16, 3, None, True, False),            # tiny, everything ragged
+    (1, 8, 8, 1024, 1024, 3, "prelu", False, False),    # one M tile: no CTA pairing -> y-halo falls back (stage budget)
     (1, 128, 128, 32, 16, 3, "prelu", False, False), (1, 256, 256, 16, 16, 3, None, False, False),
     (1, 16, 16, 64, 128, 4, "prelu", False, False), (2, 32, 32, 128, 64, 4, None, False, False),
 ]
