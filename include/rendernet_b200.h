@@ -116,13 +116,14 @@ int rn_conv3d_same(const void* x, const void* w_packed, const float* bias, const
  * activation byte is fetched from L2 9x instead of 27x.  w_banded from rn_pack_conv3d_banded
  * ([9][kblocks][128][64] 16-bit, bytes = rn_conv3d_banded_bytes); bias/alpha are per Cout (length Cout) and are
  * expanded over depth internally via bias_full/alpha_full scratch [D*Cout] fp32 supplied by the caller
- * (fill them with rn_expand_channels).  x, residual, out: [B,H,W,D,C*] 16-bit. */
-long long rn_conv3d_banded_bytes(int Cin, int Cout);
-int rn_pack_conv3d_banded(const float* w, void* packed, int Cin, int Cout, int fmt, void* stream);
+ * (fill them with rn_expand_channels).  x: [B,H,W,D,Cin]; residual, out: [B,H,W,ceil(D/sz),Cout], 16-bit.
+ * sz = stride along D (1: res blocks / e_conv3; 2: e_conv2's stride (1,1,2), RenderNet_Shader.py:41), TF SAME pads. */
+long long rn_conv3d_banded_bytes(int Cin, int Cout, int sz);
+int rn_pack_conv3d_banded(const float* w, void* packed, int Cin, int Cout, int sz, int fmt, void* stream);
 int rn_expand_channels(const float* v, float* v_full, int C, int D, void* stream);
 int rn_conv3d_banded_same(const void* x, const void* w_banded, const float* bias_full, const float* alpha_full,
                           int act, const void* residual, int residual_is_f32, void* out16, float* out32, int B,
-                          int H, int W, int D, int Cin, int Cout, int fmt, void* stream);
+                          int H, int W, int D, int Cin, int Cout, int sz, int fmt, void* stream);
 
 /* slim.conv2d_transpose / layer_util.conv2d_transpose (layer_util.py:186; RenderNet_Shader.py:106-129),
  * SAME, out = in*stride.  w_packed holds the stride^2 phase filters back to back, as produced by

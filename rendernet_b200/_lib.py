@@ -46,10 +46,10 @@ SIGNATURES = {
     "rn_conv_igemm": (_i, [C.POINTER(rn_conv_desc), _vp]),
     "rn_conv2d_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rn_conv3d_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "rn_conv3d_banded_bytes": (_ll, [_i, _i]),
-    "rn_pack_conv3d_banded": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "rn_conv3d_banded_bytes": (_ll, [_i, _i, _i]),
+    "rn_pack_conv3d_banded": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rn_expand_channels": (_i, [_vp, _vp, _i, _i, _vp]),
-    "rn_conv3d_banded_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rn_conv3d_banded_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rn_pack_conv2d_transpose_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rn_conv2d_transpose_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rn_xfold_factor": (_i, [_i, _i]),

@@ -151,10 +151,11 @@ __global__ void cast_16_to_f32_kernel(const uint16_t* __restrict__ s, float* __r
 
 
 // ------------------------------------------------------------------------------------------ banded conv3d filter
-// Wb[tap=(ky,kx)][kb][n = zo_l*Cout + co][k = zi_l*Cin + ci],  zi = z0 - 1 + kb*(64/Cin) + zi_l, zo = z0 + zo_l
-// -> w[ky][kx][zi - zo + 1][ci][co] when |zi - zo| <= 1, else 0.   (BN = 128, KB = 64)
+// Wb[tap=(ky,kx)][kb][n = zo_l*Cout + co][k = zi_l*Cin + ci] with, relative to the N tile's first output depth z0,
+// zi = sz*z0 - pz + kb*(64/Cin) + zi_l and zo = z0 + zo_l  ->  kz = zi - (sz*zo - pz) = kb*(64/Cin) + zi_l - sz*zo_l;
+// entry = w[ky][kx][kz][ci][co] when 0 <= kz < 3, else 0.   (BN = 128, KB = 64; sz = z stride)
 __global__ void pack_banded_kernel(const float* __restrict__ w, uint16_t* __restrict__ packed, int Cin, int Cout,
-                                   int kblocks, int fmt) {
+                                   int kblocks, int sz, int fmt) {
   const long long total = 9LL * kblocks * 128 * 64;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -163,9 +164,9 @@ __global__ void pack_banded_kernel(const float* __restrict__ w, uint16_t* __rest
     const int kb = static_cast<int>((i / (64 * 128)) % kblocks);
     const int tap = static_cast<int>(i / (64LL * 128 * kblocks));
     const int zi_l = k / Cin, ci = k % Cin, zo_l = n / Cout, co = n % Cout;
-    const int dz = kb * (64 / Cin) + zi_l - 1 - zo_l;
+    const int kz = kb * (64 / Cin) + zi_l - sz * zo_l;
     float v = 0.f;
-    if (dz >= -1 && dz <= 1) v = w[((static_cast<long long>(tap) * 3 + (dz + 1)) * Cin + ci) * Cout + co];
+    if (kz >= 0 && kz <= 2) v = w[((static_cast<long long>(tap) * 3 + kz) * Cin + ci) * Cout + co];
     if (fmt == 0) { __half h = __float2half_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
     else { __nv_bfloat16 h = __float2bfloat16_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
   }
@@ -693,21 +694,21 @@ extern "C" int rn_conv2d_transpose_same(const void* x, const void* w_packed, con
 
 
 // ---------------------------------------------------------------------------------- depth-folded conv3d
-static int banded_kblocks(int Cin, int Cout) {
-  const int span = (128 / Cout + 2) * Cin;  // input depths needed by one N tile, in elements
+static int banded_kblocks(int Cin, int Cout, int sz) {
+  const int span = ((128 / Cout - 1) * sz + 3) * Cin;  // input depths needed by one N tile, in elements
   return (span + 63) / 64;
 }
 
-extern "C" long long rn_conv3d_banded_bytes(int Cin, int Cout) {
-  if (Cin < 8 || Cout < 8 || 64 % Cin != 0 || 128 % Cout != 0) return -1;
-  return 9LL * banded_kblocks(Cin, Cout) * 128 * 64 * 2;
+extern "C" long long rn_conv3d_banded_bytes(int Cin, int Cout, int sz) {
+  if (Cin < 8 || Cout < 8 || 64 % Cin != 0 || 128 % Cout != 0 || sz < 1 || sz > 2) return -1;
+  return 9LL * banded_kblocks(Cin, Cout, sz) * 128 * 64 * 2;
 }
 
-extern "C" int rn_pack_conv3d_banded(const float* w, void* packed, int Cin, int Cout, int fmt, void* stream) {
-  if (!w || !packed || rn_conv3d_banded_bytes(Cin, Cout) < 0) return -1;
-  const int kb = banded_kblocks(Cin, Cout);
+extern "C" int rn_pack_conv3d_banded(const float* w, void* packed, int Cin, int Cout, int sz, int fmt, void* stream) {
+  if (!w || !packed || rn_conv3d_banded_bytes(Cin, Cout, sz) < 0) return -1;
+  const int kb = banded_kblocks(Cin, Cout, sz);
   pack_banded_kernel<<<grid_for(9LL * kb * 128 * 64, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, static_cast<uint16_t*>(packed), Cin, Cout, kb, fmt);
+      w, static_cast<uint16_t*>(packed), Cin, Cout, kb, sz, fmt);
   RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }
@@ -723,9 +724,11 @@ extern "C" int rn_expand_channels(const float* v, float* v_full, int C, int D, v
 extern "C" int rn_conv3d_banded_same(const void* x, const void* w_banded, const float* bias_full,
                                      const float* alpha_full, int act, const void* residual, int residual_is_f32,
                                      void* out16, float* out32, int B, int H, int W, int D, int Cin, int Cout,
-                                     int fmt, void* stream) {
-  if (rn_conv3d_banded_bytes(Cin, Cout) < 0) return -30;
-  const long long Fi = static_cast<long long>(D) * Cin, Fo = static_cast<long long>(D) * Cout;
+                                     int sz, int fmt, void* stream) {
+  if (rn_conv3d_banded_bytes(Cin, Cout, sz) < 0) return -30;
+  int Do, pz;
+  same_pad(D, 3, sz, &Do, &pz);                     // TF SAME along z: out = ceil(D/sz), pad-before pz
+  const long long Fi = static_cast<long long>(D) * Cin, Fo = static_cast<long long>(Do) * Cout;
   if (Fo % 128 != 0 || Fi % 8 != 0) return -31;
   int8_t taps[27];
   for (int ky = 0; ky < 3; ++ky)
@@ -736,15 +739,15 @@ extern "C" int rn_conv3d_banded_same(const void* x, const void* w_banded, const 
   rn_conv_desc d;
   memset(&d, 0, sizeof(d));
   d.ndim = 2; d.B = B; d.H = H; d.W = W; d.D = 1;
-  d.Cin = banded_kblocks(Cin, Cout) * 64;          // K elements per (ky,kx) tap
+  d.Cin = banded_kblocks(Cin, Cout, sz) * 64;      // K elements per (ky,kx) tap
   d.Cout = static_cast<int>(Fo); d.cout_pad = static_cast<int>(Fo);
   d.ntaps = 9; d.taps = taps; d.x = x; d.w_packed = w_banded; d.bias = bias_full; d.alpha = alpha_full; d.act = act;
   d.residual = residual; d.residual_is_f32 = residual_is_f32; d.out16 = out16; d.out32 = out32;
   d.o_base = 0; d.o_x = Fo; d.o_y = static_cast<long long>(W) * Fo; d.o_b = static_cast<long long>(H) * W * Fo;
   d.fmt = fmt; d.force_bn = 128;
   d.x_channels = static_cast<int>(Fi);
-  d.a_c_base = -Cin;                                // first input depth of N tile 0 is z = -1 (zero filled)
-  d.a_c_ntile = (128 / Cout) * Cin;                 // each N tile advances 128/Cout depths
+  d.a_c_base = -pz * Cin;                           // first input depth of N tile 0 is z = -pz (zero filled)
+  d.a_c_ntile = (128 / Cout) * sz * Cin;            // each N tile advances 128/Cout output = sz*128/Cout input depths
   d.w_banded = 1;
   if (g_yhalo) d.ny = 3;
   return rn_conv_igemm(&d, stream);

@@ -237,6 +237,9 @@ def conv3d(input_, num_outputs, pad="SAME", reuse=False, kernel_size=[4, 4, 4], 
             b = bias_variable([int(num_outputs)], trainable=trainable, bias_initializer=bias_initializer)
     if list(stride) == [1, 1, 1] and cin % 16 == 0:
         return _deferred_conv("conv3d", input_, w, b, 1)
+    if (USE_BANDED_CONV3D and list(kernel_size) == [3, 3, 3] and list(stride[:2]) == [1, 1] and stride[2] == 2
+            and ops.BandedConv3d.eligible(cin, int(num_outputs), int(input_.shape[3]), 2)):
+        return _deferred_conv("conv3d", input_, w, b, 2)        # e_conv2: z-strided, depth-folded onto the tensor pipe
     return _deferred_direct3d(input_, w, b, list(stride))
 
 
@@ -334,13 +337,17 @@ def _deferred_conv(kind, x, w, b, stride):
     xin = x
     if kind == "conv2d_transpose":
         oshape = (x.shape[0], x.shape[1] * stride, x.shape[2] * stride, w.shape[-2])
+    elif kind == "conv3d":          # `stride` = stride along D (1 or 2); x,y strides are 1
+        oshape = tuple(x.shape[:3]) + (-(-x.shape[3] // stride), w.shape[-1])
     else:
         oshape = tuple(x.shape[:-1]) + (w.shape[-1],)
 
     def run(act, alpha, residual, want32):
         xt = _as16(xin)
         banded = (kind == "conv3d" and USE_BANDED_CONV3D and tuple(w.shape[:3]) == (3, 3, 3)
-                  and ops.BandedConv3d.eligible(int(w.shape[3]), int(w.shape[4]), int(xt.shape[3])))
+                  and ops.BandedConv3d.eligible(int(w.shape[3]), int(w.shape[4]), int(xt.shape[3]), stride))
+        if kind == "conv3d" and stride != 1 and not banded:
+            raise NotImplementedError("z-strided conv3d needs the depth-folded path")
         xfold = 1
         if (kind == "conv2d_transpose" and USE_XFOLD and stride == 1 and residual is None
                 and tuple(w.shape[:2]) == (4, 4)):
@@ -351,13 +358,11 @@ def _deferred_conv(kind, x, w, b, stride):
         if kind == "conv2d":
             return ops.conv2d(xt, L, act=act, residual=residual, want16=want16, want32=want32, alpha=a)
         if kind == "conv3d":
-            D = xt.shape[3]
-            if (USE_BANDED_CONV3D and tuple(w.shape[:3]) == (3, 3, 3)
-                    and ops.BandedConv3d.eligible(int(w.shape[3]), int(w.shape[4]), D)):
-                Lb = _store().packed.get(("banded", w._rn_name))
+            if banded:
+                Lb = _store().packed.get(("banded", w._rn_name, stride))
                 if Lb is None:
-                    Lb = ops.BandedConv3d(w, b, dtype=tf.COMPUTE_DTYPE, device=_store().device)
-                    _store().packed[("banded", w._rn_name)] = Lb
+                    Lb = ops.BandedConv3d(w, b, dtype=tf.COMPUTE_DTYPE, device=_store().device, sz=stride)
+                    _store().packed[("banded", w._rn_name, stride)] = Lb
                 return ops.conv3d_banded(xt, Lb, act=act, residual=residual, alpha=a,
                                          alpha_tag=getattr(alpha, "_rn_name", None), want16=want16, want32=want32)
             return ops.conv3d(xt, L, act=act, residual=residual, want16=want16, want32=want32, alpha=a)

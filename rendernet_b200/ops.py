@@ -166,23 +166,24 @@ class BandedConv3d:
     """Depth-folded 3^3 SAME conv3d (rn_conv3d_banded_same): kernel-ready banded filter + per-depth expanded
     bias / alpha vectors (cached per D)."""
 
-    def __init__(self, w_tf: torch.Tensor, bias: Optional[torch.Tensor], dtype=torch.float16, device="cuda"):
+    def __init__(self, w_tf: torch.Tensor, bias: Optional[torch.Tensor], dtype=torch.float16, device="cuda", sz: int = 1):
         w_tf = torch.as_tensor(w_tf, dtype=torch.float32).to(device).contiguous()
         assert tuple(w_tf.shape[:3]) == (3, 3, 3)
-        self.cin, self.cout = int(w_tf.shape[3]), int(w_tf.shape[4])
-        nbytes = lib.rn_conv3d_banded_bytes(self.cin, self.cout)
+        self.cin, self.cout, self.sz = int(w_tf.shape[3]), int(w_tf.shape[4]), int(sz)
+        nbytes = lib.rn_conv3d_banded_bytes(self.cin, self.cout, self.sz)
         if nbytes < 0:
             raise ValueError("banded conv3d needs Cin | 64 and Cout | 128")
         self.dtype = dtype
         self.w = torch.empty(nbytes // 2, device=device, dtype=dtype)
-        check(lib.rn_pack_conv3d_banded(w_tf.data_ptr(), self.w.data_ptr(), self.cin, self.cout, fmt_of(dtype),
+        check(lib.rn_pack_conv3d_banded(w_tf.data_ptr(), self.w.data_ptr(), self.cin, self.cout, self.sz, fmt_of(dtype),
                                         _stream()), "rn_pack_conv3d_banded")
         self.bias = (bias if bias is not None else torch.zeros(self.cout)).to(device=device, dtype=torch.float32)
         self._full = {}
 
     @staticmethod
-    def eligible(cin: int, cout: int, D: int) -> bool:
-        return cin >= 8 and cout >= 8 and 64 % cin == 0 and 128 % cout == 0 and (D * cout) % 128 == 0
+    def eligible(cin: int, cout: int, D: int, sz: int = 1) -> bool:
+        return (cin >= 8 and cout >= 8 and 64 % cin == 0 and 128 % cout == 0 and sz in (1, 2)
+                and (-(-D // sz) * cout) % 128 == 0 and (D * cin) % 8 == 0)
 
     def expanded(self, v: torch.Tensor, D: int, tag) -> torch.Tensor:
         key = (tag, D)
@@ -202,18 +203,19 @@ def conv3d_banded(x: torch.Tensor, L: BandedConv3d, act: Optional[str] = None,
     x = _cuda(x, L.dtype)
     B, H, W, D, Cin = x.shape
     assert Cin == L.cin
-    out16, out32 = _out_buffers((B, H, W, D, L.cout), L.dtype, x.device, want16, want32, out16, out32)
+    Do = -(-D // L.sz)
+    out16, out32 = _out_buffers((B, H, W, Do, L.cout), L.dtype, x.device, want16, want32, out16, out32)
     res_f32 = 0
     if residual is not None:
         residual = _cuda(residual)
         res_f32 = 1 if residual.dtype == torch.float32 else 0
     a = _ACT[act]
-    bias_full = L.expanded(L.bias, D, "bias")
+    bias_full = L.expanded(L.bias, Do, "bias")
     alpha_full = None
     if a == ACT_PRELU:
-        alpha_full = L.expanded(alpha[:L.cout], D, ("alpha", alpha_tag if alpha_tag is not None else alpha.data_ptr()))
+        alpha_full = L.expanded(alpha[:L.cout], Do, ("alpha", alpha_tag if alpha_tag is not None else alpha.data_ptr()))
     check(lib.rn_conv3d_banded_same(x.data_ptr(), L.w.data_ptr(), bias_full.data_ptr(), _ptr(alpha_full), a,
-                                    _ptr(residual), res_f32, _ptr(out16), _ptr(out32), B, H, W, D, Cin, L.cout,
+                                    _ptr(residual), res_f32, _ptr(out16), _ptr(out32), B, H, W, D, Cin, L.cout, L.sz,
                                     fmt_of(L.dtype), _stream()), "rn_conv3d_banded_same")
     return out16 if not want32 else ((out16, out32) if want16 else out32)
 

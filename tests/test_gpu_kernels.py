@@ -176,6 +176,24 @@ def test_conv3d_same(B, H, W, D, Cin, Cout, path):
     close(y2, orc.conv3d(x, w, b) + torch.from_numpy(res), rel=1.2e-3)
 
 
+@pytest.mark.parametrize("B,H,W,D,Cin,Cout", [(1, 8, 8, 64, 8, 16), (2, 4, 8, 32, 8, 16), (1, 8, 16, 16, 16, 16), (1, 5, 6, 64, 8, 16)])
+def test_conv3d_banded_z_stride2(B, H, W, D, Cin, Cout):
+    """e_conv2's form: 3^3 conv, stride (1,1,2), TF SAME pads (1,1)/(1,1)/(0,1), depth-folded onto the tensor pipe."""
+    ops = _ops()
+    assert ops.BandedConv3d.eligible(Cin, Cout, D, 2)
+    rng = np.random.default_rng(D + Cin)
+    x = q16(rng.standard_normal((B, H, W, D, Cin)))
+    w = q16(rng.standard_normal((3, 3, 3, Cin, Cout)) / np.sqrt(27 * Cin))
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    a = rng.uniform(0, 0.3, Cout).astype(np.float32)
+    L = ops.BandedConv3d(torch.from_numpy(w), torch.from_numpy(b), sz=2)
+    y = ops.conv3d_banded(torch.from_numpy(x).to(dev).half(), L, act="prelu", alpha=torch.from_numpy(a).to(dev),
+                          want16=False, want32=True)
+    ref = orc.prelu(orc.conv3d(x, w, b, (1, 1, 2)), a)
+    assert tuple(y.shape) == tuple(ref.shape) == (B, H, W, D // 2, Cout)
+    close(y, ref, rel=2e-5)
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,s", [(1, 16, 16, 64, 32, 2), (1, 16, 16, 64, 64, 1), (2, 8, 8, 256, 128, 2),
                                                (1, 32, 32, 32, 16, 1), (1, 32, 32, 16, 3, 1), (1, 64, 64, 64, 32, 2),
                                                (1, 7, 9, 16, 16, 2)])
