@@ -98,6 +98,9 @@ typedef struct rn_conv_desc {
   /* y-halo sharing (2-D only): taps ordered tap = ky*nx + kx with dy(ky) = dy(0) + ky; the ny taps of a filter column
    * then share one activation load of BH+ny-1 image rows.  0/1 = off.  tile_w: M-tile width override (0 = 16). */
   int ny, tile_w;
+  /* column split of the output address: n -> (n / o_nsplit) * o_nhi + (n % o_nsplit); 0 = off (multiple of 32) */
+  int o_nsplit;
+  long long o_nhi;
 } rn_conv_desc;
 int rn_conv_igemm(const rn_conv_desc* d, void* stream);
 
@@ -133,6 +136,15 @@ int rn_pack_conv2d_transpose_weights(const float* w, void* packed, int kh, int k
 int rn_conv2d_transpose_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
                              void* out16, float* out32, int B, int H, int W, int Cin, int Cout, int cout_pad,
                              int kh, int kw, int stride, int fmt, void* stream);
+
+/* Stride-2, k = 4 SAME transposed conv (e_conv7/8/9, RenderNet_Shader.py:106-119) as ONE launch: rows = input pixels,
+ * N = (ay, ax, co) = 4*Cout, 9 taps (dy,dx in {-1,0,1}) with the unused phase/tap combinations zero in the packed
+ * filter [9][4*Cout][Cin]; each thread writes two full 2*Cout-element runs of the 2x2 output block.  bias4 / alpha4:
+ * per-Cout vectors tiled 4 times.  (The 4-launch phase form is rn_conv2d_transpose_same.) */
+int rn_pack_conv2d_transpose_s2_merged(const float* w, void* packed, int Cin, int Cout, int fmt, void* stream);
+int rn_conv2d_transpose_s2_merged(const void* x, const void* w_merged, const float* bias4, const float* alpha4, int act,
+                                  void* out16, float* out32, int B, int H, int W, int Cin, int Cout, int fmt,
+                                  void* stream);
 
 /* Thin-channel stride-1 transposed conv (e_conv10 32->16, e_conv11 16->3 at 512^2; RenderNet_Shader.py:122-129) with
  * F = 64/Cin adjacent x-pixels folded into the channel axis: rows of the implicit GEMM are pixel groups, K = F*Cin

@@ -351,7 +351,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             else mbar_arrive(&tempty_bar[acc]);
           }
         }
-        epilogue_chunk<CW>(p, r, t.n0 + c, off, row_valid);
+        const int nc = t.n0 + c;
+        const long long offc = p.o_nsplit > 0 ? off + (nc / p.o_nsplit) * p.o_nhi + (nc % p.o_nsplit) - nc : off;
+        epilogue_chunk<CW>(p, r, nc, offc, row_valid);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -605,6 +607,8 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   p.out16 = d->out16; p.out32 = d->out32; p.res = d->residual; p.res_is_f32 = d->residual_is_f32;
   p.bias = d->bias; p.alpha = d->alpha; p.act = d->act; p.n_valid = d->Cout;
   p.o_base = d->o_base; p.o_b = d->o_b; p.o_y = d->o_y; p.o_x = d->o_x; p.o_z = d->o_z;
+  p.o_nsplit = d->o_nsplit; p.o_nhi = d->o_nhi;
+  if (d->o_nsplit > 0 && (d->o_nsplit % 32 != 0 || d->o_nhi % 8 != 0)) return -15;
   const bool strides8 = (d->o_base % 8 == 0) && (d->o_b % 8 == 0) && (d->o_y % 8 == 0) && (d->o_x % 8 == 0) &&
                         (d->o_z % 8 == 0);
   auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };

@@ -41,6 +41,8 @@ struct alignas(64) IgemmParams {
   int n_valid;                    // real Cout (<= CoutPad); columns beyond are dropped
   int vec_ok;                     // output/residual rows are 16B aligned -> vector path
   long long o_base, o_b, o_y, o_x, o_z;  // output element offset = o_base + b*o_b + y*o_y + x*o_x + z*o_z + n
+  int o_nsplit;                   // > 0: column n lands at (n / o_nsplit) * o_nhi + (n % o_nsplit) instead of n (merged
+  long long o_nhi;                //      phases of a stride-2 transposed conv: n = (ay, ax, co))
 };
 
 }  // namespace rn

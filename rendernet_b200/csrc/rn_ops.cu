@@ -443,6 +443,30 @@ __global__ void pack_xfold_kernel(const float* __restrict__ w, uint16_t* __restr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ merged-phase transposed conv
+// k = 4, stride 2, SAME (pb = 1): o = 2*i + k - 1.  Output (2y+ay, 2x+ax) reads input (y+dy, x+dx) through filter tap
+// ky = ay + 1 - 2*dy (kx likewise) when that lies in [0,4): (ay,dy) in {(0,0)->1, (0,-1)->3, (1,1)->0, (1,0)->2}.
+// Wm[(dy+1)*3 + (dx+1)][(ay*2+ax)*Cout + co][ci].
+__global__ void pack_tconv_s2_merged_kernel(const float* __restrict__ w, uint16_t* __restrict__ packed, int Cin, int Cout,
+                                            int fmt) {
+  const int N = 4 * Cout;
+  const long long total = 9LL * N * Cin;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Cin);
+    const int n = static_cast<int>((i / Cin) % N);
+    const int t = static_cast<int>(i / (static_cast<long long>(Cin) * N));
+    const int dy = t / 3 - 1, dx = t % 3 - 1;
+    const int ay = n / (2 * Cout), ax = (n / Cout) % 2, co = n % Cout;
+    const int ky = ay + 1 - 2 * dy, kx = ax + 1 - 2 * dx;
+    float v = 0.f;
+    if (ky >= 0 && ky < 4 && kx >= 0 && kx < 4) v = w[((static_cast<long long>(ky) * 4 + kx) * Cout + co) * Cin + ci];
+    if (fmt == 0) { __half h = __float2half_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
+    else { __nv_bfloat16 h = __float2bfloat16_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ Phong
 __global__ void phong_kernel(const float* __restrict__ img, const float* __restrict__ light_dir,
                              const float* __restrict__ light_col, float ambient, float k_diffuse, int white,
@@ -852,6 +876,40 @@ extern "C" int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, 
   d.out16 = out16; d.out32 = out32;
   d.o_base = 0; d.o_x = static_cast<long long>(F) * Cout; d.o_y = static_cast<long long>(W) * Cout;
   d.o_b = static_cast<long long>(H) * W * Cout; d.fmt = fmt;
+  return rn_conv_igemm(&d, stream);
+}
+
+
+// ---------------------------------------------------------------------------------- merged-phase transposed conv
+extern "C" int rn_pack_conv2d_transpose_s2_merged(const float* w, void* packed, int Cin, int Cout, int fmt,
+                                                  void* stream) {
+  if (!w || !packed || Cin < 16 || Cout < 16 || Cout % 16 != 0) return -1;
+  pack_tconv_s2_merged_kernel<<<grid_for(9LL * 4 * Cout * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<uint16_t*>(packed), Cin, Cout, fmt);
+  RN_COUNT_LAUNCH();
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_conv2d_transpose_s2_merged(const void* x, const void* w_merged, const float* bias4,
+                                             const float* alpha4, int act, void* out16, float* out32, int B, int H,
+                                             int W, int Cin, int Cout, int fmt, void* stream) {
+  if (Cout % 16 != 0) return -20;
+  int8_t taps[27];
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      int8_t* t = taps + 3 * (ky * 3 + kx);
+      t[0] = static_cast<int8_t>(kx - 1); t[1] = static_cast<int8_t>(ky - 1); t[2] = 0;
+    }
+  const long long Wo = 2LL * W, Ho = 2LL * H;
+  rn_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.ndim = 2; d.B = B; d.H = H; d.W = W; d.D = 1; d.Cin = Cin; d.Cout = 4 * Cout; d.cout_pad = 4 * Cout;
+  d.ntaps = 9; d.taps = taps; d.x = x; d.w_packed = w_merged; d.bias = bias4; d.alpha = alpha4; d.act = act;
+  d.out16 = out16; d.out32 = out32;
+  d.o_base = 0; d.o_x = 2LL * Cout; d.o_y = 2LL * Wo * Cout; d.o_b = Ho * Wo * Cout;
+  d.o_nsplit = 2 * Cout; d.o_nhi = Wo * Cout;      // n = (ay, ax, co): row 2y+ay, columns (2x+ax)*Cout + co
+  d.fmt = fmt;
+  if (Cin % 64 == 0 && g_yhalo) d.ny = 3;
   return rn_conv_igemm(&d, stream);
 }
 

@@ -18,6 +18,7 @@ from . import ops
 from . import tfcompat as tf
 from .tfcompat import Deferred, realize
 
+USE_MERGED_TCONV = True    # one launch (N = 4*Cout, 9 taps) instead of 4 phase launches for k=4 stride-2 transposed convs
 USE_XFOLD = True           # fold x-pixels into channels for thin stride-1 transposed convs (e_conv10/11)
 USE_BANDED_CONV3D = True   # depth-folded tensor-core path for 3^3 convs (falls back to the 5-D TMA path)
 
@@ -352,8 +353,10 @@ def _deferred_conv(kind, x, w, b, stride):
         if (kind == "conv2d_transpose" and USE_XFOLD and stride == 1 and residual is None
                 and tuple(w.shape[:2]) == (4, 4)):
             xfold = ops.XFoldConvT.factor(int(w.shape[3]), int(xt.shape[2]))
-        L = None if (banded or xfold > 1) else _packed(w, b, kind, stride)
-        a = None if xfold > 1 else _alpha_arg(alpha, ops.round_up(int(w.shape[-1]), 16) if banded else L.cout_pad)
+        merged = (kind == "conv2d_transpose" and USE_MERGED_TCONV and stride == 2 and residual is None
+                  and tuple(w.shape[:2]) == (4, 4) and ops.MergedConvT2.eligible(int(w.shape[3]), int(w.shape[2])))
+        L = None if (banded or xfold > 1 or merged) else _packed(w, b, kind, stride)
+        a = None if (xfold > 1 or merged) else _alpha_arg(alpha, ops.round_up(int(w.shape[-1]), 16) if banded else L.cout_pad)
         want16 = not want32
         if kind == "conv2d":
             return ops.conv2d(xt, L, act=act, residual=residual, want16=want16, want32=want32, alpha=a)
@@ -366,6 +369,16 @@ def _deferred_conv(kind, x, w, b, stride):
                 return ops.conv3d_banded(xt, Lb, act=act, residual=residual, alpha=a,
                                          alpha_tag=getattr(alpha, "_rn_name", None), want16=want16, want32=want32)
             return ops.conv3d(xt, L, act=act, residual=residual, want16=want16, want32=want32, alpha=a)
+        if merged:
+            Lm = _store().packed.get(("merged", w._rn_name))
+            if Lm is None:
+                Lm = ops.MergedConvT2(w, b, dtype=tf.COMPUTE_DTYPE, device=_store().device)
+                _store().packed[("merged", w._rn_name)] = Lm
+            al = None
+            if act == "prelu":
+                al = _dev_vec(alpha) if not isinstance(alpha, str) else torch.zeros(int(w.shape[2]), device=xt.device)
+            return ops.conv2d_transpose_s2_merged(xt, Lm, act=act, alpha=al, alpha_tag=getattr(alpha, "_rn_name", None),
+                                                  want16=want16, want32=want32)
         if xfold > 1:
             F = xfold
             Lx = _store().packed.get(("xfold", w._rn_name, F))

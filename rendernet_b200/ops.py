@@ -236,6 +236,46 @@ def conv2d_transpose(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, 
     return out16 if not want32 else ((out16, out32) if want16 else out32)
 
 
+class MergedConvT2:
+    """k=4 stride-2 SAME transposed conv as one launch (rn_conv2d_transpose_s2_merged)."""
+
+    def __init__(self, w_tf: torch.Tensor, bias: Optional[torch.Tensor], dtype=torch.float16, device="cuda"):
+        w_tf = torch.as_tensor(w_tf, dtype=torch.float32).to(device).contiguous()
+        assert tuple(w_tf.shape[:2]) == (4, 4)
+        self.cout, self.cin, self.dtype = int(w_tf.shape[2]), int(w_tf.shape[3]), dtype
+        self.w = torch.empty((9, 4 * self.cout, self.cin), device=device, dtype=dtype)
+        check(lib.rn_pack_conv2d_transpose_s2_merged(w_tf.data_ptr(), self.w.data_ptr(), self.cin, self.cout, fmt_of(dtype),
+                                                     _stream()), "pack merged tconv")
+        b = bias if bias is not None else torch.zeros(self.cout)
+        self.bias = b.to(device=device, dtype=torch.float32).reshape(-1).repeat(4).contiguous()
+        self._alpha = {}
+
+    @staticmethod
+    def eligible(cin: int, cout: int) -> bool:
+        return cin % 16 == 0 and cout % 16 == 0
+
+
+def conv2d_transpose_s2_merged(x: torch.Tensor, L: MergedConvT2, act: Optional[str] = None,
+                               alpha: Optional[torch.Tensor] = None, alpha_tag=None, want16: bool = True,
+                               want32: bool = False, out16=None, out32=None):
+    x = _cuda(x, L.dtype)
+    B, H, W, Cin = x.shape
+    assert Cin == L.cin
+    out16, out32 = _out_buffers((B, 2 * H, 2 * W, L.cout), L.dtype, x.device, want16, want32, out16, out32)
+    a = _ACT[act]
+    alpha4 = None
+    if a == ACT_PRELU:
+        key = alpha_tag if alpha_tag is not None else alpha.data_ptr()
+        alpha4 = L._alpha.get(key)
+        if alpha4 is None:
+            alpha4 = alpha.to(device=x.device, dtype=torch.float32).reshape(-1)[: L.cout].repeat(4).contiguous()
+            L._alpha[key] = alpha4
+    check(lib.rn_conv2d_transpose_s2_merged(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(), _ptr(alpha4), a, _ptr(out16),
+                                            _ptr(out32), B, H, W, Cin, L.cout, fmt_of(L.dtype), _stream()),
+          "rn_conv2d_transpose_s2_merged")
+    return out16 if not want32 else ((out16, out32) if want16 else out32)
+
+
 class XFoldConvT:
     """Stride-1 transposed conv with thin channels, x-folded (rn_conv2d_transpose_s1_xfold)."""
 

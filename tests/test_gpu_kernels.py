@@ -250,6 +250,23 @@ def test_conv2d_yhalo_sharing(B, H, W, Cin, Cout, tw):
     close(y, orc.conv2d(x, w, b), rel=2e-5)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 16, 16, 64, 32), (2, 8, 8, 256, 128), (1, 7, 9, 16, 16), (1, 32, 32, 128, 64)])
+def test_conv2d_transpose_s2_merged(B, H, W, Cin, Cout):
+    """One-launch form of the k=4 stride-2 transposed conv (N = 4*Cout, 9 taps, split output addressing) vs the oracle."""
+    ops = _ops()
+    rng = np.random.default_rng(Cin + Cout + H)
+    x = q16(rng.standard_normal((B, H, W, Cin)))
+    w = q16(rng.standard_normal((4, 4, Cout, Cin)) / np.sqrt(4 * Cin))
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    a = rng.uniform(0, 0.3, Cout).astype(np.float32)
+    L = ops.MergedConvT2(torch.from_numpy(w), torch.from_numpy(b))
+    y16, y32 = ops.conv2d_transpose_s2_merged(torch.from_numpy(x).to(dev).half(), L, act="prelu",
+                                              alpha=torch.from_numpy(a).to(dev), want32=True)
+    ref = orc.prelu(orc.conv2d_transpose(x, w, b, (2, 2)), a)
+    close(y32, ref, rel=2e-5)
+    close(y16, ref, rel=1.2e-3)
+
+
 def test_conv_bf16_variant():
     ops = _ops()
     rng = np.random.default_rng(3)
