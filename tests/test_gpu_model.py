@@ -98,4 +98,4 @@ def test_engine_pipelined_submit_matches_blocking_render():
     for w, g in zip(want, got):
         assert torch.equal(w, g)
     assert not torch.equal(want[0], want[1])
-    assert eng.launches_per_step == 75
+    assert eng.launches_per_step == 66      # 1 resample + 1 direct + 64 tensor-core launches
