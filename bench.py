@@ -268,10 +268,11 @@ def run_ours(args, rank, world, local_rank):
                          "PyTorch-CPU oneDNN fp32 restatement of the TF-1 graph), after 1 warm-up"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp16 operands / fp32 accumulate", "data": "synthetic",
+            "dtype": "fp16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "per_gpu_batch": B,
                        "parallelism": f"dp{world} (batch sharded; NCCL all-gather of output images)" if world > 1 else "single GPU",
                        "weights": "reference initialisers (xavier-uniform, seeded); random-init, no checkpoint exists offline",
+                       "precision": "fp16 operands and stored activations, fp32 accumulation / epilogue, fp32 input grid and output image",
                        "cuda_graph": eng.graph is not None,
                        "l2": "no explicit flush: every layer streams 200-800 MB of activations (> 126 MB L2) per step"},
             "clocks": clocks,

@@ -83,23 +83,14 @@ def RenderNet(models_in, is_training=False, prob=0.75, reuse=False, is_greyscale
                                      activation_fn=None, scope='e_conv6'))
             enc6 = tf.nn.dropout(enc6, keep_prob(prob, is_training))
 
-        with tf.variable_scope('e_conv7'):
-            enc7 = prelu(slim.conv2d_transpose(enc6, 32 * 4, (4, 4), stride=2, activation_fn=None, scope='e_conv7'))
-            enc7 = tf.nn.dropout(enc7, keep_prob(prob, is_training))
-        with tf.variable_scope('e_conv7_1'):
-            enc7_1 = prelu(slim.conv2d_transpose(enc7, 32 * 4, (4, 4), stride=1, activation_fn=None,
-                                                 scope='e_conv7_1'))
-            enc7_1 = tf.nn.dropout(enc7_1, keep_prob(prob, is_training))
-        with tf.variable_scope('e_conv8'):
-            enc8 = prelu(slim.conv2d_transpose(enc7_1, 32 * 2, (4, 4), stride=2, activation_fn=None, scope='e_conv8'))
-            enc8 = tf.nn.dropout(enc8, keep_prob(prob, is_training))
-        with tf.variable_scope('e_conv9'):
-            enc9 = prelu(slim.conv2d_transpose(enc8, 32, (4, 4), stride=2, activation_fn=None, scope='e_conv9'))
-            enc9 = tf.nn.dropout(enc9, keep_prob(prob, is_training))
-        with tf.variable_scope('e_conv10'):
-            enc10 = prelu(slim.conv2d_transpose(enc9, 16, (4, 4), stride=1, activation_fn=None, scope='e_conv10'))
-            enc10 = tf.nn.dropout(enc10, keep_prob(prob, is_training))
-
+        # e_conv7 .. e_conv10: 4x4 transposed convs (stride 2,1,2,2,1) + PReLU; variable scopes <name>/<name> (:105-123)
+        net = enc6
+        for name, ch, stride in (('e_conv7', 32 * 4, 2), ('e_conv7_1', 32 * 4, 1), ('e_conv8', 32 * 2, 2),
+                                 ('e_conv9', 32, 2), ('e_conv10', 16, 1)):
+            with tf.variable_scope(name):
+                net = prelu(slim.conv2d_transpose(net, ch, (4, 4), stride=stride, activation_fn=None, scope=name))
+                net = tf.nn.dropout(net, keep_prob(prob, is_training))
+        enc10 = net
         keep('enc10', enc10)
         n_out = 1 if is_greyscale else 3                                 # cfg['is_greyscale'] (:125)
         enc11 = slim.conv2d_transpose(enc10, n_out, (4, 4), stride=1, activation_fn=None, scope='e_conv11')

@@ -83,46 +83,32 @@ def RenderNet(models_in, prob=0.75, reuse=False, is_training=False):
             enc5_skip = tf.add(tf.cast(enc5_skip, tf.float32), tf.cast(shortcut, tf.float32))
         enc5_skip = realize(enc5_skip)       # consumed by both heads
 
-        with tf.variable_scope("Image"):
-            with tf.variable_scope('e_conv6_1'):
-                enc6_1 = prelu(conv2d(enc5_skip, 32 * 4, kernel_size=[4, 4], stride=[1, 1], scope='e_conv6_1',
-                                      weight_initializer_type=xavier()))
-                enc6_1 = tf.nn.dropout(enc6_1, keep_prob(prob, is_training))
-            with tf.variable_scope('e_conv7_1'):
-                enc7_1 = prelu(conv2d_transpose(enc6_1, 32 * 2, [4, 4], stride=[2, 2], scope='e_conv7_2',
-                                                weight_initializer_type=xavier()))
-                enc7_1 = tf.nn.dropout(enc7_1, keep_prob(prob, is_training))
-            with tf.variable_scope('e_conv8_1'):
-                enc8_1 = prelu(conv2d_transpose(enc7_1, 32, [4, 4], stride=[2, 2], weight_initializer_type=xavier()))
-                enc8_1 = tf.nn.dropout(enc8_1, keep_prob(prob, is_training))
-            with tf.variable_scope('e_conv9_1'):
-                enc9_1 = prelu(conv2d_transpose(enc8_1, 16, [4, 4], stride=[2, 2], weight_initializer_type=xavier()))
-                enc9_1 = tf.nn.dropout(enc9_1, keep_prob(prob, is_training))
-            with tf.variable_scope('e_conv10_1'):
-                enc10_1 = conv2d_transpose(enc9_1, 3, [4, 4], stride=[1, 1], weight_initializer_type=xavier())
-                enc10_1 = tf.nn.sigmoid(enc10_1, name="encoder_output")
+        # Two heads with the reference's (irregular) scope names (:113-145):
+        #   Image : e_conv6_1/e_conv6_1, e_conv7_1/e_conv7_2 (sic), e_conv8_1|9_1|10_1/conv2d_transpose (default scope)
+        #   Normal: e_conv6_2/e_conv6_2, e_conv7_2/e_conv7_2, e_conv8_2/e_conv8_2, e_conv9_2/e_conv9_2, e_conv10_2/e_conv10_2
+        heads = (("Image", "1", {"7": "e_conv7_2", "8": None, "9": None, "10": None}),
+                 ("Normal", "2", {"7": "e_conv7_2", "8": "e_conv8_2", "9": "e_conv9_2", "10": "e_conv10_2"}))
+        outs = []
+        for head, sfx, inner in heads:
+            def tconv(x, ch, stride, blk):
+                kw = dict(weight_initializer_type=xavier())
+                if inner[blk] is not None:
+                    kw["scope"] = inner[blk]
+                return conv2d_transpose(x, ch, [4, 4], stride=[stride, stride], **kw)
 
-        with tf.variable_scope("Normal"):
-            with tf.variable_scope('e_conv6_2'):
-                enc6_2 = prelu(conv2d(enc5_skip, 32 * 4, kernel_size=[4, 4], stride=[1, 1], scope='e_conv6_2',
-                                      weight_initializer_type=xavier()))
-                enc6_2 = tf.nn.dropout(enc6_2, keep_prob(prob, is_training))
-            with tf.variable_scope('e_conv7_2'):
-                enc7_2 = prelu(conv2d_transpose(enc6_2, 32 * 2, [4, 4], stride=[2, 2], scope='e_conv7_2',
-                                                weight_initializer_type=xavier()))
-                enc7_2 = tf.nn.dropout(enc7_2, keep_prob(prob, is_training))
-            with tf.variable_scope('e_conv8_2'):
-                enc8_2 = prelu(conv2d_transpose(enc7_2, 32, [4, 4], stride=[2, 2], scope='e_conv8_2',
-                                                weight_initializer_type=xavier()))
-                enc8_2 = tf.nn.dropout(enc8_2, keep_prob(prob, is_training))
-            with tf.variable_scope('e_conv9_2'):
-                enc9_2 = prelu(conv2d_transpose(enc8_2, 16, [4, 4], stride=[2, 2], scope='e_conv9_2',
-                                                weight_initializer_type=xavier()))
-                enc9_2 = tf.nn.dropout(enc9_2, keep_prob(prob, is_training))
-            with tf.variable_scope('e_conv10_2'):
-                enc10_2 = conv2d_transpose(enc9_2, 3, [4, 4], stride=[1, 1], scope='e_conv10_2',
-                                           weight_initializer_type=xavier())
-                enc10_2 = tf.nn.sigmoid(enc10_2, name="encoder_output")
+            with tf.variable_scope(head):
+                with tf.variable_scope('e_conv6_' + sfx):
+                    net = prelu(conv2d(enc5_skip, 32 * 4, kernel_size=[4, 4], stride=[1, 1], scope='e_conv6_' + sfx,
+                                       weight_initializer_type=xavier()))
+                    net = tf.nn.dropout(net, keep_prob(prob, is_training))
+                for blk, ch in (("7", 32 * 2), ("8", 32), ("9", 16)):
+                    with tf.variable_scope('e_conv%s_%s' % (blk, sfx)):
+                        net = prelu(tconv(net, ch, 2, blk))
+                        net = tf.nn.dropout(net, keep_prob(prob, is_training))
+                with tf.variable_scope('e_conv10_' + sfx):
+                    net = tf.nn.sigmoid(tconv(net, 3, 1, "10"), name="encoder_output")
+            outs.append(net)
+        enc10_1, enc10_2 = outs
 
         return realize(enc10_1), realize(enc10_2)
 

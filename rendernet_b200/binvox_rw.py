@@ -1,46 +1,54 @@
-"""NumPy-2-safe mirror of the reader half of the reference's tools/binvox_rw.py (:45-93)."""
+"""NumPy-2-safe reader for `#binvox 1` voxel files with the call surface of the reference's tools/binvox_rw.py
+(`read_as_3d_array(fp, fix_coords=True)` -> object with `.data/.dims/.translate/.scale/.axis_order`; :45-93).
+
+Format: an ASCII header (`#binvox 1`, `dim X Y Z`, `translate tx ty tz`, `scale s`, `data`) followed by run-length
+(value, count) byte pairs in x-z-y order; `fix_coords` re-orders the axes to x-y-z.
+"""
 from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List
 
 import numpy as np
 
 
-class Voxels(object):
-    """:10-43."""
+@dataclass
+class Voxels:
+    data: np.ndarray
+    dims: List[int]
+    translate: List[float]
+    scale: float
+    axis_order: str = "xyz"
+    meta: dict = field(default_factory=dict)
 
-    def __init__(self, data, dims, translate, scale, axis_order):
-        self.data = data
-        self.dims = dims
-        self.translate = translate
-        self.scale = scale
-        assert axis_order in ('xzy', 'xyz')
-        self.axis_order = axis_order
-
-    def clone(self):
-        return Voxels(self.data.copy(), self.dims[:], self.translate[:], self.scale, self.axis_order)
+    def clone(self) -> "Voxels":
+        return Voxels(self.data.copy(), list(self.dims), list(self.translate), self.scale, self.axis_order, dict(self.meta))
 
 
 def read_header(fp):
-    """:45-56."""
-    line = fp.readline().strip()
-    if not line.startswith(b'#binvox'):
-        raise IOError('Not a binvox file')
-    dims = list(map(int, fp.readline().strip().split(b' ')[1:]))
-    translate = list(map(float, fp.readline().strip().split(b' ')[1:]))
-    scale = list(map(float, fp.readline().strip().split(b' ')[1:]))[0]
-    fp.readline()
+    """Parse the five header lines; returns (dims, translate, scale)."""
+    magic = fp.readline().strip()
+    if not magic.startswith(b"#binvox"):
+        raise IOError("Not a binvox file")
+    fields = {}
+    for _ in range(3):
+        key, *vals = fp.readline().split()
+        fields[key] = vals
+    if fp.readline().strip() != b"data":
+        raise IOError("binvox header: 'data' marker missing")
+    dims = [int(v) for v in fields[b"dim"]]
+    translate = [float(v) for v in fields[b"translate"]]
+    scale = float(fields[b"scale"][0])
     return dims, translate, scale
 
 
-def read_as_3d_array(fp, fix_coords=True):
-    """:58-93: RLE (value,count) byte pairs -> bool[dims]; xzy -> xyz transpose when fix_coords."""
+def read_as_3d_array(fp, fix_coords=True) -> Voxels:
     dims, translate, scale = read_header(fp)
-    raw_data = np.frombuffer(fp.read(), dtype=np.uint8)
-    values, counts = raw_data[::2], raw_data[1::2]
-    data = np.repeat(values, counts).astype(bool)
-    data = data.reshape(dims)
+    pairs = np.frombuffer(fp.read(), dtype=np.uint8).reshape(-1, 2)
+    dense = np.repeat(pairs[:, 0] != 0, pairs[:, 1].astype(np.int64))
+    if dense.size != int(np.prod(dims)):
+        raise IOError(f"binvox payload decodes to {dense.size} voxels, header says {int(np.prod(dims))}")
+    grid = dense.reshape(dims)                     # stored x, z, y
     if fix_coords:
-        data = np.transpose(data, (0, 2, 1))
-        axis_order = 'xyz'
-    else:
-        axis_order = 'xzy'
-    return Voxels(data, dims, translate, scale, axis_order)
+        return Voxels(np.ascontiguousarray(grid.transpose(0, 2, 1)), dims, translate, scale, "xyz")
+    return Voxels(grid, dims, translate, scale, "xzy")
