@@ -205,13 +205,6 @@ def add(a, b):
     return ops.bias_act(a, None, None, None, residual=b)
 
 
-def prelu_apply(x, alpha: torch.Tensor):
-    if isinstance(x, Deferred) and x.open and x.act is None and x.residual is None:
-        x.act, x.alpha = "prelu", alpha
-        return x
-    return ops.bias_act(realize(x), None, alpha, "prelu")
-
-
 def cond(pred, true_fn, false_fn):
     return true_fn() if bool(pred) else false_fn()
 
@@ -239,7 +232,7 @@ class _NN:
 
     @staticmethod
     def relu(x):
-        zero = None
+        """tf.nn.relu == PReLU with slope 0 (the reference's weight_dict branches, layer_util.py:76,109)."""
         if isinstance(x, Deferred) and x.open and x.act is None and x.residual is None:
             x.act, x.alpha = "prelu", "zeros"
             return x
