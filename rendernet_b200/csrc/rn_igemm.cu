@@ -50,8 +50,8 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile,
 }
 
 template <int CW>
-__device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint32_t (&r)[32], int n0, long long off,
-                                               bool row_valid) {
+__device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint32_t* __restrict__ r, int n0,
+                                               long long off, bool row_valid) {
   if (!row_valid) return;
   float v[CW];
 #pragma unroll
@@ -337,13 +337,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      // TMEM reads queue behind the MMAs already issued for the next tile (~2000 cycles each, measured), so fetch as
+      // many columns per tcgen05.ld as registers allow (SC = 128) instead of one 32-column chunk at a time: with
+      // short-K tiles (projection unit, banded 3^3 convs) the epilogue was the bottleneck.
+      constexpr int SC = (BN >= 128) ? 128 : BN;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += CW) {
-        uint32_t r[32];
-        if constexpr (CW == 32) tmem_ld_32x32b_x32(taddr + c, r);
-        else tmem_ld_32x32b_x16(taddr + c, r);
+      for (int sc = 0; sc < BN; sc += SC) {
+        uint32_t r[SC];
+        if constexpr (SC == 128) tmem_ld_32x32b_x128(taddr + sc, r);
+        else if constexpr (SC == 64) tmem_ld_32x32b_x64(taddr + sc, r);
+        else if constexpr (SC == 32) tmem_ld_32x32b_x32(taddr + sc, r);
+        else tmem_ld_32x32b_x16(taddr + sc, r);
         tmem_ld_wait();
-        if (c + CW >= BN) {  // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+        if (sc + SC >= BN) {  // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -351,9 +357,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             else mbar_arrive(&tempty_bar[acc]);
           }
         }
-        const int nc = t.n0 + c;
-        const long long offc = p.o_nsplit > 0 ? off + (nc / p.o_nsplit) * p.o_nhi + (nc % p.o_nsplit) - nc : off;
-        epilogue_chunk<CW>(p, r, nc, offc, row_valid);
+#pragma unroll
+        for (int c = 0; c < SC; c += CW) {
+          const int nc = t.n0 + sc + c;
+          const long long offc = p.o_nsplit > 0 ? off + (nc / p.o_nsplit) * p.o_nhi + (nc % p.o_nsplit) - nc : off;
+          epilogue_chunk<CW>(p, r + c, nc, offc, row_valid);
+        }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
