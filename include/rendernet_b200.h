@@ -35,6 +35,7 @@ long long rn_launch_count(void);
 int rn_set_default_cluster(int cluster);
 int rn_set_default_cta_group(int cta_group);
 int rn_set_yhalo(int on);         /* y-halo sharing in rn_conv2d_same (3x3) / rn_conv3d_banded_same; default on */
+int rn_set_tma_store(int on);     /* TMA-store epilogue for dense 16-bit outputs; default on */
 int rn_set_default_kps(int kps); /* k-iterations per smem pipeline stage, 0 = heuristic (tuning aid) */
 
 /* ---- resampler ----------------------------------------------------------------------------------

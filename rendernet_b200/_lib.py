@@ -39,6 +39,7 @@ SIGNATURES = {
     "rn_set_default_cta_group": (_i, [_i]),
     "rn_set_default_kps": (_i, [_i]),
     "rn_set_yhalo": (_i, [_i]),
+    "rn_set_tma_store": (_i, [_i]),
     "rn_resample_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rn_pack_conv_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "rn_cast_f32_to_16": (_i, [_vp, _vp, _ll, _ll, _i, _vp]),

@@ -49,10 +49,13 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile,
   return t;
 }
 
+// stg != 0: the 16-bit result goes to the shared-memory staging panel (row `m`, 16-byte chunk index `chunk0`..) in the
+// TMA swizzle of a `prow`-byte row instead of to global memory (the residual is still read from global).
 template <int CW>
 __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint32_t* __restrict__ r, int n0,
-                                               long long off, bool row_valid) {
-  if (!row_valid) return;
+                                               long long off, bool row_valid, uint32_t stg = 0, int m = 0,
+                                               int chunk0 = 0, int prow = 128) {
+  if (!row_valid && stg == 0) return;
   float v[CW];
 #pragma unroll
   for (int i = 0; i < CW; i += 4) {
@@ -77,7 +80,7 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
   }
   const bool full = p.vec_ok && (n0 + CW <= p.n_valid);
   if (full) {
-    if (p.res != nullptr) {
+    if (p.res != nullptr && row_valid) {
       if (p.res_is_f32) {
         const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + off + n0);
 #pragma unroll
@@ -104,6 +107,7 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
     }
     if (p.out16 != nullptr) {
       uint4* op = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out16) + off + n0);
+      const int sw = prow == 128 ? (m & 7) : (prow == 64 ? ((m >> 1) & 3) : ((m >> 2) & 1));
 #pragma unroll
       for (int i = 0; i < CW / 8; ++i) {
         uint32_t w[4];
@@ -117,7 +121,8 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
             w[j] = *reinterpret_cast<uint32_t*>(&h);
           }
         }
-        op[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        if (stg != 0) st_shared_v4(stg + m * prow + (((chunk0 + i) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+        else op[i] = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
     if (p.out32 != nullptr) {
@@ -176,10 +181,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
   uint64_t* tfull_bar = empty_bar + p.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  // TMA-store staging panel (128 rows x <=128 B, swizzled), 1024-aligned, after the barrier block
+  const uint32_t stg_base = (smem_u32(smem) + static_cast<uint32_t>(p.stages) * stage_bytes + 256u + 1023u) & ~1023u;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    if (p.tma_store) tma_prefetch_desc(&p.tmO);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], CG == 2 ? 1 : CL);
@@ -341,6 +349,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       // many columns per tcgen05.ld as registers allow (SC = 128) instead of one 32-column chunk at a time: with
       // short-K tiles (projection unit, banded 3^3 convs) the epilogue was the bottleneck.
       constexpr int SC = (BN >= 128) ? 128 : BN;
+      constexpr int PC = (BN >= 64) ? 64 : BN;        // staging panel columns (one TMA store box)
+      const bool tma_out = p.tma_store != 0;
+      const uint64_t mapO = reinterpret_cast<uint64_t>(&p.tmO);
 #pragma unroll 1
       for (int sc = 0; sc < BN; sc += SC) {
         uint32_t r[SC];
@@ -357,11 +368,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             else mbar_arrive(&tempty_bar[acc]);
           }
         }
+        if (!tma_out) {
 #pragma unroll
-        for (int c = 0; c < SC; c += CW) {
-          const int nc = t.n0 + sc + c;
-          const long long offc = p.o_nsplit > 0 ? off + (nc / p.o_nsplit) * p.o_nhi + (nc % p.o_nsplit) - nc : off;
-          epilogue_chunk<CW>(p, r + c, nc, offc, row_valid);
+          for (int c = 0; c < SC; c += CW) {
+            const int nc = t.n0 + sc + c;
+            const long long offc = p.o_nsplit > 0 ? off + (nc / p.o_nsplit) * p.o_nhi + (nc % p.o_nsplit) - nc : off;
+            epilogue_chunk<CW>(p, r + c, nc, offc, row_valid);
+          }
+        } else {
+          // panel by panel: registers -> swizzled smem -> one TMA store (full 128-byte lines, edges clipped by TMA)
+#pragma unroll
+          for (int pc = 0; pc < SC; pc += PC) {
+            named_bar_sync(1, 128);                      // the previous panel's store has finished reading the staging buffer
+#pragma unroll
+            for (int c = 0; c < PC; c += CW)
+              epilogue_chunk<CW>(p, r + pc + c, t.n0 + sc + pc + c, off, row_valid, stg_base, m, c / 8, PC * 2);
+            fence_proxy_async();
+            named_bar_sync(1, 128);                      // panel complete and visible to the async proxy
+            if (warp == 2 && lane == 0) {
+              tma_store_4d(mapO, stg_base, t.n0 + sc + pc, t.x0, t.y0, t.b);
+              tma_store_commit();
+              tma_store_wait_read();                     // staging buffer may be overwritten after this
+            }
+          }
         }
       }
       acc ^= 1;
@@ -369,6 +398,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     }
   }
 
+  if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync();   // no CTA exits while a peer may still multicast into / commit to it
@@ -397,6 +427,7 @@ static CUtensorMapSwizzle swizzle_of(int row_bytes) {
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+int g_tma_store = 1;                         // TMA-store epilogue where the output is a dense 16-bit NHWC tensor
 int g_default_kps = 0;                       // k-iterations per pipeline stage override (0 = heuristic)
 int g_default_cta_group = 2;                 // 2: paired tcgen05.mma.cta_group::2 tiles where the shape allows
 int g_default_cluster = 2;                   // B-multicast cluster size used when the descriptor says 0 (auto)
@@ -448,6 +479,12 @@ static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaSt
 extern "C" int rn_set_default_cluster(int c) {
   const int prev = rn::g_default_cluster;
   if (c == 1 || c == 2 || c == 4) rn::g_default_cluster = c;
+  return prev;
+}
+
+extern "C" int rn_set_tma_store(int on) {
+  const int prev = rn::g_tma_store;
+  rn::g_tma_store = on ? 1 : 0;
   return prev;
 }
 
@@ -520,7 +557,14 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   p.ab_fmt = d->fmt;
   p.rank = d->ndim == 3 ? 5 : 4;
   p.W = d->W; p.H = d->H; p.D = D; p.B = d->B;
-  const int budget = 232448 - 1024 - 256;
+  // TMA-store epilogue: dense 16-bit NHWC output only (no fp32 copy, no ragged / split columns)
+  const int PCh = BN >= 64 ? 64 : BN;
+  const bool dense_out = d->ndim == 2 && d->o_nsplit == 0 && d->o_base == 0 && d->o_z == 0 && d->o_x == d->cout_pad &&
+                         d->o_y == static_cast<long long>(d->W) * d->o_x && d->o_b == static_cast<long long>(d->H) * d->o_y;
+  p.tma_store = (g_tma_store && d->out16 != nullptr && d->out32 == nullptr && d->Cout == d->cout_pad && dense_out &&
+                 (reinterpret_cast<uintptr_t>(d->out16) & 15) == 0) ? 1 : 0;
+  const int stg_bytes = p.tma_store ? (kTileM * PCh * 2 + 1024) : 0;
+  const int budget = 232448 - 1024 - 256 - stg_bytes;
   int grid = 0, CL = 1, CG = 1, sub = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     int rem = kTileM;
@@ -574,7 +618,7 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
     p.ny = 1;                               // retry without halo sharing
   }
   if (p.stages < 2) return -10;
-  const size_t smem = static_cast<size_t>(p.stages) * p.kps * sub + 1024 + 256;
+  const size_t smem = static_cast<size_t>(p.stages) * p.kps * sub + 1024 + 256 + stg_bytes;
 
 
   const CUtensorMapDataType dt = d->fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -613,6 +657,15 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   }
   if (r != CUDA_SUCCESS) return 2000 + static_cast<int>(r);
 
+  if (p.tma_store) {
+    const cuuint64_t Ct = static_cast<cuuint64_t>(d->cout_pad);
+    const cuuint64_t dims[4] = {Ct, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    const cuuint64_t strides[3] = {Ct * 2, Ct * 2 * d->W, Ct * 2 * d->W * d->H};
+    const cuuint32_t box[4] = {(cuuint32_t)PCh, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
+    r = enc(&p.tmO, dt, 4, d->out16, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(PCh * 2),
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 3000 + static_cast<int>(r);
+  }
   p.out16 = d->out16; p.out32 = d->out32; p.res = d->residual; p.res_is_f32 = d->residual_is_f32;
   p.bias = d->bias; p.alpha = d->alpha; p.act = d->act; p.n_valid = d->Cout;
   p.o_base = d->o_base; p.o_b = d->o_b; p.o_y = d->o_y; p.o_x = d->o_x; p.o_z = d->o_z;

@@ -13,6 +13,7 @@ enum Act : int { ACT_NONE = 0, ACT_PRELU = 1, ACT_SIGMOID = 2 };
 struct alignas(64) IgemmParams {
   CUtensorMap tmA;  // activations, channel-last: rank 4 {C,W,H,B} or rank 5 {C,D,W,H,B}; box {KB,[BD],BW,BH,1}
   CUtensorMap tmB;  // weights [tap][CoutPad][Cin]: rank 3 {Cin,CoutPad,taps}; box {KB,BN,1}
+  CUtensorMap tmO;  // 16-bit output {Cout,W,H,B}; box {panel cols (<=64), BW, BH, 1}: TMA-store epilogue (tma_store != 0)
   int rank;
   int W, H, D, B;                 // extents of the output (== input) pixel space; D = 1 for rank 4
   int BW, BH, BD;                 // M tile box, BW*BH*BD == 128
@@ -41,6 +42,7 @@ struct alignas(64) IgemmParams {
   int n_valid;                    // real Cout (<= CoutPad); columns beyond are dropped
   int vec_ok;                     // output/residual rows are 16B aligned -> vector path
   long long o_base, o_b, o_y, o_x, o_z;  // output element offset = o_base + b*o_b + y*o_y + x*o_x + z*o_z + n
+  int tma_store;                  // 1: epilogue stages 64-column panels in swizzled smem and stores them with TMA
   int o_nsplit;                   // > 0: column n lands at (n / o_nsplit) * o_nhi + (n % o_nsplit) instead of n (merged
   long long o_nhi;                //      phases of a stride-2 transposed conv: n = (ay, ax, co))
 };
