@@ -267,6 +267,34 @@ def test_conv2d_transpose_s2_merged(B, H, W, Cin, Cout):
     close(y16, ref, rel=1.2e-3)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(2, 16, 16, 64, 256, 3), (1, 24, 20, 64, 64, 3), (1, 5, 9, 32, 32, 3),
+                                              (1, 64, 64, 128, 16, 1), (3, 32, 32, 128, 128, 4)])
+def test_tma_store_epilogue_bit_identical(B, H, W, Cin, Cout, k):
+    """The TMA-store epilogue (swizzled smem panels + cp.async.bulk.tensor store, edges clipped by the hardware) writes
+    exactly what the direct-store epilogue writes -- incl. ragged tiles, residual adds and untouched neighbours."""
+    ops = _ops()
+    from rendernet_b200._lib import lib
+    rng = np.random.default_rng(B * H + Cout)
+    x = torch.from_numpy(q16(rng.standard_normal((B, H, W, Cin)))).to(dev).half()
+    w = torch.from_numpy(q16(rng.standard_normal((k, k, Cin, Cout)) / np.sqrt(k * k * Cin)))
+    L = ops.pack_conv("conv2d", w, torch.from_numpy((rng.standard_normal(Cout) * 0.1).astype(np.float32)),
+                      torch.from_numpy(rng.uniform(0, 0.3, Cout).astype(np.float32)))
+    res = torch.from_numpy(q16(rng.standard_normal((B, H, W, Cout)))).to(dev).half()
+    outs = []
+    for on in (0, 1):
+        prev = lib.rn_set_tma_store(on)
+        try:
+            y1 = ops.conv2d(x, L, act="prelu")
+            y2 = ops.conv2d(x, L, act=None, residual=res)
+            torch.cuda.synchronize()
+        finally:
+            lib.rn_set_tma_store(prev)
+        outs.append((y1.clone(), y2.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    close(outs[1][0], orc.prelu(orc.conv2d(x.float().cpu().numpy(), w.numpy(), L.bias[:Cout].cpu().numpy()),
+                                L.alpha[:Cout].cpu().numpy()), rel=1.2e-3)
+
+
 def test_conv_bf16_variant():
     ops = _ops()
     rng = np.random.default_rng(3)
