@@ -431,7 +431,7 @@ __global__ void pack_xfold_kernel(const float* __restrict__ w, uint16_t* __restr
     const int k = static_cast<int>(i % K);
     const int n = static_cast<int>((i / K) % cout_pad);
     const int t = static_cast<int>(i / (static_cast<long long>(K) * cout_pad));
-    const int ky = t / 3, dq = t % 3 - 1;
+    const int ky = kh - 1 - t / 3, dq = t % 3 - 1;   // taps stored ky-reversed so that dy = pby - ky increases with t/3
     float v = 0.f;
     if (n < N) {
       const int p = k / Cin, ci = k % Cin, r = n / Cout, co = n % Cout;
@@ -864,10 +864,10 @@ extern "C" int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, 
   if (F < 2 || W % F != 0 || kh * 3 > 28) return -20;
   int8_t taps[28 * 3];
   const int pby = (kh - 1) / 2;                     // SAME stride-1 transposed: dy = pb - ky
-  for (int ky = 0; ky < kh; ++ky)
+  for (int kyr = 0; kyr < kh; ++kyr)                // ky-reversed order (see pack_xfold_kernel): dy = kyr - (kh-1-pby)
     for (int j = 0; j < 3; ++j) {
-      int8_t* t = taps + 3 * (ky * 3 + j);
-      t[0] = static_cast<int8_t>(j - 1); t[1] = static_cast<int8_t>(pby - ky); t[2] = 0;
+      int8_t* t = taps + 3 * (kyr * 3 + j);
+      t[0] = static_cast<int8_t>(j - 1); t[1] = static_cast<int8_t>(pby - (kh - 1 - kyr)); t[2] = 0;
     }
   rn_conv_desc d;
   memset(&d, 0, sizeof(d));
@@ -876,6 +876,7 @@ extern "C" int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, 
   d.out16 = out16; d.out32 = out32;
   d.o_base = 0; d.o_x = static_cast<long long>(F) * Cout; d.o_y = static_cast<long long>(W) * Cout;
   d.o_b = static_cast<long long>(H) * W * Cout; d.fmt = fmt;
+  if (g_yhalo && (F * Cin) % 64 == 0) d.ny = kh;    // tap = kyr*3 + j, dy consecutive in kyr: the kh taps share one halo load
   return rn_conv_igemm(&d, stream);
 }
 
