@@ -386,7 +386,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             fence_proxy_async();
             named_bar_sync(1, 128);                      // panel complete and visible to the async proxy
             if (warp == 2 && lane == 0) {
-              tma_store_4d(mapO, stg_base, t.n0 + sc + pc, t.x0, t.y0, t.b);
+              const int ncol = t.n0 + sc + pc;
+              if (p.tma_store == 2)   // merged stride-2 transposed conv: n = (ay, ax, co) -> "TMA scatter" into row 2y+ay
+                tma_store_5d(mapO, stg_base, ncol % p.o_nsplit, t.x0, ncol / p.o_nsplit, t.y0, t.b);
+              else
+                tma_store_4d(mapO, stg_base, ncol, t.x0, t.y0, t.b);
               tma_store_commit();
               tma_store_wait_read();                     // staging buffer may be overwritten after this
             }
@@ -563,6 +567,14 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
                          d->o_y == static_cast<long long>(d->W) * d->o_x && d->o_b == static_cast<long long>(d->H) * d->o_y;
   p.tma_store = (g_tma_store && d->out16 != nullptr && d->out32 == nullptr && d->Cout == d->cout_pad && dense_out &&
                  (reinterpret_cast<uintptr_t>(d->out16) & 15) == 0) ? 1 : 0;
+  // merged stride-2 transposed conv (rn_conv2d_transpose_s2_merged): output [B, H, 2(ay), W, 2*Cout(ax,co)]
+  const bool scatter_out = d->ndim == 2 && d->o_nsplit > 0 && d->o_nsplit % PCh == 0 && d->o_base == 0 && d->o_z == 0 &&
+                           d->o_x == d->o_nsplit && d->o_nhi == static_cast<long long>(d->W) * d->o_x &&
+                           d->o_y == 2 * d->o_nhi && d->o_b == static_cast<long long>(d->H) * d->o_y &&
+                           d->cout_pad == 2 * d->o_nsplit;
+  if (g_tma_store && scatter_out && d->out16 != nullptr && d->out32 == nullptr && d->Cout == d->cout_pad &&
+      (reinterpret_cast<uintptr_t>(d->out16) & 15) == 0)
+    p.tma_store = 2;
   const int stg_bytes = p.tma_store ? (kTileM * PCh * 2 + 1024) : 0;
   const int budget = 232448 - 1024 - 256 - stg_bytes;
   int grid = 0, CL = 1, CG = 1, sub = 0;
@@ -657,7 +669,15 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   }
   if (r != CUDA_SUCCESS) return 2000 + static_cast<int>(r);
 
-  if (p.tma_store) {
+  if (p.tma_store == 2) {
+    const cuuint64_t C2 = static_cast<cuuint64_t>(d->o_nsplit);          // 2*Cout elements per (x, ay)
+    const cuuint64_t dims[5] = {C2, (cuuint64_t)d->W, 2, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    const cuuint64_t strides[4] = {C2 * 2, (cuuint64_t)d->o_nhi * 2, (cuuint64_t)d->o_y * 2, (cuuint64_t)d->o_b * 2};
+    const cuuint32_t box[5] = {(cuuint32_t)PCh, (cuuint32_t)p.BW, 1, (cuuint32_t)p.BH, 1};
+    r = enc(&p.tmO, dt, 5, d->out16, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(PCh * 2),
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 3000 + static_cast<int>(r);
+  } else if (p.tma_store) {
     const cuuint64_t Ct = static_cast<cuuint64_t>(d->cout_pad);
     const cuuint64_t dims[4] = {Ct, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     const cuuint64_t strides[3] = {Ct * 2, Ct * 2 * d->W, Ct * 2 * d->W * d->H};
