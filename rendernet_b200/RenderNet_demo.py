@@ -2,9 +2,9 @@
 `render` (:41-66), `load_graph` (:23-30) and the feed/fetch tensor names of the frozen graph
 (`real_model_in:0`, `view_name:0`, `patch_size:0`, `is_training:0` -> `encoder/output:0`).
 
-There is no TensorFlow here: `load_graph` reads weights (an .npz file, a directory of `*.txt.npz` in the
-tools/model_util.py:26-39 convention, or nothing -> the reference's initialisers with a fixed seed) and
-`Session.run` executes the CUDA engine.
+There is no TensorFlow here: `load_graph` reads weights (frozen `.pb`, checkpoint prefix, a directory of `*.txt.npz`
+in the tools/model_util.py:26-39 convention, an .npz file, or nothing -> the reference's initialisers with a fixed
+seed; `tf_import.py`) and `Session.run` executes the CUDA engine.
 """
 from __future__ import annotations
 
@@ -28,18 +28,21 @@ class Graph:
         self.is_greyscale = is_greyscale
 
 
-def load_graph(frozen_graph_filename=None, is_greyscale=False):
-    """:23-30.  Accepts .npz / npz-dir / None (TF-1 GraphDef .pb parsing is out of scope: SURVEY §8f-3)."""
+def load_graph(frozen_graph_filename=None, is_greyscale=None):
+    """:23-30.  Accepts what the reference's tooling produces — a frozen GraphDef `.pb`
+    (demo/RenderNet_converter.py), a checkpoint prefix, an npz directory (tools/model_util.py:26-39) — or a plain
+    `.npz`; None -> the reference's initialisers with a fixed seed.  `is_greyscale` defaults to what the stored
+    e_conv11 filter says (RenderNet_Shader.py:125-131)."""
     weights = None
-    if frozen_graph_filename and os.path.isdir(frozen_graph_filename):
-        from .model_util import load_weights
-        weights = load_weights(frozen_graph_filename)
-    elif frozen_graph_filename and frozen_graph_filename.endswith(".npz") and os.path.exists(frozen_graph_filename):
-        with np.load(frozen_graph_filename) as z:
-            weights = {k: z[k] for k in z.files}
-    elif frozen_graph_filename and frozen_graph_filename.endswith(".pb"):
-        raise NotImplementedError("TF-1 frozen GraphDef import is not implemented; export the variables as .npz")
-    return Graph(weights, is_greyscale)
+    if frozen_graph_filename:
+        from .tf_import import load_variables
+        weights = load_variables(frozen_graph_filename)
+        last = [v for k, v in weights.items() if k.replace("/", "_").endswith("e_conv11_e_conv11_weights")]
+        if not last:
+            raise ValueError(f"{frozen_graph_filename}: no RenderNet variables found (looked for e_conv11/weights)")
+        if is_greyscale is None:
+            is_greyscale = int(last[0].shape[2]) == 1      # transposed filter [kh,kw,Cout,Cin]
+    return Graph(weights, bool(is_greyscale))
 
 
 class Session:
@@ -112,11 +115,13 @@ def main(argv=None):
     parser.add_argument('--rotate', type=bool, default=False,
                         help='Flag rotate and render an object by 360 degree in azimuth. '
                              'Overwrites early settings in azimuth.')
-    parser.add_argument('--model', type=str, default="./model/3d2d_renderer.npz",
-                        help='Weights (.npz or directory of *.txt.npz); seeded random weights if missing.')
+    parser.add_argument('--model', type=str, default="./model/3d2d_renderer.pb",
+                        help='Weights: frozen .pb (the reference hard-codes this path, RenderNet_demo.py:111), '
+                             'checkpoint prefix, directory of *.txt.npz, or .npz; seeded random weights if missing.')
     args = parser.parse_args(argv)
 
-    graph = load_graph(args.model if os.path.exists(args.model) else None)
+    have_model = os.path.exists(args.model) or os.path.exists(args.model + ".index")
+    graph = load_graph(args.model if have_model else None)
     with Session(graph=graph) as sess:
         os.makedirs(args.render_dir, exist_ok=True)
         light_dir = Phong_shading.generate_light_pos(args.light_elevation, args.light_azimuth)
