@@ -35,6 +35,8 @@ long long rn_launch_count(void);
 int rn_set_default_cluster(int cluster);
 int rn_set_default_cta_group(int cta_group);
 int rn_set_yhalo(int on);         /* y-halo sharing in rn_conv2d_same (3x3) / rn_conv3d_banded_same; default on */
+int rn_set_res_prefetch(int on);  /* epilogue fetches 16-bit residual rows one panel ahead; default on */
+int rn_set_default_msub(int msub); /* M sub-tiles per CTA tile when a descriptor says 0: 0 heuristic, 1, 2 */
 int rn_set_tma_store(int on);     /* TMA-store epilogue for dense 16-bit outputs; default on */
 int rn_set_default_kps(int kps); /* k-iterations per smem pipeline stage, 0 = heuristic (tuning aid) */
 
@@ -97,8 +99,10 @@ typedef struct rn_conv_desc {
   int cluster;              /* thread-block-cluster size for the weight-tile TMA multicast: 0 auto, 1, 2 or 4 */
   int cta_group;            /* 0 auto, 1 = single-CTA MMA, 2 = paired tcgen05.mma.cta_group::2 (M = 256) */
   /* y-halo sharing (2-D only): taps ordered tap = ky*nx + kx with dy(ky) = dy(0) + ky; the ny taps of a filter column
-   * then share one activation load of BH+ny-1 image rows.  0/1 = off.  tile_w: M-tile width override (0 = 16). */
-  int ny, tile_w;
+   * then share one activation load of BH+ny-1 image rows.  0/1 = off.  tile_w: M-tile width override (0 = 16).
+   * msub: M sub-tiles per CTA tile -- 2 = two 128-row accumulators share every weight stage (Cout tile <= 128; halves
+   * the weight traffic per MAC), 1 = off, 0 = auto (on for banded filters). */
+  int ny, tile_w, msub;
   /* column split of the output address: n -> (n / o_nsplit) * o_nhi + (n % o_nsplit); 0 = off (multiple of 32) */
   int o_nsplit;
   long long o_nhi;
@@ -165,6 +169,16 @@ int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, const float
 int rn_conv3d_direct(const void* x, int x_is_f32, const float* w, const float* bias, const float* alpha,
                      void* out16, int B, int H, int W, int D, int Cin, int Cout, int k, int sy, int sx, int sz,
                      int fmt, void* stream);
+
+/* ---- resampler (+) e_conv1, fused -----------------------------------------------------
+ * tf_rotation_resampling (tools/resampling_voxel_grid.py:381-614) + tf_transform_voxel_to_match_image
+ * (tools/model_util.py:41-49) + conv3d 5^3 stride 2, 1 -> 8 + bias + PReLU (RenderNet_Shader.py:36-39) without
+ * materialising the new_size^3 grid; tiles whose inputs are all exactly 0 skip the convolution.  Bit-identical to
+ * rn_resample_f32(transform=1) followed by rn_conv3d_direct.  vox fp32 [B,size^3] (C = 1), minv fp32 [B,3,4],
+ * w fp32 [5,5,5,1,8], bias/alpha fp32 [8] (alpha NULL = no activation), out16 [B,(new_size/2)^3,8];
+ * new_size % 16 == 0. */
+int rn_resample_conv1_fused(const float* vox, const float* minv, const float* w, const float* bias,
+                            const float* alpha, void* out16, int B, int size, int new_size, int fmt, void* stream);
 
 /* ---- texture decoder (BASELINE config 4; RenderNet_Texture_Face_Normal.py:34-46) ----------------------------
  * fully_connected (tools/layer_util.py:311-343): y[B,N] = prelu(x[B,K] . w[K,N] + bias[N]; alpha[N]); fp32 in,

@@ -23,7 +23,7 @@ class rn_conv_desc(C.Structure):
         ("o_z", C.c_longlong), ("fmt", C.c_int), ("force_bn", C.c_int), ("force_kps", C.c_int),
         ("max_ctas", C.c_int),
         ("x_channels", C.c_int), ("a_c_base", C.c_int), ("a_c_ntile", C.c_int), ("w_banded", C.c_int),
-        ("cluster", C.c_int), ("cta_group", C.c_int), ("ny", C.c_int), ("tile_w", C.c_int),
+        ("cluster", C.c_int), ("cta_group", C.c_int), ("ny", C.c_int), ("tile_w", C.c_int), ("msub", C.c_int),
         ("o_nsplit", C.c_int), ("o_nhi", C.c_longlong),
     ]
 
@@ -40,6 +40,8 @@ SIGNATURES = {
     "rn_set_default_kps": (_i, [_i]),
     "rn_set_yhalo": (_i, [_i]),
     "rn_set_tma_store": (_i, [_i]),
+    "rn_set_default_msub": (_i, [_i]),
+    "rn_set_res_prefetch": (_i, [_i]),
     "rn_resample_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rn_pack_conv_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "rn_cast_f32_to_16": (_i, [_vp, _vp, _ll, _ll, _i, _vp]),
@@ -60,6 +62,7 @@ SIGNATURES = {
     "rn_pack_conv2d_transpose_xfold": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rn_conv2d_transpose_s1_xfold": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rn_conv3d_direct": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rn_resample_conv1_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rn_fully_connected": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rn_conv3d_small": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rn_concat_channels_f32": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),

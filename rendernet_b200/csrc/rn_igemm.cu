@@ -43,7 +43,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile,
   const int tx = m_tile % p.tiles_x;
   const int ty = m_tile / p.tiles_x;
   t.x0 = tx * p.BW;
-  t.y0 = ty * p.BH;
+  t.y0 = ty * p.BH * p.ms;
   t.z0 = tz * p.BD;
   t.n0 = n_tile * BN;
   return t;
@@ -54,7 +54,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile,
 template <int CW>
 __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint32_t* __restrict__ r, int n0,
                                                long long off, bool row_valid, uint32_t stg = 0, int m = 0,
-                                               int chunk0 = 0, int prow = 128) {
+                                               int chunk0 = 0, int prow = 128, const uint4* rpre = nullptr) {
   if (!row_valid && stg == 0) return;
   float v[CW];
 #pragma unroll
@@ -92,7 +92,7 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
         const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res) + off + n0);
 #pragma unroll
         for (int i = 0; i < CW / 8; ++i) {
-          const uint4 q = __ldg(rp + i);
+          const uint4 q = rpre != nullptr ? rpre[i] : __ldg(rp + i);   // rpre: fetched a panel ahead by the caller
           const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -167,7 +167,8 @@ template <int BN, int CL, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   static_assert(CG == 1 || (CG == 2 && CL == 2), "cta_group::2 runs on a 2-CTA cluster");
   constexpr int CW = (BN >= 32) ? 32 : 16;                     // epilogue column chunk
-  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // double-buffered accumulator
+  const int ms = p.ms;                                         // M sub-tiles (accumulators) per tile
+  const uint32_t kTmemCols = (2 * ms * BN < 32) ? 32u : static_cast<uint32_t>(2 * ms * BN);  // double-buffered accumulators
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
   const int nx = p.ntaps / ny;
   const int total_k = nx * p.kblocks;                          // groups per tile (each = ny k-iterations of MMAs)
   const int kb_elems = p.row_bytes >> 1;
-  const uint32_t a_tx = static_cast<uint32_t>(p.BD * p.BW * (p.BH + ny - 1)) * p.row_bytes;
+  const uint32_t a_tx = static_cast<uint32_t>(p.BD * p.BW * (p.BH * ms + ny - 1)) * p.row_bytes;
   const uint32_t b_tx = (CG == 2 ? BN / 2 : BN) * p.row_bytes;   // B bytes that land in THIS CTA's smem
 
   if (warp == 0) {
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4, sub16 = static_cast<uint32_t>(sub_bytes) >> 4;
       const uint32_t a16 = static_cast<uint32_t>(p.a_sub_bytes) >> 4, b16 = static_cast<uint32_t>(p.b_sub_bytes) >> 4;
       const uint32_t ady16 = static_cast<uint32_t>(p.BD * p.BW * p.row_bytes) >> 4;   // one image row of the A halo
+      const uint32_t ams16 = static_cast<uint32_t>(kTileM * p.row_bytes) >> 4;          // one M sub-tile (BH image rows)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       for (int ct = cl_id; ct < num_ct; ct += ncl) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * ms * BN);
         uint32_t accum = 0;
         for (int left = total_k; left > 0;) {
           const int n_here = min(kps, left);
@@ -308,6 +310,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
               for (int k = 0; k < 4; ++k) {
                 if (k < mma_per_kit) {
                   umma_f16<CG>(d_tmem, dak + 2 * k, dbk + 2 * k, idesc, accum);
+                  if (ms == 2) umma_f16<CG>(d_tmem + BN, dak + ams16 + 2 * k, dbk + 2 * k, idesc, accum);  // same weights
                   accum = 1;
                 }
               }
@@ -339,60 +342,90 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     uint32_t acc_phase = 0;
     for (int ct = cl_id; ct < num_ct; ct += ncl) {
       const TileCoord t = decode_tile(p, tile_of(ct), BN);
-      const int x = t.x0 + xl, y = t.y0 + yl, z = t.z0 + zl;
-      const bool row_valid = (x < p.W) && (y < p.H) && (z < p.D);
-      const long long off = p.o_base + t.b * p.o_b + y * p.o_y + x * p.o_x + z * p.o_z;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      // TMEM reads queue behind the MMAs already issued for the next tile (~2000 cycles each, measured), so fetch as
-      // many columns per tcgen05.ld as registers allow (SC = 128) instead of one 32-column chunk at a time: with
-      // short-K tiles (projection unit, banded 3^3 convs) the epilogue was the bottleneck.
+      const int x = t.x0 + xl, z = t.z0 + zl;
+      // TMEM is read SC columns at a time (every tcgen05.ld queues behind the MMAs already issued for the next tile and
+      // costs ~2000 cycles whatever its width -- fewer, wider loads: x128), then drained panel by panel: one panel =
+      // PC columns = one swizzled staging buffer = one TMA store.  A 16-bit residual is fetched one panel AHEAD into
+      // registers (the first panel's before the accumulator-full wait), all 128 bytes of the row at once, so its L2
+      // latency overlaps the store / barrier / next TMEM load instead of stalling every 32-column chunk.
       constexpr int SC = (BN >= 128) ? 128 : BN;
       constexpr int PC = (BN >= 64) ? 64 : BN;        // staging panel columns (one TMA store box)
+      constexpr int NPT = BN / PC;                    // panels per accumulator
+      constexpr int RV = PC / 8;                      // 16-byte residual vectors per row and panel
+      const int nq = ms * NPT;
       const bool tma_out = p.tma_store != 0;
       const uint64_t mapO = reinterpret_cast<uint64_t>(&p.tmO);
-#pragma unroll 1
-      for (int sc = 0; sc < BN; sc += SC) {
-        uint32_t r[SC];
-        if constexpr (SC == 128) tmem_ld_32x32b_x128(taddr + sc, r);
-        else if constexpr (SC == 64) tmem_ld_32x32b_x64(taddr + sc, r);
-        else if constexpr (SC == 32) tmem_ld_32x32b_x32(taddr + sc, r);
-        else tmem_ld_32x32b_x16(taddr + sc, r);
-        tmem_ld_wait();
-        if (sc + SC >= BN) {  // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // leader owns the barrier
-            else mbar_arrive(&tempty_bar[acc]);
-          }
-        }
-        if (!tma_out) {
+      const bool res_pre = p.res_prefetch && (p.res != nullptr) && !p.res_is_f32 && p.vec_ok && (p.o_nsplit == 0) &&
+                           (t.n0 + BN <= p.n_valid);
+      uint4 res[RV];
 #pragma unroll
-          for (int c = 0; c < SC; c += CW) {
-            const int nc = t.n0 + sc + c;
-            const long long offc = p.o_nsplit > 0 ? off + (nc / p.o_nsplit) * p.o_nhi + (nc % p.o_nsplit) - nc : off;
-            epilogue_chunk<CW>(p, r + c, nc, offc, row_valid);
+      for (int i = 0; i < RV; ++i) res[i] = make_uint4(0u, 0u, 0u, 0u);
+      auto prefetch_res = [&](int q) {                // panel q -> M sub-tile q / NPT, columns (q % NPT) * PC
+        const int y = t.y0 + (q / NPT) * p.BH + yl;
+        if (x < p.W && y < p.H && z < p.D) {
+          const long long o = p.o_base + t.b * p.o_b + y * p.o_y + x * p.o_x + z * p.o_z + t.n0 + (q % NPT) * PC;
+          const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res) + o);
+#pragma unroll
+          for (int i = 0; i < RV; ++i) res[i] = __ldg(rp + i);
+        }
+      };
+      if (res_pre) prefetch_res(0);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      int q = 0;                                      // running panel index
+#pragma unroll 1
+      for (int s = 0; s < ms; ++s) {                  // M sub-tiles: BH image rows further down, BN TMEM columns further on
+        const int ys0 = t.y0 + s * p.BH, y = ys0 + yl;
+        const bool row_valid = (x < p.W) && (y < p.H) && (z < p.D);
+        const long long off = p.o_base + t.b * p.o_b + y * p.o_y + x * p.o_x + z * p.o_z;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>((acc * ms + s) * BN);
+#pragma unroll 1
+        for (int sc = 0; sc < BN; sc += SC) {
+          uint32_t r[SC];
+          if constexpr (SC == 128) tmem_ld_32x32b_x128(taddr + sc, r);
+          else if constexpr (SC == 64) tmem_ld_32x32b_x64(taddr + sc, r);
+          else if constexpr (SC == 32) tmem_ld_32x32b_x32(taddr + sc, r);
+          else tmem_ld_32x32b_x16(taddr + sc, r);
+          tmem_ld_wait();
+          if (sc + SC >= BN && s == ms - 1) {  // all TMEM reads of this tile's accumulators are done -> hand them back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // leader owns the barrier
+              else mbar_arrive(&tempty_bar[acc]);
+            }
           }
-        } else {
-          // panel by panel: registers -> swizzled smem -> one TMA store (full 128-byte lines, edges clipped by TMA)
 #pragma unroll
           for (int pc = 0; pc < SC; pc += PC) {
-            named_bar_sync(1, 128);                      // the previous panel's store has finished reading the staging buffer
+            if (!tma_out) {
 #pragma unroll
-            for (int c = 0; c < PC; c += CW)
-              epilogue_chunk<CW>(p, r + pc + c, t.n0 + sc + pc + c, off, row_valid, stg_base, m, c / 8, PC * 2);
-            fence_proxy_async();
-            named_bar_sync(1, 128);                      // panel complete and visible to the async proxy
-            if (warp == 2 && lane == 0) {
-              const int ncol = t.n0 + sc + pc;
-              if (p.tma_store == 2)   // merged stride-2 transposed conv: n = (ay, ax, co) -> "TMA scatter" into row 2y+ay
-                tma_store_5d(mapO, stg_base, ncol % p.o_nsplit, t.x0, ncol / p.o_nsplit, t.y0, t.b);
-              else
-                tma_store_4d(mapO, stg_base, ncol, t.x0, t.y0, t.b);
-              tma_store_commit();
-              tma_store_wait_read();                     // staging buffer may be overwritten after this
+              for (int c = 0; c < PC; c += CW) {
+                const int nc = t.n0 + sc + pc + c;
+                const long long offc = p.o_nsplit > 0 ? off + (nc / p.o_nsplit) * p.o_nhi + (nc % p.o_nsplit) - nc : off;
+                epilogue_chunk<CW>(p, r + pc + c, nc, offc, row_valid, 0, 0, 0, 128, res_pre ? res + c / 8 : nullptr);
+              }
+              ++q;
+              if (res_pre && q < nq) prefetch_res(q);
+            } else {
+              // registers -> swizzled smem -> one TMA store (full 128-byte lines, edges clipped by TMA)
+              named_bar_sync(1, 128);                    // the previous panel's store has finished reading the staging buffer
+#pragma unroll
+              for (int c = 0; c < PC; c += CW)
+                epilogue_chunk<CW>(p, r + pc + c, t.n0 + sc + pc + c, off, row_valid, stg_base, m, c / 8, PC * 2,
+                                   res_pre ? res + c / 8 : nullptr);
+              ++q;
+              if (res_pre && q < nq) prefetch_res(q);    // next panel's residual: in flight across the store + barrier
+              fence_proxy_async();
+              named_bar_sync(1, 128);                    // panel complete and visible to the async proxy
+              if (warp == 2 && lane == 0) {
+                const int ncol = t.n0 + sc + pc;
+                if (p.tma_store == 2)   // merged stride-2 transposed conv: n = (ay, ax, co) -> "TMA scatter" into row 2y+ay
+                  tma_store_5d(mapO, stg_base, ncol % p.o_nsplit, t.x0, ncol / p.o_nsplit, ys0, t.b);
+                else
+                  tma_store_4d(mapO, stg_base, ncol, t.x0, ys0, t.b);
+                tma_store_commit();
+                tma_store_wait_read();                   // staging buffer may be overwritten after this
+              }
             }
           }
         }
@@ -431,6 +464,8 @@ static CUtensorMapSwizzle swizzle_of(int row_bytes) {
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+int g_res_prefetch = 1;                      // fetch 16-bit residual rows one panel ahead in the epilogue (A/B switch)
+int g_default_msub = 0;                      // M sub-tiles per CTA tile when the descriptor says 0: 0 = heuristic, 1, 2
 int g_tma_store = 1;                         // TMA-store epilogue where the output is a dense 16-bit NHWC tensor
 int g_default_kps = 0;                       // k-iterations per pipeline stage override (0 = heuristic)
 int g_default_cta_group = 2;                 // 2: paired tcgen05.mma.cta_group::2 tiles where the shape allows
@@ -483,6 +518,18 @@ static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaSt
 extern "C" int rn_set_default_cluster(int c) {
   const int prev = rn::g_default_cluster;
   if (c == 1 || c == 2 || c == 4) rn::g_default_cluster = c;
+  return prev;
+}
+
+extern "C" int rn_set_res_prefetch(int on) {
+  const int prev = rn::g_res_prefetch;
+  rn::g_res_prefetch = on ? 1 : 0;
+  return prev;
+}
+
+extern "C" int rn_set_default_msub(int m) {
+  const int prev = rn::g_default_msub;
+  if (m >= 0 && m <= 2) rn::g_default_msub = m;
   return prev;
 }
 
@@ -578,7 +625,14 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   const int stg_bytes = p.tma_store ? (kTileM * PCh * 2 + 1024) : 0;
   const int budget = 232448 - 1024 - 256 - stg_bytes;
   int grid = 0, CL = 1, CG = 1, sub = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  // M sub-tiles: two 128-row accumulators per CTA share every weight stage (BN <= 128 so that 2 x 2 x BN TMEM columns
+  // fit).  Halves the weight bytes per MAC; measured on every BN <= 128 layer of the network (banded 3^3 convs
+  // 0.28 -> 0.22 ms, e_conv10 0.43 -> 0.26, e_conv7_1 0.25 -> 0.17: profiles/r01_probe_msub.log), never slower.
+  int want_ms = d->msub > 0 ? d->msub : (g_default_msub > 0 ? g_default_msub : 2);
+  if (want_ms > 2) return -16;
+  if (BN > 128 || d->ndim != 2) want_ms = 1;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    p.ms = want_ms;
     int rem = kTileM;
     p.BD = d->ndim == 3 ? pow2_le(D, rem) : 1;
     rem /= p.BD;
@@ -592,7 +646,8 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
     rem /= p.BW;
     p.BH = rem;
     p.tiles_x = (d->W + p.BW - 1) / p.BW;
-    p.tiles_y = (d->H + p.BH - 1) / p.BH;
+    if (p.ms == 2 && d->H < 2 * p.BH) p.ms = 1;       // nothing to pair
+    p.tiles_y = (d->H + p.BH * p.ms - 1) / (p.BH * p.ms);
     p.tiles_z = (D + p.BD - 1) / p.BD;
     p.num_tiles = d->B * p.tiles_x * p.tiles_y * p.tiles_z * p.n_tiles;
     // persistent grid, cluster size CL for the B multicast, CG = 2 for the paired (cta_group::2) MMA
@@ -609,7 +664,7 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
       else if (want >= 2 && m_tiles % 2 == 0 && grid >= 2) CL = 2;
     }
     grid -= grid % CL;
-    p.a_sub_bytes = ((p.BD * p.BW * (p.BH + p.ny - 1) * p.row_bytes + 1023) / 1024) * 1024;
+    p.a_sub_bytes = ((p.BD * p.BW * (p.BH * p.ms + p.ny - 1) * p.row_bytes + 1023) / 1024) * 1024;
     p.b_sub_bytes = (((BN / CG) * p.row_bytes + 1023) / 1024) * 1024;
     sub = p.a_sub_bytes + p.ny * p.b_sub_bytes;       // one group: A (halo) + ny weight tiles
     const int total_k = (p.ntaps / p.ny) * p.kblocks;
@@ -626,8 +681,9 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
       --p.kps;
       p.stages = budget / (p.kps * sub);
     }
-    if (p.stages >= 3 || p.ny == 1) break;
-    p.ny = 1;                               // retry without halo sharing
+    if (p.stages >= 3 || (p.ny == 1 && p.ms == 1)) break;
+    if (want_ms > 1) want_ms = 1;           // retry with one accumulator per tile,
+    else p.ny = 1;                          // then without halo sharing
   }
   if (p.stages < 2) return -10;
   const size_t smem = static_cast<size_t>(p.stages) * p.kps * sub + 1024 + 256 + stg_bytes;
@@ -643,7 +699,7 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   if (p.rank == 4) {
     const cuuint64_t dims[4] = {Cx, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     const cuuint64_t strides[3] = {Cx * 2, Cx * 2 * d->W, Cx * 2 * d->W * d->H};
-    const cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)p.BW, (cuuint32_t)(p.BH + p.ny - 1), 1};
+    const cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)p.BW, (cuuint32_t)(p.BH * p.ms + p.ny - 1), 1};
     r = enc(&p.tmA, dt, 4, const_cast<void*>(d->x), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
@@ -690,6 +746,7 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   p.bias = d->bias; p.alpha = d->alpha; p.act = d->act; p.n_valid = d->Cout;
   p.o_base = d->o_base; p.o_b = d->o_b; p.o_y = d->o_y; p.o_x = d->o_x; p.o_z = d->o_z;
   p.o_nsplit = d->o_nsplit; p.o_nhi = d->o_nhi;
+  p.res_prefetch = g_res_prefetch;
   if (d->o_nsplit > 0 && (d->o_nsplit % 32 != 0 || d->o_nhi % 8 != 0)) return -15;
   const bool strides8 = (d->o_base % 8 == 0) && (d->o_b % 8 == 0) && (d->o_y % 8 == 0) && (d->o_x % 8 == 0) &&
                         (d->o_z % 8 == 0);

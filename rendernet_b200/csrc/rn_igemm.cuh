@@ -16,7 +16,7 @@ struct alignas(64) IgemmParams {
   CUtensorMap tmO;  // 16-bit output {Cout,W,H,B}; box {panel cols (<=64), BW, BH, 1}: TMA-store epilogue (tma_store != 0)
   int rank;
   int W, H, D, B;                 // extents of the output (== input) pixel space; D = 1 for rank 4
-  int BW, BH, BD;                 // M tile box, BW*BH*BD == 128
+  int BW, BH, BD;                 // M (sub-)tile box, BW*BH*BD == 128
   int tiles_x, tiles_y, tiles_z;  // per image
   int n_tiles;                    // CoutPad / BN
   int num_tiles;                  // B*tiles_y*tiles_x*tiles_z*n_tiles
@@ -28,6 +28,8 @@ struct alignas(64) IgemmParams {
   int ab_fmt;                     // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
   int a_c_base, a_c_ntile;        // A channel coordinate = a_c_base + n_tile*a_c_ntile + kb*KB (depth-folded conv3d)
   int b_banded;                   // 1: B box = (0, 0, tap*kblocks+kb) -- one banded filter shared by all N tiles
+  int ms;                         // M sub-tiles per CTA tile (1 or 2): the CTA's tile is BW x (ms*BH) pixels = ms x 128 GEMM rows;
+                                  // every weight (B) stage is used for ms accumulators, halving B traffic per MAC (BN <= 128)
   int ny;                         // y-halo sharing: taps are ordered tap = ky*nx + kx with dy consecutive; the ny taps of a
                                   // column share ONE A load of BH+ny-1 image rows (operand ky starts ky*BW rows into it)
   int8_t tap[kMaxTaps][4];        // (dx, dy, dz, _) input offset of each filter tap
@@ -36,6 +38,7 @@ struct alignas(64) IgemmParams {
   float* out32;                   // fp32 output or nullptr
   const void* res;                // residual (same indexing as the output) or nullptr
   int res_is_f32;
+  int res_prefetch;               // 1: 16-bit residual rows are fetched one panel ahead into registers
   const float* bias;              // [CoutPad]
   const float* alpha;             // [CoutPad] (PReLU) or nullptr
   int act;

@@ -294,6 +294,165 @@ __global__ void __launch_bounds__(256) conv3d_direct_kernel(const void* __restri
 }
 
 
+// ------------------------------------------------------------------------------------------ resampler (+) e_conv1
+// rotate/resample (tools/resampling_voxel_grid.py:381-614) + axis transform (tools/model_util.py:41-49)
+// + e_conv1 (5^3, stride 2, 1 -> 8, SAME = pad 1 before / 2 after; RenderNet_Shader.py:36-39) + bias + PReLU in one
+// kernel: the 128^3 fp32 grid (8.4 MB per render) is never written.  One CTA = 8^3 outputs; it samples the 19^3 input
+// points it needs into shared memory (same arithmetic, operation for operation, as resample_kernel), and if every one
+// of them is exactly 0 -- outside the rotated cube or empty space, ~85-90 % of all tiles -- the outputs are
+// PReLU(bias) and the 5^3 convolution is skipped.  Accumulation order per output = conv3d_direct_kernel's
+// (ky, kx, kz), so results are bit-identical to the unfused pair.
+constexpr int RC_T = 8;                 // outputs per tile edge
+constexpr int RC_IN = 2 * RC_T + 3;     // 19 input points per edge
+constexpr int RC_ZP = 20;               // padded z row: even z at [0,10), odd z at [10,19) -> conflict-free stride-2 reads
+
+__global__ void __launch_bounds__(256) resample_conv1_kernel(const float* __restrict__ vox,
+                                                             const float* __restrict__ minv,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             const float* __restrict__ alpha, uint16_t* __restrict__ out,
+                                                             int B, int size, int nsz, int fmt) {
+  __shared__ float tile[RC_IN * RC_IN * RC_ZP];
+  __shared__ __align__(16) float ws[125 * 8];
+  const int tid = threadIdx.x;
+  const int No = nsz >> 1;                // output edge
+  const int tpe = No / RC_T;              // tiles per edge
+  int bid = blockIdx.x;
+  const int tz = bid % tpe; bid /= tpe;
+  const int tx = bid % tpe; bid /= tpe;
+  const int ty = bid % tpe;
+  const int b = bid / tpe;
+  for (int i = tid; i < 125 * 8; i += 256) ws[i] = __ldg(w + i);
+
+  const float* M = minv + b * 12;
+  const float m00 = __ldg(M + 0), m01 = __ldg(M + 1), m02 = __ldg(M + 2), m03 = __ldg(M + 3);
+  const float m10 = __ldg(M + 4), m11 = __ldg(M + 5), m12 = __ldg(M + 6), m13 = __ldg(M + 7);
+  const float m20 = __ldg(M + 8), m21 = __ldg(M + 9), m22 = __ldg(M + 10), m23 = __ldg(M + 11);
+  const float lim = static_cast<float>(size - 1);
+  const float* vb = vox + static_cast<size_t>(b) * size * size * size;
+  const size_t sy = static_cast<size_t>(size), sz = static_cast<size_t>(size) * size;
+  const int p0 = 2 * ty * RC_T - 1, q0 = 2 * tx * RC_T - 1, r0 = 2 * tz * RC_T - 1;
+
+  // Tile-level rejection: the source coordinate is affine in (p,q,r), so over the tile's input box each of x,y,z is
+  // bounded by its values at the box's 8 corners.  If one axis lies entirely outside [0, size-1) (with a margin far
+  // above the fmaf rounding of the per-point evaluation) every sample is exactly 0 by the clamp rule and neither the
+  // gather nor the convolution runs.
+  int nonzero = 0;
+  bool maybe_inside = true;
+  {
+    const float pl = static_cast<float>(max(p0, 0)), ph = static_cast<float>(min(p0 + RC_IN - 1, nsz - 1));
+    const float ql = static_cast<float>(max(q0, 0)), qh = static_cast<float>(min(q0 + RC_IN - 1, nsz - 1));
+    const float rl = static_cast<float>(max(r0, 0)), rh = static_cast<float>(min(r0 + RC_IN - 1, nsz - 1));
+    const float gyl = static_cast<float>(nsz - 1) - ph, gyh = static_cast<float>(nsz - 1) - pl;   // gy = nsz-1-p
+    const float mrow[3][4] = {{m00, m01, m02, m03}, {m10, m11, m12, m13}, {m20, m21, m22, m23}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      // interval arithmetic: min/max of m0*gx + m1*gy + m2*gz + m3 over gx in [rl,rh], gy in [gyl,gyh], gz in [ql,qh]
+      const float lo = fminf(mrow[a][0] * rl, mrow[a][0] * rh) + fminf(mrow[a][1] * gyl, mrow[a][1] * gyh) +
+                       fminf(mrow[a][2] * ql, mrow[a][2] * qh) + mrow[a][3];
+      const float hi = fmaxf(mrow[a][0] * rl, mrow[a][0] * rh) + fmaxf(mrow[a][1] * gyl, mrow[a][1] * gyh) +
+                       fmaxf(mrow[a][2] * ql, mrow[a][2] * qh) + mrow[a][3];
+      if (hi < -0.01f || lo > lim + 0.01f) maybe_inside = false;
+    }
+  }
+  if (maybe_inside) {
+    // i = (iy*19 + ix)*19 + iz walked with a stride of 256 = 13*19 + 9 without divisions
+    int iz = tid % RC_IN, row = tid / RC_IN;
+    for (int i = tid; i < RC_IN * RC_IN * RC_IN; i += 256) {
+      const int iy = row / RC_IN, ix = row - iy * RC_IN;
+      const int p = p0 + iy, q = q0 + ix, r = r0 + iz;
+      float v = 0.f;
+      if (p >= 0 && p < nsz && q >= 0 && q < nsz && r >= 0 && r < nsz) {
+        // N[b,p,q,r] = T[b,q,nsz-1-p,r]; grid point (gx,gy,gz) = (r, nsz-1-p, q)
+        const float gx = static_cast<float>(r), gy = static_cast<float>(nsz - 1 - p), gz = static_cast<float>(q);
+        const float bx = fmaf(m01, gy, fmaf(m02, gz, m03));
+        const float by = fmaf(m11, gy, fmaf(m12, gz, m13));
+        const float bz = fmaf(m21, gy, fmaf(m22, gz, m23));
+        const float x = fmaf(m00, gx, bx), y = fmaf(m10, gx, by), z = fmaf(m20, gx, bz);
+        if (x >= 0.f && x < lim && y >= 0.f && y < lim && z >= 0.f && z < lim) {
+          const float x0f = floorf(x), y0f = floorf(y), z0f = floorf(z);
+          const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f), z0 = static_cast<int>(z0f);
+          const float x1f = x0f + 1.f, y1f = y0f + 1.f, z1f = z0f + 1.f;
+          const float ax = __fsub_rn(x1f, x), bxw = __fsub_rn(x, x0f);
+          const float ay = __fsub_rn(y1f, y), byw = __fsub_rn(y, y0f);
+          const float az = __fsub_rn(z1f, z), bzw = __fsub_rn(z, z0f);
+          const float wa = __fmul_rn(__fmul_rn(ax, ay), az), wb = __fmul_rn(__fmul_rn(ax, byw), az);
+          const float wc = __fmul_rn(__fmul_rn(bxw, ay), az), wd = __fmul_rn(__fmul_rn(bxw, byw), az);
+          const float we = __fmul_rn(__fmul_rn(ax, ay), bzw), wf = __fmul_rn(__fmul_rn(ax, byw), bzw);
+          const float wg = __fmul_rn(__fmul_rn(bxw, ay), bzw), wh = __fmul_rn(__fmul_rn(bxw, byw), bzw);
+          const float* c0 = vb + (static_cast<size_t>(z0) * size + y0) * size + x0;
+          float s = __fmul_rn(wa, __ldg(c0));                       // add_n order a..h (:485)
+          s = __fadd_rn(s, __fmul_rn(wb, __ldg(c0 + sy)));
+          s = __fadd_rn(s, __fmul_rn(wc, __ldg(c0 + 1)));
+          s = __fadd_rn(s, __fmul_rn(wd, __ldg(c0 + sy + 1)));
+          s = __fadd_rn(s, __fmul_rn(we, __ldg(c0 + sz)));
+          s = __fadd_rn(s, __fmul_rn(wf, __ldg(c0 + sz + sy)));
+          s = __fadd_rn(s, __fmul_rn(wg, __ldg(c0 + sz + 1)));
+          s = __fadd_rn(s, __fmul_rn(wh, __ldg(c0 + sz + sy + 1)));
+          v = s;
+        }
+      }
+      nonzero |= (v != 0.f);
+      tile[row * RC_ZP + (iz & 1) * 10 + (iz >> 1)] = v;
+      iz += 256 % RC_IN;
+      row += 256 / RC_IN;
+      if (iz >= RC_IN) { iz -= RC_IN; ++row; }
+    }
+  }
+  const int any = __syncthreads_or(nonzero);
+
+  const int oz = tid & 7, ox = (tid >> 3) & 7, oy = tid >> 6;   // second output: oy + 4
+  float acc0[8], acc1[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc0[c] = acc1[c] = 0.f;
+  if (any) {
+    for (int ky = 0; ky < 5; ++ky) {
+      for (int kx = 0; kx < 5; ++kx) {
+        const float* t0 = tile + ((2 * oy + ky) * RC_IN + (2 * ox + kx)) * RC_ZP + oz;
+        const float* t1 = t0 + 8 * RC_IN * RC_ZP;
+        const float4* wt = reinterpret_cast<const float4*>(ws + (ky * 5 + kx) * 5 * 8);
+#pragma unroll
+        for (int kz = 0; kz < 5; ++kz) {
+          const int zi = (kz & 1) * 10 + (kz >> 1);
+          const float a0 = t0[zi], a1 = t1[zi];
+          const float4 wlo = wt[2 * kz], whi = wt[2 * kz + 1];
+          acc0[0] = fmaf(a0, wlo.x, acc0[0]); acc0[1] = fmaf(a0, wlo.y, acc0[1]);
+          acc0[2] = fmaf(a0, wlo.z, acc0[2]); acc0[3] = fmaf(a0, wlo.w, acc0[3]);
+          acc0[4] = fmaf(a0, whi.x, acc0[4]); acc0[5] = fmaf(a0, whi.y, acc0[5]);
+          acc0[6] = fmaf(a0, whi.z, acc0[6]); acc0[7] = fmaf(a0, whi.w, acc0[7]);
+          acc1[0] = fmaf(a1, wlo.x, acc1[0]); acc1[1] = fmaf(a1, wlo.y, acc1[1]);
+          acc1[2] = fmaf(a1, wlo.z, acc1[2]); acc1[3] = fmaf(a1, wlo.w, acc1[3]);
+          acc1[4] = fmaf(a1, whi.x, acc1[4]); acc1[5] = fmaf(a1, whi.y, acc1[5]);
+          acc1[6] = fmaf(a1, whi.z, acc1[6]); acc1[7] = fmaf(a1, whi.w, acc1[7]);
+        }
+      }
+    }
+  }
+  uint32_t pk0[4], pk1[4];
+#pragma unroll
+  for (int c = 0; c < 8; c += 2) {
+    const float b0 = __ldg(bias + c), b1 = __ldg(bias + c + 1);
+    float u0 = acc0[c] + b0, u1 = acc0[c + 1] + b1, v0 = acc1[c] + b0, v1 = acc1[c + 1] + b1;
+    if (alpha != nullptr) {
+      const float al0 = __ldg(alpha + c), al1 = __ldg(alpha + c + 1);
+      u0 = fmaxf(u0, 0.f) + al0 * fminf(u0, 0.f);
+      u1 = fmaxf(u1, 0.f) + al1 * fminf(u1, 0.f);
+      v0 = fmaxf(v0, 0.f) + al0 * fminf(v0, 0.f);
+      v1 = fmaxf(v1, 0.f) + al1 * fminf(v1, 0.f);
+    }
+    if (fmt == 0) {
+      __half2 h = __floats2half2_rn(u0, u1); pk0[c / 2] = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(v0, v1); pk1[c / 2] = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __nv_bfloat162 h = __floats2bfloat162_rn(u0, u1); pk0[c / 2] = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(v0, v1); pk1[c / 2] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  const size_t o0 = (((static_cast<size_t>(b) * No + (ty * RC_T + oy)) * No + (tx * RC_T + ox)) * No + (tz * RC_T + oz)) * 8;
+  *reinterpret_cast<uint4*>(out + o0) = make_uint4(pk0[0], pk0[1], pk0[2], pk0[3]);
+  *reinterpret_cast<uint4*>(out + o0 + static_cast<size_t>(4) * No * No * 8) = make_uint4(pk1[0], pk1[1], pk1[2], pk1[3]);
+}
+
+
 // ------------------------------------------------------------------------------------------ texture decoder (config 4)
 // fully_connected (tools/layer_util.py:311-343): y[b][n] = act(sum_k x[b][k] w[k][n] + bias[n]); w is TF [in,out].
 // One thread per output column, weights streamed once (coalesced across n), x staged in shared memory.
@@ -938,6 +1097,20 @@ extern "C" int rn_conv3d_direct(const void* x, int x_is_f32, const float* w, con
   else if (Cin == 2 && Cout == 8 && k == 3 && x_is_f32) RN_LAUNCH_DIRECT(2, 8, 3, true);
   else return -2;
 #undef RN_LAUNCH_DIRECT
+  RN_COUNT_LAUNCH();
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_resample_conv1_fused(const float* vox, const float* minv, const float* w, const float* bias,
+                                       const float* alpha, void* out16, int B, int size, int new_size, int fmt,
+                                       void* stream) {
+  if (!vox || !minv || !w || !bias || !out16 || B < 1 || size < 2) return -1;
+  if (new_size < 16 || new_size % 16 != 0) return -2;   // 8^3-output tiles
+  const int tpe = new_size / 2 / RC_T;
+  const long long blocks = static_cast<long long>(B) * tpe * tpe * tpe;
+  if (blocks > 0x7fffffffLL) return -3;
+  resample_conv1_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      vox, minv, w, bias, alpha, static_cast<uint16_t*>(out16), B, size, new_size, fmt);
   RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }

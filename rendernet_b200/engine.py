@@ -15,7 +15,7 @@ import torch
 from . import ops
 from . import tfcompat as tf
 from .RenderNet_Shader import RenderNet
-from .resampling_voxel_grid import inverse_sampling_matrix, tf_rotation_around_grid_centroid
+from .resampling_voxel_grid import ResampledGrid, inverse_sampling_matrix, tf_rotation_around_grid_centroid
 
 
 class RenderEngine:
@@ -50,6 +50,9 @@ class RenderEngine:
         from ._lib import lib
         self._forward()
         torch.cuda.synchronize()
+        # the captured graph holds raw pointers into the packed weights: keep them alive even if another engine (or
+        # tf.reset_default_graph) later clears the process-wide variable store
+        self._keepalive = (dict(tf.get_store().vars), dict(tf.get_store().packed))
         n0 = lib.rn_launch_count()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -63,13 +66,14 @@ class RenderEngine:
             with torch.cuda.graph(self.graph):
                 self._forward()
             torch.cuda.synchronize()
+        self._keepalive = (dict(tf.get_store().vars), dict(tf.get_store().packed))
         out_shape = tuple(self.out.shape)
         self.out_host = torch.zeros(out_shape, dtype=torch.float32).pin_memory()
         self.out_u8_host = torch.zeros(out_shape, dtype=torch.uint8).pin_memory() if phong is not None else None
 
     # -------------------------------------------------------------------------------------------
     def _forward(self):
-        grid = ops.resample(self.vox, self.minv, self.new_size, True)
+        grid = ResampledGrid(self.vox, self.minv, self.new_size, transform=True)   # deferred: fuses into e_conv1
         img = RenderNet(grid, is_training=False, is_greyscale=self.is_greyscale)
         if self.phong is not None:
             shaded, u8 = ops.phong_composite(img, self.light_dir, self.light_col, self.phong["ambient"],
@@ -217,6 +221,7 @@ class TextureRenderEngine:
                 self._forward()
             torch.cuda.synchronize()
         self.out_host = tuple(torch.zeros(tuple(o.shape), dtype=torch.float32).pin_memory() for o in self.out)
+        self._keepalive = (dict(tf.get_store().vars), dict(tf.get_store().packed))   # see RenderEngine.__init__
 
     def _forward(self):
         from .RenderNet_Texture_Face_Normal import RenderNet as RenderNetTexture, decoder_texture

@@ -16,10 +16,12 @@ import torch
 
 from . import ops
 from . import tfcompat as tf
+from .resampling_voxel_grid import ResampledGrid
 from .tfcompat import Deferred, realize
 
 USE_MERGED_TCONV = True    # one launch (N = 4*Cout, 9 taps) instead of 4 phase launches for k=4 stride-2 transposed convs
 USE_XFOLD = True           # fold x-pixels into channels for thin stride-1 transposed convs (e_conv10/11)
+USE_FUSED_RESAMPLE_CONV1 = True   # resampler + axis transform + e_conv1 in one kernel with empty-tile skipping
 USE_BANDED_CONV3D = True   # depth-folded tensor-core path for 3^3 convs (falls back to the 5-D TMA path)
 
 _XAVIER = tf.xavier_initializer
@@ -444,14 +446,21 @@ def _deferred_direct3d(x, w, b, stride):
               w.shape[-1])
 
     def run(act, alpha, residual, want32):
-        xt = realize(xin)
-        if not xt.is_cuda:
-            xt = xt.to(_store().device)
         cout = w.shape[-1]
         wd = _store().packed.get(("w32", w._rn_name))
         if wd is None:
             wd = w.to(_store().device).contiguous()
             _store().packed[("w32", w._rn_name)] = wd
+        if (USE_FUSED_RESAMPLE_CONV1 and isinstance(xin, ResampledGrid) and xin.transform and xin._value is None
+                and key == (1, 8, 5) and list(stride) == [2, 2, 2] and xin.new_size % 16 == 0
+                and act in (None, "prelu") and residual is None and not want32):
+            # resample + axis transform + e_conv1 + bias + PReLU in one kernel; the 128^3 grid is never written
+            bd = _dev_vec(b) if b is not None else torch.zeros(cout, device=wd.device, dtype=torch.float32)
+            ad = _alpha_arg(alpha, cout) if act == "prelu" else None
+            return ops.resample_conv1(xin.voxel, xin.minv, xin.new_size, wd, bd, ad, tf.COMPUTE_DTYPE)
+        xt = realize(xin)
+        if not xt.is_cuda:
+            xt = xt.to(_store().device)
         bd = _dev_vec(b) if b is not None else torch.zeros(cout, device=xt.device, dtype=torch.float32)
         if act == "prelu":
             ad = _alpha_arg(alpha, cout)

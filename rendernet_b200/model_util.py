@@ -29,8 +29,9 @@ def load_weights(weight_dir):
 
 def tf_transform_voxel_to_match_image(tensor_voxel):
     """:41-49: N[b,p,q,r,c] = T[b,q,P-1-p,r,c].  Fused into the resampling kernel when applied to its
-    (deferred) output; a plain strided copy otherwise (pure data movement)."""
+    (deferred) output -- which stays deferred, so that e_conv1 can absorb it too; a plain strided copy otherwise
+    (pure data movement)."""
     if isinstance(tensor_voxel, ResampledGrid):
-        return tensor_voxel.realize(transform=True)
+        return tensor_voxel.transformed()
     t = tensor_voxel if isinstance(tensor_voxel, torch.Tensor) else torch.as_tensor(np.asarray(tensor_voxel))
     return torch.flip(t.permute(0, 2, 1, 3, 4), dims=(1,)).contiguous()

@@ -25,6 +25,8 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _cuda(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) and hasattr(t, "realize"):
+        t = t.realize()            # deferred conv output / deferred resampled grid
     if not t.is_cuda:
         raise RuntimeError("rendernet_b200 kernels need CUDA tensors (there is no CPU fallback)")
     if dtype is not None and t.dtype != dtype:
@@ -323,7 +325,7 @@ def conv2d_transpose_xfold(x: torch.Tensor, L: XFoldConvT, act: Optional[str] = 
 
 def conv_igemm_raw(x, w_packed, bias, taps, ndim, B, H, W, D, Cin, Cout, cout_pad, out16=None, out32=None,
                    alpha=None, act=ACT_NONE, residual=None, o=None, fmt=0, force_bn=0, force_kps=0, max_ctas=0,
-                   cluster=0, cta_group=0, ny=0, tile_w=0):
+                   cluster=0, cta_group=0, ny=0, tile_w=0, msub=0):
     """Direct access to rn_conv_igemm for tests / tuning.  taps: list of (dx,dy,dz)."""
     n = len(taps)
     arr = (C.c_int8 * (3 * n))(*[v for t in taps for v in t])
@@ -345,7 +347,7 @@ def conv_igemm_raw(x, w_packed, bias, taps, ndim, B, H, W, D, Cin, Cout, cout_pa
     d.fmt, d.force_bn, d.force_kps, d.max_ctas = fmt, force_bn, force_kps, max_ctas
     d.cluster = cluster
     d.cta_group = cta_group
-    d.ny, d.tile_w = ny, tile_w
+    d.ny, d.tile_w, d.msub = ny, tile_w, msub
     check(lib.rn_conv_igemm(C.byref(d), _stream()), "rn_conv_igemm")
 
 
@@ -366,6 +368,25 @@ def conv3d_direct(x: torch.Tensor, w_tf: torch.Tensor, bias: torch.Tensor, alpha
     check(lib.rn_conv3d_direct(x.data_ptr(), 1 if x.dtype == torch.float32 else 0, w_tf.data_ptr(),
                                bias.data_ptr(), _ptr(alpha), out.data_ptr(), B, H, W, D, Cin, Cout, k, sy, sx, sz,
                                fmt_of(dtype), _stream()), "rn_conv3d_direct")
+    return out
+
+
+def resample_conv1(vox: torch.Tensor, minv: torch.Tensor, new_size: int, w_tf: torch.Tensor, bias: torch.Tensor,
+                   alpha: Optional[torch.Tensor], dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """Fused resampler + axis transform + e_conv1 (5^3 s2, 1->8) + bias + PReLU; empty tiles skip the conv.
+    vox fp32 [B,S,S,S,1], minv fp32 [B,3,4], w_tf fp32 [5,5,5,1,8] -> 16-bit [B,new/2,new/2,new/2,8]."""
+    vox = _cuda(vox, torch.float32)
+    minv = _cuda(minv, torch.float32)
+    w_tf = _cuda(w_tf, torch.float32)
+    bias = _cuda(bias, torch.float32)
+    B, S = vox.shape[0], vox.shape[1]
+    if tuple(vox.shape) != (B, S, S, S, 1) or tuple(w_tf.shape) != (5, 5, 5, 1, 8) or tuple(minv.shape) != (B, 3, 4):
+        raise ValueError(f"resample_conv1: unsupported shapes {tuple(vox.shape)}, {tuple(w_tf.shape)}")
+    No = new_size // 2
+    out = torch.empty((B, No, No, No, 8), device=vox.device, dtype=dtype)
+    check(lib.rn_resample_conv1_fused(vox.data_ptr(), minv.data_ptr(), w_tf.data_ptr(), bias.data_ptr(), _ptr(alpha),
+                                      out.data_ptr(), B, S, new_size, fmt_of(dtype), _stream()),
+          "rn_resample_conv1_fused")
     return out
 
 

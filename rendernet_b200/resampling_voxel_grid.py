@@ -66,19 +66,29 @@ def inverse_sampling_matrix(transformation_matrix, Scale_matrix=None, size=64, n
 
 
 class ResampledGrid:
-    """Deferred result of tf_resampling so that a following tf_transform_voxel_to_match_image is fused."""
+    """Deferred result of tf_resampling, so that a following tf_transform_voxel_to_match_image is fused into the
+    gather kernel and -- when the consumer is the Shader net's e_conv1 -- the whole resample+transform+conv becomes
+    one kernel that never writes the new_size^3 grid (layer_util.conv3d)."""
 
-    def __init__(self, voxel: torch.Tensor, minv: torch.Tensor, new_size: int):
-        self.voxel, self.minv, self.new_size = voxel, minv, new_size
+    def __init__(self, voxel: torch.Tensor, minv: torch.Tensor, new_size: int, transform: bool = False):
+        self.voxel, self.minv, self.new_size, self.transform = voxel, minv, new_size, transform
         B, _, _, _, C = voxel.shape
         self.shape = (B, new_size, new_size, new_size, C)
+        self.dtype = torch.float32
         self._value = None
 
-    def realize(self, transform: bool = False) -> torch.Tensor:
-        if transform:
-            return ops.resample(self.voxel, self.minv, self.new_size, True)
+    def transformed(self) -> "ResampledGrid":
+        """tools/model_util.py:41-49 applied lazily: N[b,p,q,r,c] = T[b,q,P-1-p,r,c] (cubic grid: same shape)."""
+        if self.transform:
+            raise ValueError("axis transform already applied")
+        return ResampledGrid(self.voxel, self.minv, self.new_size, True)
+
+    def realize(self, transform=None) -> torch.Tensor:
+        t = self.transform if transform is None else bool(transform)
+        if t != self.transform:
+            return ops.resample(self.voxel, self.minv, self.new_size, t)
         if self._value is None:
-            self._value = ops.resample(self.voxel, self.minv, self.new_size, False)
+            self._value = ops.resample(self.voxel, self.minv, self.new_size, t)
         return self._value
 
     def get_shape(self):

@@ -175,8 +175,8 @@ class Deferred:
 
 
 def realize(x):
-    """Materialise a (possibly deferred) tensor."""
-    return x.realize() if isinstance(x, Deferred) else x
+    """Materialise a (possibly deferred) tensor (Deferred conv output or a deferred ResampledGrid)."""
+    return x.realize() if hasattr(x, "realize") else x
 
 
 def shape(x):

@@ -352,6 +352,75 @@ def test_conv_cluster_multicast_bit_identical(cluster, cta_group, bn):
     assert torch.equal(out, ref)
 
 
+@pytest.mark.parametrize("case", ["3x3_bn128_yhalo", "1x1_bn64_ragged", "banded_res", "merged_tconv", "xfold"])
+def test_conv_m_subtiles_bit_identical(case):
+    """msub = 2 (two 128-row accumulators per CTA share each weight stage) must not change a bit: plain 3x3 with
+    y-halo (BN = 128, CTA pairs), a 1x1 with BN = 64 on an image whose height is not a multiple of the doubled tile
+    (TMA zero fill / store clipping on the second sub-tile), the banded 3^3 conv with residual + PReLU, the merged
+    stride-2 transposed conv (TMA scatter store) and the x-folded thin transposed conv."""
+    ops = _ops()
+    from rendernet_b200._lib import lib
+    torch.manual_seed(4)
+
+    def both(fn):
+        outs = []
+        for m in (1, 2):
+            prev = lib.rn_set_default_msub(m)
+            try:
+                outs.append(fn().clone())
+            finally:
+                lib.rn_set_default_msub(prev)
+        assert torch.equal(outs[0], outs[1])
+        return outs[0]
+
+    if case == "3x3_bn128_yhalo":
+        B, H, W, Cin, Cout = 2, 48, 32, 64, 128
+        x = torch.randn(B, H, W, Cin, device=dev).half()
+        w = torch.randn(3, 3, Cin, Cout, device=dev) / (9 * Cin) ** 0.5
+        L = ops.pack_conv("conv2d", w, torch.randn(Cout) * 0.1, torch.rand(Cout) * 0.3)
+        res = torch.randn(B, H, W, Cout, device=dev).half()
+        y = both(lambda: ops.conv2d(x, L, act="prelu", residual=res))
+        want = orc.prelu(orc.conv2d(x.float().cpu().numpy(), w.half().float().cpu().numpy(), L.bias[:Cout].cpu().numpy()),
+                         L.alpha[:Cout].cpu().numpy()) + res.float().cpu().numpy()
+        close(y, want, rel=1.5e-3)
+    elif case == "1x1_bn64_ragged":
+        B, H, W, Cin, Cout = 3, 20, 24, 32, 64          # H = 20: second sub-tile of the last tile row is partly outside
+        x = torch.randn(B, H, W, Cin, device=dev).half()
+        w = torch.randn(1, 1, Cin, Cout, device=dev) / Cin ** 0.5
+        L = ops.pack_conv("conv2d", w, torch.randn(Cout) * 0.1, None)
+        y = both(lambda: ops.conv2d(x, L))
+        close(y, orc.conv2d(x.float().cpu().numpy(), w.half().float().cpu().numpy(), L.bias[:Cout].cpu().numpy()), rel=1.5e-3)
+    elif case == "banded_res":
+        x = torch.randn(2, 32, 32, 32, 32, device=dev).half()
+        res = torch.randn(2, 32, 32, 32, 32, device=dev).half()
+        w = torch.randn(3, 3, 3, 32, 32, device=dev) / (27 * 32) ** 0.5
+        Lb = ops.BandedConv3d(w, torch.randn(32) * 0.1)
+        al = torch.rand(32, device=dev) * 0.3
+        y = both(lambda: ops.conv3d_banded(x, Lb, act="prelu", alpha=al, residual=res))
+        want = orc.prelu(orc.conv3d(x.float().cpu().numpy(), w.half().float().cpu().numpy(), Lb.bias.cpu().numpy(), (1, 1, 1)),
+                         al.cpu().numpy()) + res.float().cpu().numpy()
+        close(y, want, rel=1.5e-3)
+    elif case == "merged_tconv":
+        x = torch.randn(2, 32, 32, 64, device=dev).half()
+        w = torch.randn(4, 4, 32, 64, device=dev) / (16 * 64) ** 0.5
+        L = ops.MergedConvT2(w, torch.randn(32) * 0.1)
+        al = torch.rand(32, device=dev) * 0.3
+        y = both(lambda: ops.conv2d_transpose_s2_merged(x, L, act="prelu", alpha=al))
+        want = orc.prelu(orc.conv2d_transpose(x.float().cpu().numpy(), w.half().float().cpu().numpy(),
+                                              L.bias[:32].cpu().numpy(), (2, 2)), al.cpu().numpy())
+        close(y, want, rel=1.5e-3)
+    else:
+        x = torch.randn(2, 64, 64, 32, device=dev).half()
+        w = torch.randn(4, 4, 16, 32, device=dev) / (16 * 32) ** 0.5
+        b = torch.randn(16) * 0.1
+        L = ops.XFoldConvT(w, b, ops.XFoldConvT.factor(32, 64))
+        al = torch.rand(16, device=dev) * 0.3
+        y = both(lambda: ops.conv2d_transpose_xfold(x, L, act="prelu", alpha=al))
+        want = orc.prelu(orc.conv2d_transpose(x.float().cpu().numpy(), w.half().float().cpu().numpy(), b.numpy(), (1, 1)),
+                         al.cpu().numpy())
+        close(y, want, rel=1.5e-3)
+
+
 # ----------------------------------------------------------------------------------------- thin conv3d / misc
 def test_conv3d_direct_first_layers():
     ops = _ops()
@@ -369,6 +438,44 @@ def test_conv3d_direct_first_layers():
     a = rng.uniform(0, 0.3, 16).astype(np.float32)
     y = ops.conv3d_direct(t(x).half(), t(w), t(b), t(a), (1, 1, 2))
     close(y, orc.prelu(orc.conv3d(x, w, b, (1, 1, 2)), a), rel=1.2e-3)
+
+
+def test_resample_conv1_fused_bit_identical_to_unfused_and_matches_oracle(golden_dir):
+    """resampler + axis transform + e_conv1 + bias + PReLU in one kernel with empty-tile skipping must
+    equal, bit for bit, rn_resample_f32(transform) followed by rn_conv3d_direct -- on the chair fixture (mostly empty
+    tiles), on dense random occupancy with poses that clip the cube at the grid border (partial tiles, SAME padding
+    on every face) and for a reduced grid; and it must match the CPU oracle within one fp16 rounding."""
+    ops = _ops()
+    from rendernet_b200.engine import RenderEngine
+    rng = np.random.default_rng(21)
+    w = (rng.standard_normal((5, 5, 5, 1, 8)) / np.sqrt(125)).astype(np.float32)
+    b = (rng.standard_normal(8) * 0.1).astype(np.float32)
+    a = rng.uniform(0.05, 0.3, 8).astype(np.float32)
+    t = lambda v: torch.from_numpy(np.ascontiguousarray(v)).to(dev)
+    bv = np.load(os.path.join(golden_dir, "binvox.npz"))
+    chair = np.unpackbits(bv["chair_bits"]).reshape(1, 64, 64, 64, 1).astype(np.float32)
+    dense = rng.random((3, 64, 64, 64, 1)).astype(np.float32)
+    poses = np.array([[4.363, 0.524, 1.0], [0.3, 1.2, 1.32], [2.0, -0.4, 2.2], [5.5, 2.8, 0.74]], np.float32)
+    vox = np.concatenate([chair, dense], 0)
+    for new_size, v in ((128, vox), (32, vox[:, :16, :16, :16]), (16, vox[:2, :8, :8, :8])):
+        size = v.shape[1]
+        minv = t(RenderEngine.pose_to_matrix(poses[:v.shape[0]], size, new_size))
+        for alpha in (t(a), None):
+            fused = ops.resample_conv1(t(v), minv, new_size, t(w), t(b), alpha)
+            grid = ops.resample(t(v), minv, new_size, True)
+            unfused = ops.conv3d_direct(grid, t(w), t(b), alpha, (2, 2, 2))
+            assert fused.shape == unfused.shape == (v.shape[0], new_size // 2, new_size // 2, new_size // 2, 8)
+            assert torch.equal(fused, unfused), (new_size, alpha is None)
+        if new_size == 32:
+            want = orc.prelu(orc.conv3d(grid.cpu().numpy(), w, b, (2, 2, 2)), a)
+            close(ops.resample_conv1(t(v), minv, new_size, t(w), t(b), t(a)), want, rel=1.2e-3)
+    # an all-empty input exercises only the skip path: output == PReLU(bias) everywhere
+    zero = torch.zeros(1, 64, 64, 64, 1, device=dev)
+    y = ops.resample_conv1(zero, t(RenderEngine.pose_to_matrix(poses[:1], 64, 128)), 128, t(w), t(b), t(a))
+    const = np.where(b > 0, b, a * b).astype(np.float32)
+    assert torch.equal(y, torch.from_numpy(const).to(dev).half().expand_as(y))
+    with pytest.raises(Exception):
+        ops.resample_conv1(zero, minv[:1], 24, t(w), t(b), t(a))      # new_size % 16 != 0 is rejected (rc -2)
 
 
 def test_bias_act_and_casts():

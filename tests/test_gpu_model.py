@@ -71,7 +71,7 @@ def test_texture_model_matches_reference_golden(golden_dir):
     tr = tf_transform_voxel_to_match_image(tf_rotation_resampling(tex_t, pose))
     x5 = ops.concat_channels(n, tr)
     a, b, c, d = g["patch_slice"]
-    img, nrm = RenderNet(x5[:, a:b, c:d].contiguous())
+    img, nrm = RenderNet(x5[:, a:b, c:d].contiguous())      # x5: concat realises the two deferred grids
     e1, _ = _rel(img, g["image"]); e2, _ = _rel(nrm, g["normal"])
     print("texture net image/normal max-abs err:", e1, e2)
     assert e1 < 1e-3 and e2 < 1e-3
@@ -98,7 +98,25 @@ def test_engine_pipelined_submit_matches_blocking_render():
     for w, g in zip(want, got):
         assert torch.equal(w, g)
     assert not torch.equal(want[0], want[1])
-    assert eng.launches_per_step == 66      # 1 resample + 1 direct + 64 tensor-core launches
+    assert eng.launches_per_step == 65      # 1 fused resample+e_conv1 + 64 tensor-core launches
+
+
+def test_two_engines_coexist():
+    """A second RenderEngine (e.g. Session.run with another batch size) resets the process-wide variable store; the
+    first engine's captured graph must keep its own packed weights alive and still render the same image."""
+    from rendernet_b200.engine import RenderEngine
+    rng = np.random.default_rng(3)
+    vox = (rng.random((1, 64, 64, 64, 1)) < 0.1).astype(np.float32)
+    pose = np.array([[4.36, 0.52, 1.0]], np.float32)
+    a = RenderEngine(None, 1, seed=0)
+    first = a.render(vox, pose).clone()
+    b = RenderEngine(None, 2, seed=1)                 # different weights, different shapes: reuses freed memory if any
+    junk = [torch.randn(64 << 20, device="cuda") for _ in range(4)]      # churn the allocator
+    other = b.render(np.concatenate([vox, vox]), np.concatenate([pose, pose])).clone()
+    again = a.render(vox, pose).clone()
+    del junk
+    assert torch.equal(first, again)
+    assert not torch.equal(first, other[:1])
 
 
 def test_full_size_batch_independence_and_sharding():

@@ -98,8 +98,8 @@ def test_demo_helpers(golden_dir, tmp_path):
     assert v.data.dtype == bool and np.array_equal(v.data, grid) and int(v.data.sum()) == 27933
     with pytest.raises(KeyError):
         Session(load_graph(None)).run("encoder/nope:0", {})
-    with pytest.raises(NotImplementedError):
-        load_graph("model/3d2d_renderer.pb")
+    with pytest.raises(FileNotFoundError):                     # the reference's hard-coded path (RenderNet_demo.py:111)
+        load_graph(str(tmp_path / "model" / "3d2d_renderer.pb"))
 
 
 def test_variable_store_names_and_npz_spelling():
