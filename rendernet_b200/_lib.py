@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librendernet_b200.so")
+# RENDERNET_B200_LIB points at another build of the SAME C ABI (same-box A/B of two builds: scripts/step_time.py)
+LIB_PATH = os.environ.get("RENDERNET_B200_LIB") or os.path.join(_HERE, "librendernet_b200.so")
 
 
 class rn_conv_desc(C.Structure):

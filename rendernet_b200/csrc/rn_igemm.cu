@@ -163,12 +163,13 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
 // 1-CTA kernel is bound by the ~64 B/clk an SM can ingest from L2.  Only the leader CTA (rank 0) issues MMAs; its
 // full barrier collects the TMA bytes of both CTAs; commits are multicast to both CTAs' barriers; the peer's
 // epilogue warps release the accumulator on the leader's barrier with a remote arrive.
-template <int BN, int CL, int CG>
+template <int BN, int CL, int CG, int MS>
 __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   static_assert(CG == 1 || (CG == 2 && CL == 2), "cta_group::2 runs on a 2-CTA cluster");
+  static_assert(MS == 1 || (MS == 2 && BN <= 128), "two accumulators per tile need 4 x BN <= 512 TMEM columns");
   constexpr int CW = (BN >= 32) ? 32 : 16;                     // epilogue column chunk
-  const int ms = p.ms;                                         // M sub-tiles (accumulators) per tile
-  const uint32_t kTmemCols = (2 * ms * BN < 32) ? 32u : static_cast<uint32_t>(2 * ms * BN);  // double-buffered accumulators
+  constexpr int ms = MS;                                       // M sub-tiles (accumulators) per tile (== p.ms)
+  constexpr uint32_t kTmemCols = (2 * MS * BN < 32) ? 32u : static_cast<uint32_t>(2 * MS * BN);  // double-buffered accumulators
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -310,7 +311,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
               for (int k = 0; k < 4; ++k) {
                 if (k < mma_per_kit) {
                   umma_f16<CG>(d_tmem, dak + 2 * k, dbk + 2 * k, idesc, accum);
-                  if (ms == 2) umma_f16<CG>(d_tmem + BN, dak + ams16 + 2 * k, dbk + 2 * k, idesc, accum);  // same weights
+                  if constexpr (MS == 2)   // second accumulator, same weight operand
+                    umma_f16<CG>(d_tmem + BN, dak + ams16 + 2 * k, dbk + 2 * k, idesc, accum);
                   accum = 1;
                 }
               }
@@ -355,8 +357,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       const int nq = ms * NPT;
       const bool tma_out = p.tma_store != 0;
       const uint64_t mapO = reinterpret_cast<uint64_t>(&p.tmO);
+#ifdef RN_NO_RES_PREFETCH   // A/B build: compile the residual prefetch out
+      constexpr bool res_pre = false;
+#else
       const bool res_pre = p.res_prefetch && (p.res != nullptr) && !p.res_is_f32 && p.vec_ok && (p.o_nsplit == 0) &&
                            (t.n0 + BN <= p.n_valid);
+#endif
       uint4 res[RV];
 #pragma unroll
       for (int i = 0; i < RV; ++i) res[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -481,17 +487,17 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int CL, int CG = 1>
-static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+template <int BN, int CL, int CG, int MS>
+static cudaError_t launch_ms(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, CL, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, CL, CG, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if constexpr (CL == 1) {
-    igemm_kernel<BN, 1, 1><<<grid, kNumThreads, smem, stream>>>(p);
+    igemm_kernel<BN, 1, 1, MS><<<grid, kNumThreads, smem, stream>>>(p);
     return cudaGetLastError();
   } else {
     cudaLaunchConfig_t cfg;
@@ -507,8 +513,16 @@ static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaSt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, igemm_kernel<BN, CL, CG>, p);
+    return cudaLaunchKernelEx(&cfg, igemm_kernel<BN, CL, CG, MS>, p);
   }
+}
+
+template <int BN, int CL, int CG = 1>
+static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+  if constexpr (BN <= 128) {
+    if (p.ms == 2) return launch_ms<BN, CL, CG, 2>(p, grid, smem, stream);
+  }
+  return launch_ms<BN, CL, CG, 1>(p, grid, smem, stream);
 }
 
 }  // namespace rn
