@@ -180,6 +180,14 @@ int rn_conv3d_direct(const void* x, int x_is_f32, const float* w, const float* b
 int rn_resample_conv1_fused(const float* vox, const float* minv, const float* w, const float* bias,
                             const float* alpha, void* out16, int B, int size, int new_size, int fmt, void* stream);
 
+/* ---- binvox run-length decode on the device (tools/binvox_rw.py:84-93) ----------------------
+ * pairs: the raw (value, count) byte pairs of n_items files back to back; run_start[r] = number of voxels before run r
+ * WITHIN its item (exclusive prefix sum of the counts, host-computed); item_first_run[i] = index of item i's first
+ * run, item_first_run[n_items] = total runs.  out fp32 [n_items, d0, d2, d1] for fix_coords = 1 (the reference's
+ * transpose(0, 2, 1); what RenderNet_demo.py:125-127 feeds as [1,64,64,64,1]) or [n_items, d0, d1, d2] for 0. */
+int rn_binvox_decode(const uint8_t* pairs, const int* run_start, const int* item_first_run, float* out, int n_items,
+                     int d0, int d1, int d2, int fix_coords, void* stream);
+
 /* ---- texture decoder (BASELINE config 4; RenderNet_Texture_Face_Normal.py:34-46) ----------------------------
  * fully_connected (tools/layer_util.py:311-343): y[B,N] = prelu(x[B,K] . w[K,N] + bias[N]; alpha[N]); fp32 in,
  * 16-bit and/or fp32 out; B <= 32.  alpha NULL -> no activation. */

@@ -626,6 +626,35 @@ __global__ void pack_tconv_s2_merged_kernel(const float* __restrict__ w, uint16_
   }
 }
 
+// ------------------------------------------------------------------------------------------ binvox RLE decode
+// tools/binvox_rw.py:84-93 on the device: the payload is (value, count) byte pairs; the reference
+// expands them with np.repeat, reshapes to dims (x, z, y order) and transposes (0, 2, 1).  Here the 6-12 KB payload is
+// uploaded as is (plus the exclusive prefix sum of the counts, computed on the host over <= a few thousand runs) and
+// each output voxel binary-searches its run: out[b][a][b'][c] = value(run containing flat index (a*d1 + c)*d2 + b').
+__global__ void binvox_decode_kernel(const uint8_t* __restrict__ pairs, const int* __restrict__ run_start,
+                                     const int* __restrict__ item_first_run, float* __restrict__ out, int n_items,
+                                     int d0, int d1, int d2, int fix_coords) {
+  const long long per = static_cast<long long>(d0) * d1 * d2;
+  const long long total = per * n_items;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int item = static_cast<int>(i / per);
+    const int o = static_cast<int>(i - item * per);
+    int f = o;
+    if (fix_coords) {       // output [a][b][c] (extents d0, d2, d1) reads stored [a][c][b]
+      const int c = o % d1, b = (o / d1) % d2, a = o / (d1 * d2);
+      f = (a * d1 + c) * d2 + b;
+    }
+    int lo = __ldg(item_first_run + item), hi = __ldg(item_first_run + item + 1);   // runs [lo, hi) of this item
+    const int* rs = run_start;                                                     // starts are item-relative
+    while (hi - lo > 1) {    // last run r with run_start[r] <= f (zero-length runs are skipped by construction)
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(rs + mid) <= f) lo = mid; else hi = mid;
+    }
+    out[i] = __ldg(pairs + 2 * static_cast<size_t>(lo)) != 0 ? 1.f : 0.f;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ Phong
 __global__ void phong_kernel(const float* __restrict__ img, const float* __restrict__ light_dir,
                              const float* __restrict__ light_col, float ambient, float k_diffuse, int white,
@@ -1111,6 +1140,17 @@ extern "C" int rn_resample_conv1_fused(const float* vox, const float* minv, cons
   if (blocks > 0x7fffffffLL) return -3;
   resample_conv1_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       vox, minv, w, bias, alpha, static_cast<uint16_t*>(out16), B, size, new_size, fmt);
+  RN_COUNT_LAUNCH();
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_binvox_decode(const uint8_t* pairs, const int* run_start, const int* item_first_run, float* out,
+                                int n_items, int d0, int d1, int d2, int fix_coords, void* stream) {
+  if (!pairs || !run_start || !item_first_run || !out || n_items < 1 || d0 < 1 || d1 < 1 || d2 < 1) return -1;
+  const long long total = static_cast<long long>(d0) * d1 * d2 * n_items;
+  if (static_cast<long long>(d0) * d1 * d2 > 0x7fffffffLL) return -2;
+  binvox_decode_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pairs, run_start, item_first_run, out, n_items, d0, d1, d2, fix_coords);
   RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }

@@ -390,6 +390,31 @@ def resample_conv1(vox: torch.Tensor, minv: torch.Tensor, new_size: int, w_tf: t
     return out
 
 
+def binvox_decode(pairs_list, dims, fix_coords: bool = True, device="cuda") -> torch.Tensor:
+    """Run-length (value, count) byte pairs of n binvox payloads -> float32 [n, d0, d2, d1, 1] on the device."""
+    import numpy as np
+    d0, d1, d2 = (int(v) for v in dims)
+    kept, starts, first = [], [], [0]
+    for pairs in pairs_list:
+        pairs = np.asarray(pairs, np.uint8).reshape(-1, 2)
+        pairs = pairs[pairs[:, 1] != 0]                       # zero-length runs carry no voxels
+        cnt = pairs[:, 1].astype(np.int64)
+        if int(cnt.sum()) != d0 * d1 * d2:
+            raise ValueError(f"binvox payload decodes to {int(cnt.sum())} voxels, dims say {d0 * d1 * d2}")
+        kept.append(pairs)
+        starts.append(np.cumsum(cnt) - cnt)
+        first.append(first[-1] + pairs.shape[0])
+    pairs_d = torch.from_numpy(np.ascontiguousarray(np.concatenate(kept))).to(device)
+    starts_d = torch.from_numpy(np.concatenate(starts).astype(np.int32)).to(device)
+    first_d = torch.tensor(first, dtype=torch.int32, device=device)
+    n = len(kept)
+    shape = (n, d0, d2, d1, 1) if fix_coords else (n, d0, d1, d2, 1)
+    out = torch.empty(shape, device=device, dtype=torch.float32)
+    check(lib.rn_binvox_decode(pairs_d.data_ptr(), starts_d.data_ptr(), first_d.data_ptr(), out.data_ptr(), n, d0, d1, d2,
+                               1 if fix_coords else 0, _stream()), "rn_binvox_decode")
+    return out
+
+
 # --------------------------------------------------------------------------------------- misc
 def cast_to_16(x: torch.Tensor, dtype: torch.dtype = torch.float16) -> torch.Tensor:
     x = _cuda(x, torch.float32)

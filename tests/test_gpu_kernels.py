@@ -478,6 +478,49 @@ def test_resample_conv1_fused_bit_identical_to_unfused_and_matches_oracle(golden
         ops.resample_conv1(zero, minv[:1], 24, t(w), t(b), t(a))      # new_size % 16 != 0 is rejected (rc -2)
 
 
+def _rle_bytes(grid_xyz, max_run=255, zero_runs=False):
+    """Encode a bool [d0,d1,d2] grid (x, y, z) the way binvox files store it: x-z-y order, (value, count) byte pairs."""
+    flat = np.transpose(grid_xyz, (0, 2, 1)).reshape(-1).astype(np.uint8)
+    out = bytearray()
+    i = 0
+    while i < flat.size:
+        j = i
+        while j < flat.size and flat[j] == flat[i] and j - i < max_run:
+            j += 1
+        out += bytes([int(flat[i]), j - i])
+        if zero_runs and (i % 7 == 0):
+            out += bytes([1 - int(flat[i]), 0])           # legal zero-length run
+        i = j
+    return bytes(out)
+
+
+def test_binvox_decode_on_device_matches_reader(golden_dir, tmp_path):
+    """rn_binvox_decode (RLE payload -> float32 grid on the GPU) == tools/binvox_rw.read_as_3d_array
+    (:58-93) on the reference's own fixtures (chair, teapot occupancy known-answers), batched, with short and
+    zero-length runs, with and without the axis fix."""
+    import io
+    from rendernet_b200 import binvox_rw
+    bv = np.load(os.path.join(golden_dir, "binvox.npz"))
+    grids = {k: np.unpackbits(bv[k + "_bits"]).reshape(64, 64, 64).astype(bool) for k in ("chair", "teapot")}
+    hdr = b"#binvox 1\ndim 64 64 64\ntranslate 0 0 0\nscale 1\ndata\n"
+    files = [hdr + _rle_bytes(grids["chair"]), hdr + _rle_bytes(grids["teapot"], max_run=17),
+             hdr + _rle_bytes(grids["teapot"], zero_runs=True)]
+    for fix in (True, False):
+        want = np.stack([binvox_rw.read_as_3d_array(io.BytesIO(f), fix_coords=fix).data for f in files])
+        got = binvox_rw.read_to_device([io.BytesIO(f) for f in files], fix_coords=fix)
+        assert got.dtype == torch.float32 and tuple(got.shape) == (3, 64, 64, 64, 1)
+        assert np.array_equal(got.cpu().numpy()[..., 0], want.astype(np.float32))
+    assert int(got[1].sum()) == 27933                                       # teapot occupancy (SURVEY 4)
+    rng = np.random.default_rng(0)                                          # non-cubic dims, dense random occupancy
+    g = rng.random((5, 12, 7)) < 0.5
+    f = b"#binvox 1\ndim 5 12 7\ntranslate 0 0 0\nscale 1\ndata\n" + _rle_bytes(g)
+    got = binvox_rw.read_to_device(io.BytesIO(f))
+    want = binvox_rw.read_as_3d_array(io.BytesIO(f)).data
+    assert tuple(got.shape) == (1,) + want.shape + (1,) and np.array_equal(got.cpu().numpy()[0, ..., 0], want)
+    with pytest.raises(IOError):
+        binvox_rw.read_to_device(io.BytesIO(hdr + _rle_bytes(grids["chair"])[:-2]))     # truncated payload
+
+
 def test_bias_act_and_casts():
     ops = _ops()
     rng = np.random.default_rng(5)

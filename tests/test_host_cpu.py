@@ -102,6 +102,21 @@ def test_demo_helpers(golden_dir, tmp_path):
         load_graph(str(tmp_path / "model" / "3d2d_renderer.pb"))
 
 
+def test_binvox_rle_reader_rejects_bad_payloads():
+    """binvox_rw.read_rle (the host half of the device decode path): header parsing and payload validation."""
+    import io
+    from rendernet_b200 import binvox_rw
+    hdr = b"#binvox 1\ndim 2 2 2\ntranslate 0 0 0\nscale 1\ndata\n"
+    dims, tr, sc, pairs = binvox_rw.read_rle(io.BytesIO(hdr + bytes([0, 3, 1, 5])))
+    assert dims == [2, 2, 2] and tr == [0.0, 0.0, 0.0] and sc == 1.0 and pairs.tolist() == [[0, 3], [1, 5]]
+    with pytest.raises(IOError):
+        binvox_rw.read_rle(io.BytesIO(hdr + bytes([0, 3, 1])))            # odd byte count
+    with pytest.raises(IOError):
+        binvox_rw.read_rle(io.BytesIO(hdr + bytes([0, 3, 1, 4])))         # 7 voxels for a 2x2x2 grid
+    with pytest.raises(IOError):
+        binvox_rw.read_rle(io.BytesIO(b"#notbinvox\n"))
+
+
 def test_variable_store_names_and_npz_spelling():
     from rendernet_b200 import tfcompat as tf
     tf.reset_default_graph(seed=3)
