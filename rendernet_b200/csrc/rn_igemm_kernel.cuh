@@ -21,6 +21,7 @@
 // rn_igemm.cu (host side: validation, tile/pipeline sizing, tensor maps) only sees `launch_variant`.
 #pragma once
 #include <atomic>
+#include <type_traits>
 #include <cstdio>
 #include <cstring>
 #include <cuda_bf16.h>
@@ -364,25 +365,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       const int nq = ms * NPT;
       const bool tma_out = p.tma_store != 0;
       const uint64_t mapO = reinterpret_cast<uint64_t>(&p.tmO);
-#ifdef RN_NO_RES_PREFETCH   // A/B build: compile the residual prefetch out
-      constexpr bool res_pre = false;
-#else
-      const bool res_pre = p.res_prefetch && (p.res != nullptr) && !p.res_is_f32 && p.vec_ok && (p.o_nsplit == 0) &&
-                           (t.n0 + BN <= p.n_valid);
-#endif
-      uint4 res[RV];
+      const bool want_pre = p.res_prefetch && (p.res != nullptr) && !p.res_is_f32 && p.vec_ok && (p.o_nsplit == 0) &&
+                            (t.n0 + BN <= p.n_valid);
+      // Two copies of the drain loop, selected per tile: the one without a residual keeps no prefetch registers alive
+      // (the 1x1 projection kernel is epilogue-bound and measurably slower with them: profiles/r01_ab_oldnew.log).
+      auto drain = [&](auto pre_tag) {
+      constexpr bool res_pre = decltype(pre_tag)::value;
+      uint4 res[res_pre ? RV : 1];
 #pragma unroll
-      for (int i = 0; i < RV; ++i) res[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = 0; i < (res_pre ? RV : 1); ++i) res[i] = make_uint4(0u, 0u, 0u, 0u);
       auto prefetch_res = [&](int q) {                // panel q -> M sub-tile q / NPT, columns (q % NPT) * PC
         const int y = t.y0 + (q / NPT) * p.BH + yl;
         if (x < p.W && y < p.H && z < p.D) {
           const long long o = p.o_base + t.b * p.o_b + y * p.o_y + x * p.o_x + z * p.o_z + t.n0 + (q % NPT) * PC;
           const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res) + o);
 #pragma unroll
-          for (int i = 0; i < RV; ++i) res[i] = __ldg(rp + i);
+          for (int i = 0; i < (res_pre ? RV : 1); ++i) res[i] = __ldg(rp + i);
         }
       };
-      if (res_pre) prefetch_res(0);
+      if constexpr (res_pre) prefetch_res(0);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       int q = 0;                                      // running panel index
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
                 epilogue_chunk<CW>(p, r + pc + c, nc, offc, row_valid, 0, 0, 0, 128, res_pre ? res + c / 8 : nullptr);
               }
               ++q;
-              if (res_pre && q < nq) prefetch_res(q);
+              if constexpr (res_pre) { if (q < nq) prefetch_res(q); }
             } else {
               // registers -> swizzled smem -> one TMA store (full 128-byte lines, edges clipped by TMA)
               named_bar_sync(1, 128);                    // the previous panel's store has finished reading the staging buffer
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
                 epilogue_chunk<CW>(p, r + pc + c, t.n0 + sc + pc + c, off, row_valid, stg_base, m, c / 8, PC * 2,
                                    res_pre ? res + c / 8 : nullptr);
               ++q;
-              if (res_pre && q < nq) prefetch_res(q);    // next panel's residual: in flight across the store + barrier
+              if constexpr (res_pre) { if (q < nq) prefetch_res(q); }   // next panel's residual: in flight across the store + barrier
               fence_proxy_async();
               named_bar_sync(1, 128);                    // panel complete and visible to the async proxy
               if (warp == 2 && lane == 0) {
@@ -443,6 +444,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
           }
         }
       }
+      };
+      if (want_pre) drain(std::true_type{});
+      else drain(std::false_type{});
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
