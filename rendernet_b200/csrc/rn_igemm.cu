@@ -304,6 +304,19 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return 3000 + static_cast<int>(r);
   }
+  // residual L2 prefetch: 16-bit residual laid out exactly like the dense 16-bit output (same map, other base pointer)
+  p.res_l2_prefetch = 0;
+  if (g_res_prefetch && p.tma_store == 1 && d->residual != nullptr && !d->residual_is_f32 &&
+      (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) {
+    const cuuint64_t Ct = static_cast<cuuint64_t>(d->cout_pad);
+    const cuuint64_t dims[4] = {Ct, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    const cuuint64_t strides[3] = {Ct * 2, Ct * 2 * d->W, Ct * 2 * d->W * d->H};
+    const cuuint32_t box[4] = {(cuuint32_t)PCh, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
+    r = enc(&p.tmR, dt, 4, const_cast<void*>(d->residual), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle_of(PCh * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 4000 + static_cast<int>(r);
+    p.res_l2_prefetch = 1;
+  }
   p.out16 = d->out16; p.out32 = d->out32; p.res = d->residual; p.res_is_f32 = d->residual_is_f32;
   p.bias = d->bias; p.alpha = d->alpha; p.act = d->act; p.n_valid = d->Cout;
   p.o_base = d->o_base; p.o_b = d->o_b; p.o_y = d->o_y; p.o_x = d->o_x; p.o_z = d->o_z;

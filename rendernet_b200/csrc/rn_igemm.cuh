@@ -13,6 +13,7 @@ enum Act : int { ACT_NONE = 0, ACT_PRELU = 1, ACT_SIGMOID = 2 };
 struct alignas(64) IgemmParams {
   CUtensorMap tmA;  // activations, channel-last: rank 4 {C,W,H,B} or rank 5 {C,D,W,H,B}; box {KB,[BD],BW,BH,1}
   CUtensorMap tmB;  // weights [tap][CoutPad][Cin]: rank 3 {Cin,CoutPad,taps}; box {KB,BN,1}
+  CUtensorMap tmR;  // 16-bit residual, same geometry and box as tmO (dense output): L2 prefetch of the next tile's rows
   CUtensorMap tmO;  // 16-bit output {Cout,W,H,B}; box {panel cols (<=64), BW, BH, 1}: TMA-store epilogue (tma_store != 0)
   int rank;
   int W, H, D, B;                 // extents of the output (== input) pixel space; D = 1 for rank 4
@@ -38,6 +39,7 @@ struct alignas(64) IgemmParams {
   float* out32;                   // fp32 output or nullptr
   const void* res;                // residual (same indexing as the output) or nullptr
   int res_is_f32;
+  int res_l2_prefetch;            // 1: tmR is valid; the epilogue prefetches the NEXT tile's residual boxes into L2
   int res_prefetch;               // 1: 16-bit residual rows are fetched one panel ahead into registers
   const float* bias;              // [CoutPad]
   const float* alpha;             // [CoutPad] (PReLU) or nullptr

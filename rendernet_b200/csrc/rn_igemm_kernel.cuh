@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     if (p.tma_store) tma_prefetch_desc(&p.tmO);
+    if (p.res_l2_prefetch) tma_prefetch_desc(&p.tmR);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], CG == 2 ? 1 : CL);
@@ -365,6 +366,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       const int nq = ms * NPT;
       const bool tma_out = p.tma_store != 0;
       const uint64_t mapO = reinterpret_cast<uint64_t>(&p.tmO);
+      // HBM -> L2 prefetch of the residual rows of the NEXT tile of this CTA (and of the first tile at start-up): the
+      // register prefetch below is only one 64-column panel deep, enough for L2 latency but not for DRAM latency.
+      if (p.res_l2_prefetch && warp == 2 && lane == 0) {
+        const uint64_t mapR = reinterpret_cast<uint64_t>(&p.tmR);
+        constexpr int PCR = (BN >= 64) ? 64 : BN;
+        auto l2_prefetch_tile = [&](const TileCoord& tt) {
+          for (int s = 0; s < ms; ++s)
+#pragma unroll
+            for (int pc = 0; pc < BN; pc += PCR) tma_prefetch_l2_4d(mapR, tt.n0 + pc, tt.x0, tt.y0 + s * p.BH, tt.b);
+        };
+        if (ct == cl_id) l2_prefetch_tile(t);
+        if (ct + ncl < num_ct) l2_prefetch_tile(decode_tile(p, tile_of(ct + ncl), BN));
+      }
       const bool want_pre = p.res_prefetch && (p.res != nullptr) && !p.res_is_f32 && p.vec_ok && (p.o_nsplit == 0) &&
                             (t.n0 + BN <= p.n_valid);
       // Two copies of the drain loop, selected per tile: the one without a residual keeps no prefetch registers alive

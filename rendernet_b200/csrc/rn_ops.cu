@@ -962,6 +962,11 @@ extern "C" int rn_conv3d_banded_same(const void* x, const void* w_banded, const 
   d.a_c_ntile = (128 / Cout) * sz * Cin;            // each N tile advances 128/Cout output = sz*128/Cout input depths
   d.w_banded = 1;
   if (g_yhalo) d.ny = 3;
+  // With a residual the epilogue is the critical path of these short-K tiles, and the paired (cta_group::2) form couples
+  // the two CTAs' epilogues through the shared accumulator hand-over: multicast clusters of independent CTAs are 17 %
+  // faster there (0.296 vs 0.355 ms), while the PReLU-only convs prefer the pair (0.238 vs 0.270 ms);
+  // profiles/r01_probe_res1_cg.log.  Results are bit-identical either way.
+  if (residual != nullptr) d.cta_group = 1;
   return rn_conv_igemm(&d, stream);
 }
 

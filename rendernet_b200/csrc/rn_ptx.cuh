@@ -198,6 +198,13 @@ __device__ __forceinline__ void tma_store_5d(uint64_t map, uint32_t src, int c0,
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared memory, no completion tracking): used to pull the next tile's residual
+// rows from HBM into L2 a whole tile ahead of the epilogue that adds them
+__device__ __forceinline__ void tma_prefetch_l2_4d(uint64_t map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

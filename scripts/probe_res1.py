@@ -42,6 +42,13 @@ for cl, cg, msub in ((2, 2, 1), (2, 2, 2), (2, 1, 2), (1, 1, 2)):
 lib.rn_set_default_cluster(2)
 lib.rn_set_default_cta_group(2)
 lib.rn_set_tma_store(1)
+lib.rn_set_default_msub(0)
+for rnd in range(2):
+    for pre in (0, 1):
+        lib.rn_set_res_prefetch(pre)
+        ms = timeit(lambda: ops.conv3d_banded(x, Lb, out16=out, residual=res), iters=40)
+        print(f"[res1] round {rnd} residual conv, residual prefetch (registers + L2) {'on ' if pre else 'off'}: {ms:.3f} ms", flush=True)
+lib.rn_set_res_prefetch(1)
 
 # other BN <= 128 layers of the decoder / encoder with and without M sub-tiles
 def layer_probe():
