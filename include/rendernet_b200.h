@@ -35,6 +35,7 @@ long long rn_launch_count(void);
 int rn_set_default_cluster(int cluster);
 int rn_set_default_cta_group(int cta_group);
 int rn_set_yhalo(int on);         /* y-halo sharing in rn_conv2d_same (3x3) / rn_conv3d_banded_same; default on */
+int rn_set_epilogue_groups(int groups); /* 1 or 2 epilogue warp groups where a two-group kernel variant exists; default 2 */
 int rn_set_res_prefetch(int on);  /* epilogue fetches 16-bit residual rows one panel ahead; default on */
 int rn_set_default_msub(int msub); /* M sub-tiles per CTA tile when a descriptor says 0: 0 heuristic, 1, 2 */
 int rn_set_tma_store(int on);     /* TMA-store epilogue for dense 16-bit outputs; default on */

@@ -43,6 +43,7 @@ SIGNATURES = {
     "rn_set_tma_store": (_i, [_i]),
     "rn_set_default_msub": (_i, [_i]),
     "rn_set_res_prefetch": (_i, [_i]),
+    "rn_set_epilogue_groups": (_i, [_i]),
     "rn_resample_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rn_pack_conv_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "rn_cast_f32_to_16": (_i, [_vp, _vp, _ll, _ll, _i, _vp]),

@@ -33,6 +33,8 @@ cudaError_t launch_bn256(int CL, int CG, const IgemmParams& p, int grid, size_t 
 cudaError_t launch_bn128(int CL, int CG, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_bn128_ms2(int CL, int CG, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_small(int BN, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_eg2_256(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);              // <256,2,2,1,2>
+cudaError_t launch_eg2_128(int CG, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);      // <128,2,CG,ms,2>
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -56,6 +58,7 @@ static CUtensorMapSwizzle swizzle_of(int row_bytes) {
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+int g_epi_groups = 1;                        // epilogue warp groups where a two-group kernel variant exists (1 = always one)
 int g_res_prefetch = 1;                      // fetch 16-bit residual rows one panel ahead in the epilogue (A/B switch)
 int g_default_msub = 0;                      // M sub-tiles per CTA tile when the descriptor says 0: 0 = heuristic, 1, 2
 int g_tma_store = 1;                         // TMA-store epilogue where the output is a dense 16-bit NHWC tensor
@@ -80,6 +83,12 @@ static int num_sms() {
 extern "C" int rn_set_default_cluster(int c) {
   const int prev = rn::g_default_cluster;
   if (c == 1 || c == 2 || c == 4) rn::g_default_cluster = c;
+  return prev;
+}
+
+extern "C" int rn_set_epilogue_groups(int g) {
+  const int prev = rn::g_epi_groups;
+  if (g == 1 || g == 2) rn::g_epi_groups = g;
   return prev;
 }
 
@@ -184,15 +193,24 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   if (g_tma_store && scatter_out && d->out16 != nullptr && d->out32 == nullptr && d->Cout == d->cout_pad &&
       (reinterpret_cast<uintptr_t>(d->out16) & 15) == 0)
     p.tma_store = 2;
-  const int stg_bytes = p.tma_store ? (kTileM * PCh * 2 + 1024) : 0;
-  const int budget = 232448 - 1024 - 256 - stg_bytes;
-  int grid = 0, CL = 1, CG = 1, sub = 0;
+  int grid = 0, CL = 1, CG = 1, sub = 0, EG = 1, stg_bytes = 0;
   // M sub-tiles: two 128-row accumulators per CTA share every weight stage (BN <= 128 so that 2 x 2 x BN TMEM columns
   // fit).  Halves the weight bytes per MAC; measured on every BN <= 128 layer of the network (banded 3^3 convs
   // 0.28 -> 0.22 ms, e_conv10 0.43 -> 0.26, e_conv7_1 0.25 -> 0.17: profiles/r01_probe_msub.log), never slower.
   int want_ms = d->msub > 0 ? d->msub : (g_default_msub > 0 ? g_default_msub : 2);
   if (want_ms > 2) return -16;
   if (BN > 128 || d->ndim != 2) want_ms = 1;
+  // Epilogue warp groups: a second group of four epilogue warps (own staging buffer) where the kernel variant exists and
+  // the extra 16 KB do not cost the pipeline its third stage, its halo sharing or its second accumulator.
+  const int ny_req = p.ny, ms_req = want_ms;
+  IgemmParams p_one;                         // sizing with one epilogue group (always valid), kept as the fall-back
+  int grid_one = 0, CL_one = 1, CG_one = 1, sub_one = 0, stg_one = 0;
+  for (int eg = 1; eg <= ((g_epi_groups == 2 && BN >= 128) ? 2 : 1); ++eg) {
+  EG = eg;
+  p.ny = ny_req;
+  want_ms = ms_req;
+  stg_bytes = p.tma_store ? (eg * kTileM * PCh * 2 + 1024) : 0;
+  const int budget = 232448 - 1024 - 256 - stg_bytes;
   for (int attempt = 0; attempt < 3; ++attempt) {
     p.ms = want_ms;
     int rem = kTileM;
@@ -246,6 +264,16 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
     if (p.stages >= 3 || (p.ny == 1 && p.ms == 1)) break;
     if (want_ms > 1) want_ms = 1;           // retry with one accumulator per tile,
     else p.ny = 1;                          // then without halo sharing
+  }
+  if (eg == 1) {
+    p_one = p; grid_one = grid; CL_one = CL; CG_one = CG; sub_one = sub; stg_one = stg_bytes;
+  } else {
+    const bool have_variant = (BN == 256 && CG == 2) || (BN == 128 && (CG == 2 || (CG == 1 && CL == 2)));
+    const bool same_shape = p.ms == p_one.ms && p.ny == p_one.ny && CL == CL_one && CG == CG_one;
+    if (!(have_variant && same_shape && p.stages >= 3)) {    // keep the single-group sizing
+      p = p_one; grid = grid_one; CL = CL_one; CG = CG_one; sub = sub_one; stg_bytes = stg_one; EG = 1;
+    }
+  }
   }
   if (p.stages < 2) return -10;
   const size_t smem = static_cast<size_t>(p.stages) * p.kps * sub + 1024 + 256 + stg_bytes;
@@ -329,7 +357,9 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   p.vec_ok = strides8 && al16(d->out16) && al16(d->out32) && al16(d->residual) ? 1 : 0;
 
   cudaError_t e;
-  if (BN == 256) e = launch_bn256(CL, CG, p, grid, smem, stream);
+  if (EG == 2 && BN == 256) e = launch_eg2_256(p, grid, smem, stream);
+  else if (EG == 2) e = launch_eg2_128(CG, p, grid, smem, stream);
+  else if (BN == 256) e = launch_bn256(CL, CG, p, grid, smem, stream);
   else if (BN == 128) e = (p.ms == 2) ? launch_bn128_ms2(CL, CG, p, grid, smem, stream) : launch_bn128(CL, CG, p, grid, smem, stream);
   else e = launch_small(BN, p, grid, smem, stream);
   return e == cudaSuccess ? 0 : static_cast<int>(e);

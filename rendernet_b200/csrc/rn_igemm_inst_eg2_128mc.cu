@@ -1,0 +1,11 @@
+// igemm_kernel with two epilogue warp groups, 128-column N tile, multicast cluster of 2 independent CTAs.
+#include "rn_igemm_kernel.cuh"
+
+namespace rn {
+cudaError_t launch_eg2_128_pair(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_eg2_128(int CG, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+  if (CG == 2) return launch_eg2_128_pair(p, grid, smem, stream);
+  if (p.ms == 2) return launch_ms<128, 2, 1, 2, 2>(p, grid, smem, stream);
+  return launch_ms<128, 2, 1, 1, 2>(p, grid, smem, stream);
+}
+}  // namespace rn

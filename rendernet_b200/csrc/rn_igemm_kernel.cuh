@@ -171,9 +171,15 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
 // 1-CTA kernel is bound by the ~64 B/clk an SM can ingest from L2.  Only the leader CTA (rank 0) issues MMAs; its
 // full barrier collects the TMA bytes of both CTAs; commits are multicast to both CTAs' barriers; the peer's
 // epilogue warps release the accumulator on the leader's barrier with a remote arrive.
-template <int BN, int CL, int CG, int MS>
-__global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+//
+// EG = epilogue warp groups (1 or 2).  EG = 2 adds warps 6..9: both groups of four warps cover the four TMEM lane
+// quadrants, each drains half of the tile's panels (its own M sub-tile, or its own half of the columns) through its own
+// staging buffer and named barrier.  For the short-K tiles (1x1 projection unit, banded 3^3 convs, thin decoder layers)
+// the epilogue is latency-bound (tcgen05.ld behind queued MMAs, residual rows from L2) and was the critical path.
+template <int BN, int CL, int CG, int MS, int EG>
+__global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   static_assert(CG == 1 || (CG == 2 && CL == 2), "cta_group::2 runs on a 2-CTA cluster");
+  static_assert(EG == 1 || EG == 2, "one or two epilogue warp groups");
   static_assert(MS == 1 || (MS == 2 && BN <= 128), "two accumulators per tile need 4 x BN <= 512 TMEM columns");
   constexpr int CW = (BN >= 32) ? 32 : 16;                     // epilogue column chunk
   constexpr int ms = MS;                                       // M sub-tiles (accumulators) per tile (== p.ms)
@@ -205,7 +211,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], CG == 2 ? 8 : 4);   // 4 epilogue warps (x2 CTAs feeding the leader's barrier)
+      mbar_init(&tempty_bar[a], (CG == 2 ? 8 : 4) * EG);   // 4 epilogue warps per group (x2 CTAs feeding the leader's barrier)
     }
     fence_barrier_init();
   }
@@ -351,6 +357,109 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     const int yl = m / (p.BD * p.BW);
     int acc = 0;
     uint32_t acc_phase = 0;
+    if constexpr (EG == 2) {
+      // ---------------------------------------------------------- two warp groups, one 64-column panel per tcgen05.ld
+      constexpr int PC = (BN >= 64) ? 64 : BN;        // panel = TMEM load = staging buffer = TMA store box
+      constexpr int NPT = BN / PC;                    // panels per accumulator
+      constexpr int RV = PC / 8;
+      constexpr int NQ = MS * NPT;                    // panels per tile
+      constexpr int PER = NQ >= 2 ? NQ / 2 : NQ;      // panels per group (a lone panel goes to group 0)
+      const int grp = (warp - 2) >> 2;
+      const int q_lo = grp * PER, q_hi = (NQ >= 2) ? q_lo + PER : (grp == 0 ? 1 : 0);
+      const int bar_id = 1 + grp;
+      const uint32_t stg = stg_base + static_cast<uint32_t>(grp) * (kTileM * PC * 2);
+      const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+      const bool tma_out = p.tma_store != 0;
+      const uint64_t mapO = reinterpret_cast<uint64_t>(&p.tmO);
+      for (int ct = cl_id; ct < num_ct; ct += ncl) {
+        const TileCoord t = decode_tile(p, tile_of(ct), BN);
+        const int x = t.x0 + xl, z = t.z0 + zl;
+        if (p.res_l2_prefetch && warp == 2 && lane == 0) {   // next tile's residual rows: HBM -> L2 a whole tile ahead
+          const uint64_t mapR = reinterpret_cast<uint64_t>(&p.tmR);
+          auto l2_prefetch_tile = [&](const TileCoord& tt) {
+            for (int s = 0; s < ms; ++s)
+#pragma unroll
+              for (int pc = 0; pc < BN; pc += PC) tma_prefetch_l2_4d(mapR, tt.n0 + pc, tt.x0, tt.y0 + s * p.BH, tt.b);
+          };
+          if (ct == cl_id) l2_prefetch_tile(t);
+          if (ct + ncl < num_ct) l2_prefetch_tile(decode_tile(p, tile_of(ct + ncl), BN));
+        }
+        const bool want_pre = p.res_prefetch && (p.res != nullptr) && !p.res_is_f32 && p.vec_ok && (p.o_nsplit == 0) &&
+                              (t.n0 + BN <= p.n_valid);
+        auto drain = [&](auto pre_tag) {
+          constexpr bool res_pre = decltype(pre_tag)::value;
+          uint4 res[res_pre ? RV : 1];
+#pragma unroll
+          for (int i = 0; i < (res_pre ? RV : 1); ++i) res[i] = make_uint4(0u, 0u, 0u, 0u);
+          auto prefetch_res = [&](int q) {
+            const int y = t.y0 + (q / NPT) * p.BH + yl;
+            if (x < p.W && y < p.H && z < p.D) {
+              const long long o = p.o_base + t.b * p.o_b + y * p.o_y + x * p.o_x + z * p.o_z + t.n0 + (q % NPT) * PC;
+              const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res) + o);
+#pragma unroll
+              for (int i = 0; i < (res_pre ? RV : 1); ++i) res[i] = __ldg(rp + i);
+            }
+          };
+          if constexpr (res_pre) { if (q_lo < q_hi) prefetch_res(q_lo); }
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+          auto release = [&]() {     // this warp has read all it will read of the tile's accumulators
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // leader owns the barrier
+              else mbar_arrive(&tempty_bar[acc]);
+            }
+          };
+          if (q_lo >= q_hi) release();
+#pragma unroll 1
+          for (int q = q_lo; q < q_hi; ++q) {
+            const int s = q / NPT, pc = (q % NPT) * PC;
+            const int ys0 = t.y0 + s * p.BH, y = ys0 + yl;
+            const bool row_valid = (x < p.W) && (y < p.H) && (z < p.D);
+            const long long off = p.o_base + t.b * p.o_b + y * p.o_y + x * p.o_x + z * p.o_z;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                   static_cast<uint32_t>((acc * ms + s) * BN + pc);
+            uint32_t r[PC];
+            if constexpr (PC == 64) tmem_ld_32x32b_x64(taddr, r);
+            else if constexpr (PC == 32) tmem_ld_32x32b_x32(taddr, r);
+            else tmem_ld_32x32b_x16(taddr, r);
+            tmem_ld_wait();
+            if (q == q_hi - 1) release();
+            if (!tma_out) {
+#pragma unroll
+              for (int c = 0; c < PC; c += CW) {
+                const int nc = t.n0 + pc + c;
+                const long long offc = p.o_nsplit > 0 ? off + (nc / p.o_nsplit) * p.o_nhi + (nc % p.o_nsplit) - nc : off;
+                epilogue_chunk<CW>(p, r + c, nc, offc, row_valid, 0, 0, 0, 128, res_pre ? res + c / 8 : nullptr);
+              }
+              if constexpr (res_pre) { if (q + 1 < q_hi) prefetch_res(q + 1); }
+            } else {
+              named_bar_sync(bar_id, 128);               // this group's previous store has finished reading its staging buffer
+#pragma unroll
+              for (int c = 0; c < PC; c += CW)
+                epilogue_chunk<CW>(p, r + c, t.n0 + pc + c, off, row_valid, stg, m, c / 8, PC * 2,
+                                   res_pre ? res + c / 8 : nullptr);
+              if constexpr (res_pre) { if (q + 1 < q_hi) prefetch_res(q + 1); }
+              fence_proxy_async();
+              named_bar_sync(bar_id, 128);               // panel complete and visible to the async proxy
+              if (leader) {
+                const int ncol = t.n0 + pc;
+                if (p.tma_store == 2) tma_store_5d(mapO, stg, ncol % p.o_nsplit, t.x0, ncol / p.o_nsplit, ys0, t.b);
+                else tma_store_4d(mapO, stg, ncol, t.x0, ys0, t.b);
+                tma_store_commit();
+                tma_store_wait_read();
+              }
+            }
+          }
+        };
+        if (want_pre) drain(std::true_type{});
+        else drain(std::false_type{});
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (p.tma_store && leader) tma_store_wait_all();
+    } else {
     for (int ct = cl_id; ct < num_ct; ct += ncl) {
       const TileCoord t = decode_tile(p, tile_of(ct), BN);
       const int x = t.x0 + xl, z = t.z0 + zl;
@@ -464,32 +573,33 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_all();
+    }   // EG == 1
   }
 
-  if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync();   // no CTA exits while a peer may still multicast into / commit to it
   if (warp == 1) tmem_dealloc<CG>(tmem_base, kTmemCols);
 }
 
-template <int BN, int CL, int CG, int MS>
+template <int BN, int CL, int CG, int MS, int EG = 1>
 static cudaError_t launch_ms(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, CL, CG, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, CL, CG, MS, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if constexpr (CL == 1) {
-    igemm_kernel<BN, 1, 1, MS><<<grid, kNumThreads, smem, stream>>>(p);
+    igemm_kernel<BN, 1, 1, MS, EG><<<grid, 64 + 128 * EG, smem, stream>>>(p);
     return cudaGetLastError();
   } else {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kNumThreads);
+    cfg.blockDim = dim3(64 + 128 * EG);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -499,7 +609,7 @@ static cudaError_t launch_ms(const IgemmParams& p, int grid, size_t smem, cudaSt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, igemm_kernel<BN, CL, CG, MS>, p);
+    return cudaLaunchKernelEx(&cfg, igemm_kernel<BN, CL, CG, MS, EG>, p);
   }
 }
 

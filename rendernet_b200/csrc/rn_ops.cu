@@ -16,6 +16,9 @@
 
 #include <atomic>
 namespace rn {
+extern int g_epi_groups;   // rn_igemm.cu: epilogue warp groups (rn_set_epilogue_groups)
+}
+namespace rn {
 extern std::atomic<long long> g_launch_count;
 #define RN_COUNT_LAUNCH() rn::g_launch_count.fetch_add(1, std::memory_order_relaxed)
 int g_yhalo = 1;   // share one activation halo load between the 3 ky taps of 3x3 / banded 3^3 convs
@@ -966,7 +969,9 @@ extern "C" int rn_conv3d_banded_same(const void* x, const void* w_banded, const 
   // the two CTAs' epilogues through the shared accumulator hand-over: multicast clusters of independent CTAs are 17 %
   // faster there (0.296 vs 0.355 ms), while the PReLU-only convs prefer the pair (0.238 vs 0.270 ms);
   // profiles/r01_probe_res1_cg.log.  Results are bit-identical either way.
-  if (residual != nullptr) d.cta_group = 1;
+  // (With two epilogue warp groups the pair form drains fast enough again, so the override only applies to the
+  // single-group configuration.)
+  if (residual != nullptr && rn::g_epi_groups == 1) d.cta_group = 1;
   return rn_conv_igemm(&d, stream);
 }
 

@@ -19,10 +19,11 @@ vox = (rng.random((B, 64, 64, 64, 1)) < 0.10).astype(np.float32)
 pose = np.stack([rng.uniform(0, 2 * np.pi, B), (90 - rng.uniform(10, 170, B)) * np.pi / 180,
                  3.3 / rng.uniform(2.5, 4.5, B)], 1).astype(np.float32)
 
-configs = [("msub=1 res_prefetch=0 unfused", 1, 0, False), ("msub=2 res_prefetch=0 fused", 2, 0, True),
-           ("msub=2 res_prefetch=1 fused", 2, 1, True), ("msub=1 res_prefetch=1 fused", 1, 1, True)]
+configs = [("epilogue groups=1", 0, 1, True, 1), ("epilogue groups=2", 0, 1, True, 2),
+           ("msub=1 res_prefetch=0 unfused groups=1 (round-1 mid state)", 1, 0, False, 1)]
 engines = []
-for name, msub, pre, fused in configs:
+for name, msub, pre, fused, groups in configs:
+    lib.rn_set_epilogue_groups(groups)
     lib.rn_set_default_msub(msub)
     lib.rn_set_res_prefetch(pre)
     layer_util.USE_FUSED_RESAMPLE_CONV1 = fused
@@ -32,6 +33,7 @@ for name, msub, pre, fused in configs:
     engines.append((name, eng))
 lib.rn_set_default_msub(0)
 lib.rn_set_res_prefetch(1)
+lib.rn_set_epilogue_groups(2)
 layer_util.USE_FUSED_RESAMPLE_CONV1 = True
 
 ref = None

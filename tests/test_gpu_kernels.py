@@ -363,14 +363,17 @@ def test_conv_m_subtiles_bit_identical(case):
     torch.manual_seed(4)
 
     def both(fn):
+        """msub 1/2 x epilogue warp groups 1/2: all four kernel variants must agree bit for bit."""
         outs = []
         for m in (1, 2):
-            prev = lib.rn_set_default_msub(m)
-            try:
-                outs.append(fn().clone())
-            finally:
-                lib.rn_set_default_msub(prev)
-        assert torch.equal(outs[0], outs[1])
+            for g in (1, 2):
+                prev, prev_g = lib.rn_set_default_msub(m), lib.rn_set_epilogue_groups(g)
+                try:
+                    outs.append(fn().clone())
+                finally:
+                    lib.rn_set_default_msub(prev)
+                    lib.rn_set_epilogue_groups(prev_g)
+        assert all(torch.equal(outs[0], o) for o in outs[1:])
         return outs[0]
 
     if case == "3x3_bn128_yhalo":
@@ -419,6 +422,36 @@ def test_conv_m_subtiles_bit_identical(case):
         want = orc.prelu(orc.conv2d_transpose(x.float().cpu().numpy(), w.half().float().cpu().numpy(), b.numpy(), (1, 1)),
                          al.cpu().numpy())
         close(y, want, rel=1.5e-3)
+
+
+def test_conv_two_epilogue_groups_bit_identical():
+    """The second group of four epilogue warps (EG = 2: projection unit 1x1, 4x4 convs with short K, residual adds) must
+    reproduce the single-group kernel bit for bit, including ragged image edges and the residual / sigmoid epilogues."""
+    ops = _ops()
+    from rendernet_b200._lib import lib
+    torch.manual_seed(9)
+    for (B, H, W, Cin, Cout, k, act, use_res) in ((4, 32, 32, 256, 256, 1, "prelu", False), (3, 24, 40, 128, 512, 1, None, True),
+                                                  (2, 32, 32, 64, 256, 4, "sigmoid", False), (2, 16, 48, 128, 128, 3, "prelu", True)):
+        x = torch.randn(B, H, W, Cin, device=dev).half()
+        w = torch.randn(k, k, Cin, Cout, device=dev) / (k * k * Cin) ** 0.5
+        L = ops.pack_conv("conv2d", w, torch.randn(Cout) * 0.1, torch.rand(Cout) * 0.3)
+        res = torch.randn(B, H, W, Cout, device=dev).half() if use_res else None
+        outs = []
+        for g in (1, 2):
+            prev = lib.rn_set_epilogue_groups(g)
+            try:
+                outs.append(ops.conv2d(x, L, act=act, residual=res).clone())
+            finally:
+                lib.rn_set_epilogue_groups(prev)
+        assert torch.equal(outs[0], outs[1]), (B, H, W, Cin, Cout, k, act, use_res)
+        want = orc.conv2d(x.float().cpu().numpy(), w.half().float().cpu().numpy(), L.bias[:Cout].cpu().numpy())
+        if act == "prelu":
+            want = orc.prelu(want, L.alpha[:Cout].cpu().numpy())
+        elif act == "sigmoid":
+            want = 1.0 / (1.0 + np.exp(-want))
+        if use_res:
+            want = want + res.float().cpu().numpy()
+        close(outs[1], want, rel=1.5e-3)
 
 
 # ----------------------------------------------------------------------------------------- thin conv3d / misc
