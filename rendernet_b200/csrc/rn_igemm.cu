@@ -58,7 +58,7 @@ static CUtensorMapSwizzle swizzle_of(int row_bytes) {
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-int g_epi_groups = 1;                        // epilogue warp groups where a two-group kernel variant exists (1 = always one)
+int g_epi_groups = 2;                        // epilogue warp groups where a two-group kernel variant exists (1 = always one)
 int g_res_prefetch = 1;                      // fetch 16-bit residual rows one panel ahead in the epilogue (A/B switch)
 int g_default_msub = 0;                      // M sub-tiles per CTA tile when the descriptor says 0: 0 = heuristic, 1, 2
 int g_tma_store = 1;                         // TMA-store epilogue where the output is a dense 16-bit NHWC tensor

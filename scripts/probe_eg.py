@@ -45,4 +45,4 @@ for rnd in range(2):
             lib.rn_set_epilogue_groups(g)
             t[g] = timeit(fn, iters=40, warm=5)
         print(f"[eg] round {rnd} {name}: groups=1 {t[1]:.4f} ms, groups=2 {t[2]:.4f} ms ({(t[1] / t[2] - 1) * 100:+.1f} %)", flush=True)
-lib.rn_set_epilogue_groups(1)
+lib.rn_set_epilogue_groups(2)
