@@ -252,7 +252,7 @@ def run_ours(args, rank, world, local_rank):
         return
 
     peaks = measured_peaks()
-    # ---- roofline of the dominant kernel: igemm_kernel<256> on the 3x3 1024->1024 trunk conv (21 of the 75 launches,
+    # ---- roofline of the dominant kernel: igemm_kernel<256> on the 3x3 1024->1024 trunk conv (21 of the 65 launches,
     # ~half of the step), timed alone with CUDA events on its launch stream, inputs (201 MB) larger than L2.
     x = torch.randn(B, 64, 64, 1024, device=dev).half()
     w = torch.randn(3, 3, 1024, 1024, device=dev) / 96.0
