@@ -33,6 +33,7 @@ cudaError_t launch_bn256(int CL, int CG, const IgemmParams& p, int grid, size_t 
 cudaError_t launch_bn128(int CL, int CG, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_bn128_ms2(int CL, int CG, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_small(int BN, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_small_eg2(int BN, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);   // <BN,1,1,2,2>
 cudaError_t launch_eg2_256(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);              // <256,2,2,1,2>
 cudaError_t launch_eg2_128(int CG, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);      // <128,2,CG,ms,2>
 
@@ -205,7 +206,7 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   const int ny_req = p.ny, ms_req = want_ms;
   IgemmParams p_one;                         // sizing with one epilogue group (always valid), kept as the fall-back
   int grid_one = 0, CL_one = 1, CG_one = 1, sub_one = 0, stg_one = 0;
-  for (int eg = 1; eg <= ((g_epi_groups == 2 && BN >= 128) ? 2 : 1); ++eg) {
+  for (int eg = 1; eg <= (g_epi_groups == 2 ? 2 : 1); ++eg) {
   EG = eg;
   p.ny = ny_req;
   want_ms = ms_req;
@@ -268,7 +269,8 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   if (eg == 1) {
     p_one = p; grid_one = grid; CL_one = CL; CG_one = CG; sub_one = sub; stg_one = stg_bytes;
   } else {
-    const bool have_variant = (BN == 256 && CG == 2) || (BN == 128 && (CG == 2 || (CG == 1 && CL == 2)));
+    const bool have_variant = (BN == 256 && CG == 2) || (BN == 128 && (CG == 2 || (CG == 1 && CL == 2))) ||
+                              (BN < 128 && p.ms == 2);
     const bool same_shape = p.ms == p_one.ms && p.ny == p_one.ny && CL == CL_one && CG == CG_one;
     if (!(have_variant && same_shape && p.stages >= 3)) {    // keep the single-group sizing
       p = p_one; grid = grid_one; CL = CL_one; CG = CG_one; sub = sub_one; stg_bytes = stg_one; EG = 1;
@@ -358,7 +360,8 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
 
   cudaError_t e;
   if (EG == 2 && BN == 256) e = launch_eg2_256(p, grid, smem, stream);
-  else if (EG == 2) e = launch_eg2_128(CG, p, grid, smem, stream);
+  else if (EG == 2 && BN == 128) e = launch_eg2_128(CG, p, grid, smem, stream);
+  else if (EG == 2) e = launch_small_eg2(BN, p, grid, smem, stream);
   else if (BN == 256) e = launch_bn256(CL, CG, p, grid, smem, stream);
   else if (BN == 128) e = (p.ms == 2) ? launch_bn128_ms2(CL, CG, p, grid, smem, stream) : launch_bn128(CL, CG, p, grid, smem, stream);
   else e = launch_small(BN, p, grid, smem, stream);

@@ -38,6 +38,14 @@ wt = torch.randn(4, 4, 128, 128, device=dev) / (16 * 128) ** 0.5
 Lt = ops.pack_conv("conv2d_transpose", wt, torch.zeros(128), torch.rand(128) * 0.3, stride=1)
 ot = torch.empty(B, 128, 128, 128, device=dev, dtype=torch.float16)
 cases.append(("e_conv7_1 T s1 128->128", lambda: ops.conv2d_transpose(xt, Lt, act="prelu", out16=ot)))
+for nm, cin, cout in (("e_conv10 T s1 32->16 @512 xfold", 32, 16), ("e_conv11 T s1 16->3 @512 xfold", 16, 3)):
+    xx = torch.randn(B, 512, 512, cin, device=dev).half()
+    ww = torch.randn(4, 4, cout, cin, device=dev) / (16 * cin) ** 0.5
+    Lx = ops.XFoldConvT(ww, torch.zeros(cout), ops.XFoldConvT.factor(cin, 512))
+    ox = torch.empty(B, 512, 512, cout, device=dev, dtype=torch.float16)
+    ax = torch.rand(cout, device=dev) * 0.3
+    cases.append((nm, (lambda xx=xx, Lx=Lx, ox=ox, ax=ax: ops.conv2d_transpose_xfold(xx, Lx, act="prelu", alpha=ax, out16=ox))))
+cases = cases[-2:] + cases[:2]
 for rnd in range(2):
     for name, fn in cases:
         t = {}
