@@ -109,6 +109,12 @@ typedef struct rn_conv_desc {
   long long o_nhi;
 } rn_conv_desc;
 int rn_conv_igemm(const rn_conv_desc* d, void* stream);
+/* The launch plan rn_conv_igemm would use for `d`, without touching the device (works on a host without a GPU; the SM
+ * count then defaults to 148).  Pointers in `d` are only tested for null / 16-byte alignment.  out[0..n_out) receives
+ * {N tile, cluster size, cta_group, M sub-tiles, epilogue warp groups, ny (halo sharing), tile W, tile H, tile D,
+ *  k-groups per stage, stages, dynamic shared memory bytes, grid, tiles, epilogue mode (0 direct, 1 TMA store, 2 TMA
+ *  scatter), swizzle row bytes}; n_out <= 16.  Same status codes as rn_conv_igemm. */
+int rn_conv_plan(const rn_conv_desc* d, int* out, int n_out);
 
 /* Reference-shaped wrappers over rn_conv_igemm (stride 1, TF SAME), 16-bit in/out:
  * slim.conv2d / layer_util.conv2d (layer_util.py:147, RenderNet_Shader.py:83,87,98,102),

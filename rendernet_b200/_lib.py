@@ -30,6 +30,8 @@ class rn_conv_desc(C.Structure):
 
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+PLAN_FIELDS = ("bn", "cluster", "cta_group", "msub", "epilogue_groups", "ny", "tile_w", "tile_h", "tile_d", "kps", "stages",
+               "smem_bytes", "grid", "tiles", "epilogue_mode", "row_bytes")
 
 # name -> (restype, argtypes); mirrors include/rendernet_b200.h one to one
 SIGNATURES = {
@@ -50,6 +52,7 @@ SIGNATURES = {
     "rn_cast_16_to_f32": (_i, [_vp, _vp, _ll, _i, _vp]),
     "rn_bias_act_16": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "rn_conv_igemm": (_i, [C.POINTER(rn_conv_desc), _vp]),
+    "rn_conv_plan": (_i, [C.POINTER(rn_conv_desc), C.POINTER(C.c_int), _i]),
     "rn_conv2d_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rn_conv3d_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rn_conv3d_banded_bytes": (_ll, [_i, _i, _i]),

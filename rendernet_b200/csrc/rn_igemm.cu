@@ -72,7 +72,11 @@ static int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) {
+      cudaGetLastError();
+      g_num_sms = 0;
+      return 148;       // no device visible (rn_conv_plan on a CPU-only host): plan for a B200
+    }
   }
   return g_num_sms;
 }
@@ -125,9 +129,16 @@ extern "C" int rn_set_default_cta_group(int g) {
 
 extern "C" long long rn_launch_count(void) { return rn::g_launch_count.load(std::memory_order_relaxed); }
 
-extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
-  using namespace rn;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+namespace rn {
+struct ConvPlan {
+  int BN, CL, CG, EG, grid, sub, stg_bytes, PCh, KB, D;
+  size_t smem;
+};
+
+// Everything rn_conv_igemm decides before it touches the device: N tile, M tile box, halo sharing, M sub-tiles, cluster /
+// CTA-pair mode, epilogue groups, pipeline depth, shared-memory size, epilogue mode.  Pure host arithmetic on the
+// descriptor (pointers are only tested for null / alignment), so rn_conv_plan can report it on a machine without a GPU.
+static int plan_conv(const rn_conv_desc* d, IgemmParams& p, ConvPlan& pl) {
   if (d == nullptr || d->x == nullptr || d->w_packed == nullptr || d->bias == nullptr) return -1;
   if (d->ndim != 2 && d->ndim != 3) return -2;
   if (d->ntaps < 1 || d->ntaps > kMaxTaps) return -3;
@@ -136,10 +147,7 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   if (d->out16 == nullptr && d->out32 == nullptr) return -6;
   const int D = d->ndim == 3 ? d->D : 1;
   if (d->B < 1 || d->H < 1 || d->W < 1 || D < 1) return -7;
-  PFN_encodeTiled enc = get_encode_fn();
-  if (enc == nullptr) return -8;
 
-  IgemmParams p;
   memset(&p, 0, sizeof(p));
   // K block: as many input channels as fit one 128/64/32-byte swizzle row
   p.row_bytes = (d->Cin % 64 == 0) ? 128 : ((d->Cin % 32 == 0) ? 64 : 32);
@@ -278,7 +286,35 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   }
   }
   if (p.stages < 2) return -10;
-  const size_t smem = static_cast<size_t>(p.stages) * p.kps * sub + 1024 + 256 + stg_bytes;
+  pl.BN = BN; pl.CL = CL; pl.CG = CG; pl.EG = EG; pl.grid = grid; pl.sub = sub; pl.stg_bytes = stg_bytes; pl.PCh = PCh;
+  pl.KB = KB; pl.D = D;
+  pl.smem = static_cast<size_t>(p.stages) * p.kps * sub + 1024 + 256 + stg_bytes;
+  return 0;
+}
+}  // namespace rn
+
+extern "C" int rn_conv_plan(const rn_conv_desc* d, int* out, int n_out) {
+  rn::IgemmParams p;
+  rn::ConvPlan pl;
+  const int rc = rn::plan_conv(d, p, pl);
+  if (rc != 0) return rc;
+  const int v[16] = {pl.BN, pl.CL, pl.CG, p.ms, pl.EG, p.ny, p.BW, p.BH, p.BD, p.kps, p.stages, static_cast<int>(pl.smem),
+                     pl.grid, p.num_tiles, p.tma_store, p.row_bytes};
+  for (int i = 0; i < n_out && i < 16; ++i) out[i] = v[i];
+  return 0;
+}
+
+extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
+  using namespace rn;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  IgemmParams p;
+  ConvPlan pl;
+  const int prc = plan_conv(d, p, pl);
+  if (prc != 0) return prc;
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) return -8;
+  const int BN = pl.BN, CL = pl.CL, CG = pl.CG, EG = pl.EG, grid = pl.grid, PCh = pl.PCh, KB = pl.KB, D = pl.D;
+  const size_t smem = pl.smem;
 
 
   const CUtensorMapDataType dt = d->fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
