@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
     if (elect_one()) {
       constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
       constexpr int kBRows = BN / CL;               // rows of the B tile this CTA fetches (and multicasts)
-      const int kps = p.kps, kblocks = p.kblocks, ntaps = p.ntaps, stages = p.stages;
+      const int kps = p.kps, kblocks = p.kblocks, stages = p.stages;
       const bool rank5 = (p.rank == 5), banded = (p.b_banded != 0);
       const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(full_bar);
       const uint32_t a_sub = static_cast<uint32_t>(p.a_sub_bytes), sub_u = static_cast<uint32_t>(sub_bytes);
