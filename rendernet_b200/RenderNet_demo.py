@@ -37,7 +37,7 @@ def load_graph(frozen_graph_filename=None, is_greyscale=None):
     if frozen_graph_filename:
         from .tf_import import load_variables
         weights = load_variables(frozen_graph_filename)
-        last = [v for k, v in weights.items() if k.replace("/", "_").endswith("e_conv11_e_conv11_weights")]
+        last = [v for k, v in weights.items() if k.replace("/", "_").endswith("e_conv11_weights")]   # encoder/e_conv11/weights
         if not last:
             raise ValueError(f"{frozen_graph_filename}: no RenderNet variables found (looked for e_conv11/weights)")
         if is_greyscale is None:

@@ -77,6 +77,62 @@ def test_texture_model_matches_reference_golden(golden_dir):
     assert e1 < 1e-3 and e2 < 1e-3
 
 
+def test_shader_greyscale_variant_matches_oracle(golden_dir):
+    """cfg['is_greyscale'] (RenderNet_Shader.py:125-131): e_conv11 has ONE output channel.  Patch-level parity vs the
+    oracle with the reference's initialisers; bar 1e-3 on the sigmoid image."""
+    from rendernet_b200 import tfcompat as tf
+    from rendernet_b200.RenderNet_Shader import RenderNet
+    r = np.load(os.path.join(golden_dir, "resample.npz"))
+    bv = np.load(os.path.join(golden_dir, "binvox.npz"))
+    chair = np.unpackbits(bv["chair_bits"]).reshape(1, 64, 64, 64, 1).astype(np.float32)
+    n = np.ascontiguousarray(orc.transform_voxel_to_match_image(orc.rotation_resampling(chair, r["chair_pose"])))
+    patch = np.ascontiguousarray(n[:, 56:72, 52:68])
+    W = orc.init_shader_weights(seed=11, is_greyscale=True, alpha_range=(0.05, 0.3), bias_jitter=0.02)
+    assert W["encoder/e_conv11/weights"].shape == (4, 4, 1, 16)
+    tf.reset_default_graph()
+    tf.load_weight_dict(W)
+    img = RenderNet(torch.from_numpy(patch).cuda(), is_training=False, is_greyscale=True)
+    assert img.dtype == torch.float32 and tuple(img.shape) == (1, 64, 64, 1)
+    ref = orc.rendernet_shader(patch, W).numpy()
+    err, _ = _rel(img, ref)
+    print("greyscale image max-abs err:", err)
+    assert err < 1e-3
+
+
+def test_demo_render_end_to_end_png(golden_dir, tmp_path):
+    """RenderNet_demo.render (:41-66) through Session.run + NumPy-convention Phong + uint8 + PNG, full size (64^3 -> 512^2),
+    against the oracle's restatement of the same pipeline: the float network output must meet the 1e-3 bar, the file name
+    follows :60-64, the PNG holds exactly the returned array."""
+    from PIL import Image
+    from rendernet_b200 import Phong_shading
+    from rendernet_b200.RenderNet_demo import AMBIENT_IN, K_DIFFUSE, LIGHT_COL, Session, compute_pose_param, load_graph, render
+    bv = np.load(os.path.join(golden_dir, "binvox.npz"))
+    chair = np.unpackbits(bv["chair_bits"]).reshape(1, 64, 64, 64, 1).astype(np.float32)
+    W = orc.init_shader_weights(seed=0, alpha_range=(0.05, 0.3))
+    wfile = tmp_path / "w.npz"
+    np.savez(str(wfile), **W)
+    light = Phong_shading.generate_light_pos(60.0, 250.0)
+    with Session(graph=load_graph(str(wfile))) as sess:
+        out = render(250.0, 60.0, 3.3, sess, chair, light.copy(), str(tmp_path), 0, 250.0, 60.0, "chair")
+        net = sess.run("encoder/output:0", {"real_model_in:0": chair, "view_name:0": compute_pose_param(250.0, 60.0, 3.3),
+                                            "patch_size:0": 128, "is_training:0": False})
+    pngs = [f for f in os.listdir(tmp_path) if f.endswith(".png")]
+    assert pngs == ["000_chair_pose_250.000000_60.000000_3.300000_light_250.000000_60.000000.png"]   # RenderNet_demo.py:60-64
+    assert np.array_equal(np.asarray(Image.open(tmp_path / pngs[0])), out)
+    ref_net = orc.render_forward(chair, orc.compute_pose_param(250.0, 60.0, 3.3), W).numpy()
+    err = float(np.abs(net - ref_net).max())
+    print("demo path network output max-abs err:", err)
+    assert net.shape == (1, 512, 512, 3) and err < 1e-3
+    # Phong + uint8 + PNG plumbing: the oracle's restatement applied to the SAME network output must give the same picture
+    # (the normalisation (img - 0.5)/|img - 0.5| amplifies the 1e-3 network tolerance, so the two halves are checked apart)
+    ref_u8 = orc.to_uint8(orc.np_phong_composite(net.astype(np.float32), orc.generate_light_pos(60.0, 250.0), LIGHT_COL,
+                                                  AMBIENT_IN, K_DIFFUSE))[0]
+    assert out.dtype == np.uint8 and out.shape == (512, 512, 3)
+    diff = np.abs(out.astype(np.int16) - ref_u8.astype(np.int16))
+    print("uint8 image: max level diff", int(diff.max()), "pixels differing", int((diff > 0).sum()))
+    assert int(diff.max()) <= 1
+
+
 def test_engine_pipelined_submit_matches_blocking_render():
     """RenderEngine.submit/result (overlapped H2D / compute / D2H, 2 steps in flight) returns exactly what the
     blocking render() returns, for different inputs in consecutive steps; graph replay == eager."""

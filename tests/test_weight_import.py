@@ -22,8 +22,8 @@ def _variables(seed=0, grey=False):
         "encoder/e_conv1/e_conv1/biases": np.full((8,), 0.001, np.float32),
         "encoder/e_conv1/alpha": rng.uniform(0, 0.3, (8,)).astype(np.float32),
         "encoder/res2_3/con1_3X3/weights": rng.standard_normal((3, 3, 16, 16)).astype(np.float32),
-        "encoder/e_conv11/e_conv11/weights": rng.standard_normal((4, 4, 1 if grey else 3, 16)).astype(np.float32),
-        "encoder/e_conv11/e_conv11/biases": np.zeros((1 if grey else 3,), np.float32),
+        "encoder/e_conv11/weights": rng.standard_normal((4, 4, 1 if grey else 3, 16)).astype(np.float32),
+        "encoder/e_conv11/biases": np.zeros((1 if grey else 3,), np.float32),
     }
 
 
