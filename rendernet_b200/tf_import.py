@@ -10,7 +10,7 @@ Only the protobuf *wire format* is decoded here (varints, length-delimited field
 tensorflow/core/framework/{graph,node_def,attr_value,tensor,tensor_shape}.proto and
 tensorflow/core/protobuf/tensor_bundle.proto.  The `.pb` reader is tested against GraphDefs produced by a real
 protobuf encoder over the TF schema (tensorboard's compiled protos); the checkpoint reader is tested against a writer
-that follows the published table format (tests/test_host_cpu.py) — no TF-written checkpoint exists in this
+that follows the published table format, plain and Snappy-compressed blocks (tests/test_weight_import.py) — no TF-written checkpoint exists in this
 environment to pin it against, so treat it as unpinned until one is tried.
 """
 from __future__ import annotations
@@ -207,15 +207,63 @@ def graph_has_node(path: str, node_name: str) -> bool:
 _TABLE_MAGIC = 0xdb4775248b80fb57
 
 
+def snappy_decompress(src) -> bytes:
+    """Raw Snappy (the block format LevelDB tables may use for their blocks): varint uncompressed length, then literal /
+    copy elements (tag & 3: 0 literal, 1 copy with 11-bit offset, 2 copy with 16-bit offset, 3 copy with 32-bit offset)."""
+    src = bytes(src)
+    n, pos = _varint(src, 0)
+    out = bytearray()
+    while pos < len(src):
+        tag = src[pos]
+        pos += 1
+        kind = tag & 3
+        if kind == 0:
+            ln = tag >> 2
+            if ln >= 60:
+                nb = ln - 59
+                ln = int.from_bytes(src[pos:pos + nb], "little")
+                pos += nb
+            ln += 1
+            if pos + ln > len(src):
+                raise TFImportError("snappy: literal runs past the end of the block")
+            out += src[pos:pos + ln]
+            pos += ln
+            continue
+        if kind == 1:
+            ln = ((tag >> 2) & 7) + 4
+            off = ((tag >> 5) << 8) | src[pos]
+            pos += 1
+        elif kind == 2:
+            ln = (tag >> 2) + 1
+            off = int.from_bytes(src[pos:pos + 2], "little")
+            pos += 2
+        else:
+            ln = (tag >> 2) + 1
+            off = int.from_bytes(src[pos:pos + 4], "little")
+            pos += 4
+        if off == 0 or off > len(out):
+            raise TFImportError("snappy: copy offset outside the data produced so far")
+        for _ in range(ln):                       # byte-wise: copies may overlap their own output
+            out.append(out[-off])
+    if len(out) != n:
+        raise TFImportError(f"snappy: produced {len(out)} bytes, header says {n}")
+    return bytes(out)
+
+
 def _table_block(buf, offset: int, size: int) -> Iterator[Tuple[bytes, bytes]]:
     """One block of the index table (the LevelDB table format TF's tensor bundle uses): prefix-compressed
     entries `shared | non_shared | value_len | key_delta | value`, then the restart array and its length; a
     1-byte compression tag and a 4-byte crc follow the block."""
     if offset + size + 5 > len(buf):
         raise TFImportError("index block runs past the end of the file")
-    if buf[offset + size] != 0:
-        raise TFImportError("compressed index blocks (snappy) are not supported")
-    blk = buf[offset:offset + size]
+    ctype = buf[offset + size]
+    if ctype == 1:                                # kSnappyCompression
+        blk = memoryview(snappy_decompress(buf[offset:offset + size]))
+        size = len(blk)
+    elif ctype == 0:
+        blk = buf[offset:offset + size]
+    else:
+        raise TFImportError(f"index block compression type {ctype} is not supported")
     n_restarts = struct.unpack_from("<I", blk, size - 4)[0]
     end = size - 4 - 4 * n_restarts
     pos, key = 0, b""

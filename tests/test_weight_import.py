@@ -133,7 +133,44 @@ def _block(items, restart_interval=16):
     return bytes(out)
 
 
-def _write_checkpoint(prefix, variables, entries_per_block=4):
+def _snappy(raw: bytes) -> bytes:
+    """A valid (if naive) Snappy stream: runs of a repeated byte become a literal + overlapping copy, the rest literals."""
+    out = bytearray(_vi(len(raw)))
+    i = 0
+    while i < len(raw):
+        j = i
+        while j < len(raw) and raw[j] == raw[i]:
+            j += 1
+        run = j - i
+        if run >= 8:
+            out += bytes([0 << 2 | 0, raw[i]])                    # 1-byte literal
+            left = run - 1
+            while left > 0:
+                ln = min(left, 64)
+                if ln < 4 and ln != left:
+                    ln = left
+                out += bytes([((ln - 1) << 2) | 2, 1, 0])          # copy, 2-byte offset = 1 (overlapping)
+                left -= ln
+            i = j
+            continue
+        k = i
+        while k < len(raw) and k - i < 60:
+            m = k
+            while m < len(raw) and raw[m] == raw[k]:
+                m += 1
+            if m - k >= 8:
+                break
+            k = m if m - k < 8 else k
+            if k == i:
+                k += 1
+        k = max(k, i + 1)
+        k = min(k, i + 60)
+        out += bytes([((k - i - 1) << 2) | 0]) + raw[i:k]
+        i = k
+    return bytes(out)
+
+
+def _write_checkpoint(prefix, variables, entries_per_block=4, snappy=False):
     names = sorted(variables)
     data = bytearray()
     items = [(b"", _pb_field(1, 0, _vi(1)) + _pb_field(3, 2, _vi(2) + _pb_field(1, 0, _vi(1))))]  # header: 1 shard
@@ -153,8 +190,10 @@ def _write_checkpoint(prefix, variables, entries_per_block=4):
     for i in range(0, len(items), entries_per_block):
         chunk = items[i:i + entries_per_block]
         blk = _block(chunk, restart_interval=3)
+        if snappy:
+            blk = _snappy(blk)
         index_items.append((chunk[-1][0] + b"~", _vi(len(table)) + _vi(len(blk))))
-        table += blk + b"\x00" + struct.pack("<I", 0)
+        table += blk + (b"\x01" if snappy else b"\x00") + struct.pack("<I", 0)
     meta = _block([])
     meta_handle = _vi(len(table)) + _vi(len(meta))
     table += meta + b"\x00" + struct.pack("<I", 0)
@@ -187,6 +226,23 @@ def test_checkpoint_reader_roundtrip(tmp_path):
         f.write(b"\x00")
     with pytest.raises(tf_import.TFImportError, match="magic"):
         tf_import.read_checkpoint(prefix)
+
+
+def test_checkpoint_reader_snappy_blocks(tmp_path):
+    """LevelDB tables may Snappy-compress their blocks; the reader carries its own decompressor."""
+    raw = bytes(range(50)) + b"\x00" * 300 + b"abcabcabc" + b"\x07" * 9 + bytes(range(200, 256))
+    assert tf_import.snappy_decompress(_snappy(raw)) == raw
+    assert tf_import.snappy_decompress(bytes([11, (5 - 1) << 2]) + b"hello" + bytes([((6 - 4) << 2) | 1 | (0 << 5), 5])) \
+        == b"hellohelloh"                                       # copy with 11-bit offset, overlapping its own output
+    with pytest.raises(tf_import.TFImportError):
+        tf_import.snappy_decompress(bytes([4, (2 - 1) << 2]) + b"ab" + bytes([((4 - 4) << 2) | 1, 9]))   # offset too far
+    variables = _variables(8)
+    prefix = str(tmp_path / "ckpt")
+    _write_checkpoint(prefix, variables, snappy=True)
+    got = tf_import.read_checkpoint(prefix)
+    assert set(got) == set(variables)
+    for k, v in variables.items():
+        np.testing.assert_array_equal(got[k], v)
 
 
 def test_npz_dir_and_npz_file(tmp_path):
