@@ -8,10 +8,18 @@
  * Conventions
  *   - Every pointer is a DEVICE pointer unless stated otherwise; the caller owns every buffer (the
  *     library never allocates device memory).  `stream` is a cudaStream_t passed as void*; calls are
- *     asynchronous and stream-ordered; no global mutable state besides cached function attributes.
+ *     asynchronous and stream-ordered and may be issued from any thread on any device.  The library has NO mutable
+ *     global state: what it caches is immutable once set (per-device kernel attributes / SM counts, and the launch-
+ *     heuristic defaults, which the environment variable RN_TUNE can override once per process -- a tuning aid);
+ *     per-call overrides go through the 0-means-auto fields of rn_conv_desc.  The only counter is rn_launch_count().
  *   - Tensors are channel-last and dense: 2-D [B,H,W,C], 3-D [B,H,W,D,C] (D innermost spatial axis),
  *     exactly the reference's layouts (tools/layer_util.py:228,147).
- *   - "16-bit" tensors are IEEE fp16 (fmt=0) or bfloat16 (fmt=1); accumulation is always fp32.
+ *   - "16-bit" tensors (`fmt`): RN_FMT_F16 = IEEE fp16, RN_FMT_BF16 = bfloat16, RN_FMT_F16X2 = "exact" mode: a PAIR of
+ *     fp16 planes stored back to back, [2][numel]: plane 0 = hi = fp16(v), plane 1 = lo = fp16(v - hi), together ~22
+ *     significant bits.  In that mode every convolution evaluates x_hi.w_hi + x_lo.w_hi + x_hi.w_lo on the tensor cores
+ *     (3x the MMAs) and matches the reference's fp32 convolutions (tools/layer_util.py:171,212,253) to ~1e-6 relative;
+ *     packed filters, 16-bit activations, residuals and outputs are all such pairs (buffers twice the size).
+ *     Accumulation is always fp32.
  *   - Return value: 0 = ok; <0 = invalid argument (see source for the code); >0 = CUDA / driver error.
  */
 #ifndef RENDERNET_B200_H_
@@ -23,6 +31,10 @@
 extern "C" {
 #endif
 
+#define RN_FMT_F16 0
+#define RN_FMT_BF16 1
+#define RN_FMT_F16X2 2 /* fp16 hi/lo pairs, "exact" mode */
+
 #define RN_ACT_NONE 0
 #define RN_ACT_PRELU 1   /* max(0,x) + alpha[c]*min(0,x)    tools/layer_util.py:27-45 */
 #define RN_ACT_SIGMOID 2 /* tf.nn.sigmoid                   RenderNet_Shader.py:127,130 */
@@ -31,16 +43,6 @@ int rn_version(void);
 const char* rn_error_string(int code);
 /* number of kernels this library has launched in this process (host-side counter) */
 long long rn_launch_count(void);
-/* default cluster size (1, 2, 4) used by descriptors that leave `cluster` at 0; returns the previous value */
-int rn_set_default_cluster(int cluster);
-int rn_set_default_cta_group(int cta_group);
-int rn_set_yhalo(int on);         /* y-halo sharing in rn_conv2d_same (3x3) / rn_conv3d_banded_same; default on */
-int rn_set_epilogue_groups(int groups); /* 1 or 2 epilogue warp groups where a two-group kernel variant exists; default 2 */
-int rn_set_res_prefetch(int on);  /* epilogue fetches 16-bit residual rows one panel ahead; default on */
-int rn_set_default_msub(int msub); /* M sub-tiles per CTA tile when a descriptor says 0: 0 heuristic, 1, 2 */
-int rn_set_tma_store(int on);     /* TMA-store epilogue for dense 16-bit outputs; default on */
-int rn_set_default_kps(int kps); /* k-iterations per smem pipeline stage, 0 = heuristic (tuning aid) */
-
 /* ---- resampler ----------------------------------------------------------------------------------
  * Replaces tf_resampling + tf_interpolate + tf_voxel_meshgrid (tools/resampling_voxel_grid.py:381-614)
  * fused with tf_transform_voxel_to_match_image (tools/model_util.py:41-49).
@@ -79,7 +81,7 @@ typedef struct rn_conv_desc {
   int Cin;                  /* multiple of 16 */
   int Cout;                 /* real output channels */
   int cout_pad;             /* rows of w_packed / entries of bias, alpha; multiple of 16 */
-  int ntaps;                /* <= 28 */
+  int ntaps;                /* <= 48 (<= 16 for RN_FMT_F16X2: every tap expands to 3 operand-split terms) */
   const int8_t* taps;       /* HOST pointer: ntaps x (dx, dy, dz) */
   const void* x;            /* 16-bit [B,H,W,(D),Cin] */
   const void* w_packed;     /* 16-bit [ntaps][cout_pad][Cin] */
@@ -91,7 +93,7 @@ typedef struct rn_conv_desc {
   void* out16;              /* 16-bit output or NULL */
   float* out32;             /* fp32 output or NULL */
   long long o_base, o_b, o_y, o_x, o_z;
-  int fmt;                  /* 0 fp16, 1 bf16 */
+  int fmt;                  /* RN_FMT_* */
   int force_bn, force_kps, max_ctas; /* 0 = auto (tuning / tests) */
   /* depth-folded ("banded") conv3d: x is [B,H,W,x_channels] with x_channels = D*C, Cin = K elements read per
    * tap starting at channel a_c_base + n_tile*a_c_ntile (may run out of range: zero filled), and w_packed is one
@@ -107,6 +109,12 @@ typedef struct rn_conv_desc {
   /* column split of the output address: n -> (n / o_nsplit) * o_nhi + (n % o_nsplit); 0 = off (multiple of 32) */
   int o_nsplit;
   long long o_nhi;
+  /* fmt == RN_FMT_F16X2: element offsets of the LO plane of x, of w_packed and of out16 / a 16-bit residual (multiples
+   * of 8).  The reference-shaped wrappers below derive them from the tensor shapes ([2][numel] pairs). */
+  long long x_plane, w_plane, o_plane;
+  /* per-call overrides of the launch heuristics, 0 = library default: epilogue warp groups (1 or 2); residual register
+   * prefetch / TMA-store epilogue (1 = on, -1 = off) */
+  int epi_groups, res_prefetch, tma_store;
 } rn_conv_desc;
 int rn_conv_igemm(const rn_conv_desc* d, void* stream);
 /* The launch plan rn_conv_igemm would use for `d`, without touching the device (works on a host without a GPU; the SM

@@ -48,8 +48,11 @@ def load_graph(frozen_graph_filename=None, is_greyscale=None):
 class Session:
     """`tf.Session(graph=graph)` look-alike for the demo's single fetch."""
 
-    def __init__(self, graph: Graph = None):
+    def __init__(self, graph: Graph = None, precision: str = "exact"):
+        """precision: "exact" (default here: matches the reference's fp32 graph to ~1e-5 on the image whatever the
+        weights) or "fast" (fp16 operands, 3x the throughput; see engine.py)."""
         self.graph = graph or Graph(None)
+        self.precision = precision
         self._engines = {}
 
     def __enter__(self):
@@ -70,7 +73,7 @@ class Session:
         eng = self._engines.get(B)
         if eng is None:
             from .engine import RenderEngine
-            eng = RenderEngine(self.graph.weights, B, is_greyscale=self.graph.is_greyscale)
+            eng = RenderEngine(self.graph.weights, B, is_greyscale=self.graph.is_greyscale, precision=self.precision)
             self._engines[B] = eng
         return eng.render(voxel, param).numpy().copy()
 

@@ -26,6 +26,8 @@ class rn_conv_desc(C.Structure):
         ("x_channels", C.c_int), ("a_c_base", C.c_int), ("a_c_ntile", C.c_int), ("w_banded", C.c_int),
         ("cluster", C.c_int), ("cta_group", C.c_int), ("ny", C.c_int), ("tile_w", C.c_int), ("msub", C.c_int),
         ("o_nsplit", C.c_int), ("o_nhi", C.c_longlong),
+        ("x_plane", C.c_longlong), ("w_plane", C.c_longlong), ("o_plane", C.c_longlong),
+        ("epi_groups", C.c_int), ("res_prefetch", C.c_int), ("tma_store", C.c_int),
     ]
 
 
@@ -38,14 +40,6 @@ SIGNATURES = {
     "rn_version": (_i, []),
     "rn_error_string": (C.c_char_p, [_i]),
     "rn_launch_count": (_ll, []),
-    "rn_set_default_cluster": (_i, [_i]),
-    "rn_set_default_cta_group": (_i, [_i]),
-    "rn_set_default_kps": (_i, [_i]),
-    "rn_set_yhalo": (_i, [_i]),
-    "rn_set_tma_store": (_i, [_i]),
-    "rn_set_default_msub": (_i, [_i]),
-    "rn_set_res_prefetch": (_i, [_i]),
-    "rn_set_epilogue_groups": (_i, [_i]),
     "rn_resample_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rn_pack_conv_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "rn_cast_f32_to_16": (_i, [_vp, _vp, _ll, _ll, _i, _vp]),

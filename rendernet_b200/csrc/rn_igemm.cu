@@ -20,6 +20,7 @@
 // in rn_igemm_kernel.cuh and is instantiated in rn_igemm_inst_*.cu.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -28,14 +29,32 @@
 
 namespace rn {
 
-// one entry point per instantiation unit (rn_igemm_inst_*.cu)
-cudaError_t launch_bn256(int CL, int CG, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);
-cudaError_t launch_bn128(int CL, int CG, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);
-cudaError_t launch_bn128_ms2(int CL, int CG, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);
-cudaError_t launch_small(int BN, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);
-cudaError_t launch_small_eg2(int BN, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);   // <BN,1,1,2,2>
-cudaError_t launch_eg2_256(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);              // <256,2,2,1,2>
-cudaError_t launch_eg2_128(int CG, const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);      // <128,2,CG,ms,2>
+// launch_ms<BN, CL, CG, MS, EG, SPLIT> is defined in rn_igemm_kernel.cuh and explicitly instantiated once per variant
+// (rn_igemm_inst.cu x the Makefile's VARIANTS list); this table must list exactly those variants.
+template <int BN, int CL, int CG, int MS, int EG, bool SPLIT>
+cudaError_t launch_ms(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream);
+
+static cudaError_t launch_variant(int BN, int CL, int CG, int MS, int EG, int SP, const IgemmParams& p, int grid, size_t smem,
+                                  cudaStream_t stream) {
+#define RN_V(bn, cl, cg, ms, eg, sp) \
+  if (BN == bn && CL == cl && CG == cg && MS == ms && EG == eg && SP == sp) return launch_ms<bn, cl, cg, ms, eg, (sp != 0)>(p, grid, smem, stream);
+  // one epilogue warp group
+  RN_V(256, 2, 2, 1, 1, 0) RN_V(256, 4, 1, 1, 1, 0) RN_V(256, 2, 1, 1, 1, 0) RN_V(256, 1, 1, 1, 1, 0)
+  RN_V(128, 2, 2, 1, 1, 0) RN_V(128, 4, 1, 1, 1, 0) RN_V(128, 2, 1, 1, 1, 0) RN_V(128, 1, 1, 1, 1, 0)
+  RN_V(128, 2, 2, 2, 1, 0) RN_V(128, 4, 1, 2, 1, 0) RN_V(128, 2, 1, 2, 1, 0) RN_V(128, 1, 1, 2, 1, 0)
+  RN_V(64, 1, 1, 1, 1, 0) RN_V(64, 1, 1, 2, 1, 0) RN_V(32, 1, 1, 1, 1, 0) RN_V(32, 1, 1, 2, 1, 0)
+  RN_V(16, 1, 1, 1, 1, 0) RN_V(16, 1, 1, 2, 1, 0)
+  // two epilogue warp groups
+  RN_V(256, 2, 2, 1, 2, 0) RN_V(128, 2, 2, 1, 2, 0) RN_V(128, 2, 2, 2, 2, 0) RN_V(128, 2, 1, 1, 2, 0) RN_V(128, 2, 1, 2, 2, 0)
+  RN_V(64, 1, 1, 2, 2, 0) RN_V(32, 1, 1, 2, 2, 0) RN_V(16, 1, 1, 2, 2, 0)
+  // operand-split "exact" mode (fmt 2): CTA pairs or single CTAs, always two epilogue groups
+  RN_V(256, 2, 2, 1, 2, 1) RN_V(256, 1, 1, 1, 2, 1)
+  RN_V(128, 2, 2, 1, 2, 1) RN_V(128, 2, 2, 2, 2, 1) RN_V(128, 1, 1, 1, 2, 1) RN_V(128, 1, 1, 2, 2, 1)
+  RN_V(64, 1, 1, 1, 2, 1) RN_V(64, 1, 1, 2, 2, 1) RN_V(32, 1, 1, 1, 2, 1) RN_V(32, 1, 1, 2, 2, 1)
+  RN_V(16, 1, 1, 1, 2, 1) RN_V(16, 1, 1, 2, 2, 1)
+#undef RN_V
+  return cudaErrorInvalidDeviceFunction;   // plan_conv chose a variant that is not built
+}
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -59,73 +78,59 @@ static CUtensorMapSwizzle swizzle_of(int row_bytes) {
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-int g_epi_groups = 2;                        // epilogue warp groups where a two-group kernel variant exists (1 = always one)
-int g_res_prefetch = 1;                      // fetch 16-bit residual rows one panel ahead in the epilogue (A/B switch)
-int g_default_msub = 0;                      // M sub-tiles per CTA tile when the descriptor says 0: 0 = heuristic, 1, 2
-int g_tma_store = 1;                         // TMA-store epilogue where the output is a dense 16-bit NHWC tensor
-int g_default_kps = 0;                       // k-iterations per pipeline stage override (0 = heuristic)
-int g_default_cta_group = 2;                 // 2: paired tcgen05.mma.cta_group::2 tiles where the shape allows
-int g_default_cluster = 2;                   // B-multicast cluster size used when the descriptor says 0 (auto)
 std::atomic<long long> g_launch_count{0};   // kernels launched by this library (bench.py's gpu_launches)
-static int g_num_sms = 0;
+
+// Library defaults of the launch heuristics.  They can be overridden ONCE per process through the environment variable
+// RN_TUNE ("epi=1,msub=1,kps=4,cluster=4,cta_group=1,res_prefetch=0,tma_store=0,yhalo=0"; read at first use, immutable
+// afterwards -- a tuning / A-B aid, see scripts/ab_step.py) and per call through the 0-means-auto fields of rn_conv_desc.
+// There is no mutable global state.
+static Tuning parse_tuning() {
+  Tuning t;
+  const char* e = getenv("RN_TUNE");
+  if (e == nullptr) return t;
+  auto get = [&](const char* key, int* dst, int lo, int hi) {
+    const char* q = strstr(e, key);
+    if (q == nullptr || q[strlen(key)] != '=') return;
+    const int v = atoi(q + strlen(key) + 1);
+    if (v >= lo && v <= hi) *dst = v;
+  };
+  get("cluster", &t.cluster, 1, 4);
+  get("cta_group", &t.cta_group, 1, 2);
+  get("kps", &t.kps, 0, 16);
+  get("msub", &t.msub, 0, 2);
+  get("epi", &t.epi_groups, 1, 2);
+  get("res_prefetch", &t.res_prefetch, 0, 1);
+  get("tma_store", &t.tma_store, 0, 1);
+  get("yhalo", &t.yhalo, 0, 1);
+  return t;
+}
+const Tuning& tuning() {
+  static const Tuning t = parse_tuning();
+  return t;
+}
+
+// SM count of the CURRENT device (cached per device ordinal); 148 when no device is visible (rn_conv_plan on a CPU host)
 static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) {
-      cudaGetLastError();
-      g_num_sms = 0;
-      return 148;       // no device visible (rn_conv_plan on a CPU-only host): plan for a B200
-    }
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    cudaGetLastError();
+    return 148;
   }
-  return g_num_sms;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      return 148;
+    }
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
 }
 
 }  // namespace rn
 
 #include "../../include/rendernet_b200.h"
-
-extern "C" int rn_set_default_cluster(int c) {
-  const int prev = rn::g_default_cluster;
-  if (c == 1 || c == 2 || c == 4) rn::g_default_cluster = c;
-  return prev;
-}
-
-extern "C" int rn_set_epilogue_groups(int g) {
-  const int prev = rn::g_epi_groups;
-  if (g == 1 || g == 2) rn::g_epi_groups = g;
-  return prev;
-}
-
-extern "C" int rn_set_res_prefetch(int on) {
-  const int prev = rn::g_res_prefetch;
-  rn::g_res_prefetch = on ? 1 : 0;
-  return prev;
-}
-
-extern "C" int rn_set_default_msub(int m) {
-  const int prev = rn::g_default_msub;
-  if (m >= 0 && m <= 2) rn::g_default_msub = m;
-  return prev;
-}
-
-extern "C" int rn_set_tma_store(int on) {
-  const int prev = rn::g_tma_store;
-  rn::g_tma_store = on ? 1 : 0;
-  return prev;
-}
-
-extern "C" int rn_set_default_kps(int k) {
-  const int prev = rn::g_default_kps;
-  if (k >= 0 && k <= 16) rn::g_default_kps = k;
-  return prev;
-}
-
-extern "C" int rn_set_default_cta_group(int g) {
-  const int prev = rn::g_default_cta_group;
-  if (g == 1 || g == 2) rn::g_default_cta_group = g;
-  return prev;
-}
 
 extern "C" long long rn_launch_count(void) { return rn::g_launch_count.load(std::memory_order_relaxed); }
 
@@ -141,13 +146,19 @@ struct ConvPlan {
 static int plan_conv(const rn_conv_desc* d, IgemmParams& p, ConvPlan& pl) {
   if (d == nullptr || d->x == nullptr || d->w_packed == nullptr || d->bias == nullptr) return -1;
   if (d->ndim != 2 && d->ndim != 3) return -2;
-  if (d->ntaps < 1 || d->ntaps > kMaxTaps) return -3;
+  if (d->ntaps < 1 || d->ntaps * (d->fmt == 2 ? 3 : 1) > kMaxTaps) return -3;
+  if (d->fmt < 0 || d->fmt > 2) return -17;
+  if (d->fmt == 2 && (d->x_plane <= 0 || d->w_plane <= 0 || (d->out16 != nullptr && d->o_plane <= 0) ||
+                      d->x_plane % 8 != 0 || d->w_plane % 8 != 0 || d->o_plane % 8 != 0))
+    return -18;   // fp16 hi/lo pairs: the LO plane of every 16-bit tensor must be given (16-byte aligned offsets)
   if (d->Cin % 16 != 0 || d->cout_pad % 16 != 0 || d->Cout > d->cout_pad || d->Cout < 1) return -4;
   if (d->act == ACT_PRELU && d->alpha == nullptr) return -5;
   if (d->out16 == nullptr && d->out32 == nullptr) return -6;
   const int D = d->ndim == 3 ? d->D : 1;
   if (d->B < 1 || d->H < 1 || d->W < 1 || D < 1) return -7;
 
+  const Tuning& tn = tuning();
+  const bool split = d->fmt == 2;
   memset(&p, 0, sizeof(p));
   // K block: as many input channels as fit one 128/64/32-byte swizzle row
   p.row_bytes = (d->Cin % 64 == 0) ? 128 : ((d->Cin % 32 == 0) ? 64 : 32);
@@ -180,33 +191,56 @@ static int plan_conv(const rn_conv_desc* d, IgemmParams& p, ConvPlan& pl) {
   // variant cannot keep >= 3 stages in flight (tiny images -> no CTA pairing -> 3 full-width B tiles per group),
   // fall back to one A load per tap.
   auto pow2_le = [](int v, int cap) { int r = 1; while (r * 2 <= cap && r < v) r *= 2; return r; };
-  for (int t = 0; t < d->ntaps; ++t) {
-    p.tap[t][0] = d->taps[3 * t + 0];
-    p.tap[t][1] = d->taps[3 * t + 1];
-    p.tap[t][2] = d->taps[3 * t + 2];
+  if (!split) {
+    for (int t = 0; t < d->ntaps; ++t) {
+      p.tap[t][0] = d->taps[3 * t + 0];
+      p.tap[t][1] = d->taps[3 * t + 1];
+      p.tap[t][2] = d->taps[3 * t + 2];
+      p.tap[t][3] = 0;
+      p.tap_b[t] = static_cast<uint8_t>(t);
+    }
+  } else {
+    // Split ("exact") mode: tap t = ky*nx0 + kx0 becomes the three pseudo-taps ky*(3*nx0) + 3*kx0 + {0,1,2} =
+    // (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo) with the same input offset; the ky-major order that y-halo sharing needs
+    // is preserved, so the three terms of a filter column still share one activation load each.
+    const int nx0 = d->ntaps / p.ny;
+    for (int t = 0; t < d->ntaps; ++t) {
+      const int ky = t / nx0, kx0 = t % nx0;
+      for (int j = 0; j < 3; ++j) {
+        const int q = ky * (3 * nx0) + 3 * kx0 + j;
+        p.tap[q][0] = d->taps[3 * t + 0];
+        p.tap[q][1] = d->taps[3 * t + 1];
+        p.tap[q][2] = d->taps[3 * t + 2];
+        p.tap[q][3] = static_cast<int8_t>(j == 1 ? 1 : (j == 2 ? 2 : 0));
+        p.tap_b[q] = static_cast<uint8_t>(t);
+      }
+    }
+    p.ntaps = 3 * d->ntaps;
+    p.split = 1;
   }
-  p.ab_fmt = d->fmt;
+  p.ab_fmt = d->fmt == 1 ? 1 : 0;
   p.rank = d->ndim == 3 ? 5 : 4;
   p.W = d->W; p.H = d->H; p.D = D; p.B = d->B;
   // TMA-store epilogue: dense 16-bit NHWC output only (no fp32 copy, no ragged / split columns)
   const int PCh = BN >= 64 ? 64 : BN;
   const bool dense_out = d->ndim == 2 && d->o_nsplit == 0 && d->o_base == 0 && d->o_z == 0 && d->o_x == d->cout_pad &&
                          d->o_y == static_cast<long long>(d->W) * d->o_x && d->o_b == static_cast<long long>(d->H) * d->o_y;
-  p.tma_store = (g_tma_store && d->out16 != nullptr && d->out32 == nullptr && d->Cout == d->cout_pad && dense_out &&
+  const bool use_tma_store = !split && (d->tma_store > 0 || (d->tma_store == 0 && tn.tma_store));
+  p.tma_store = (use_tma_store && d->out16 != nullptr && d->out32 == nullptr && d->Cout == d->cout_pad && dense_out &&
                  (reinterpret_cast<uintptr_t>(d->out16) & 15) == 0) ? 1 : 0;
   // merged stride-2 transposed conv (rn_conv2d_transpose_s2_merged): output [B, H, 2(ay), W, 2*Cout(ax,co)]
   const bool scatter_out = d->ndim == 2 && d->o_nsplit > 0 && d->o_nsplit % PCh == 0 && d->o_base == 0 && d->o_z == 0 &&
                            d->o_x == d->o_nsplit && d->o_nhi == static_cast<long long>(d->W) * d->o_x &&
                            d->o_y == 2 * d->o_nhi && d->o_b == static_cast<long long>(d->H) * d->o_y &&
                            d->cout_pad == 2 * d->o_nsplit;
-  if (g_tma_store && scatter_out && d->out16 != nullptr && d->out32 == nullptr && d->Cout == d->cout_pad &&
+  if (use_tma_store && scatter_out && d->out16 != nullptr && d->out32 == nullptr && d->Cout == d->cout_pad &&
       (reinterpret_cast<uintptr_t>(d->out16) & 15) == 0)
     p.tma_store = 2;
   int grid = 0, CL = 1, CG = 1, sub = 0, EG = 1, stg_bytes = 0;
   // M sub-tiles: two 128-row accumulators per CTA share every weight stage (BN <= 128 so that 2 x 2 x BN TMEM columns
   // fit).  Halves the weight bytes per MAC; measured on every BN <= 128 layer of the network (banded 3^3 convs
   // 0.28 -> 0.22 ms, e_conv10 0.43 -> 0.26, e_conv7_1 0.25 -> 0.17: profiles/r01_probe_msub.log), never slower.
-  int want_ms = d->msub > 0 ? d->msub : (g_default_msub > 0 ? g_default_msub : 2);
+  int want_ms = d->msub > 0 ? d->msub : (tn.msub > 0 ? tn.msub : 2);
   if (want_ms > 2) return -16;
   if (BN > 128 || d->ndim != 2) want_ms = 1;
   // Epilogue warp groups: a second group of four epilogue warps (own staging buffer) where the kernel variant exists and
@@ -214,7 +248,8 @@ static int plan_conv(const rn_conv_desc* d, IgemmParams& p, ConvPlan& pl) {
   const int ny_req = p.ny, ms_req = want_ms;
   IgemmParams p_one;                         // sizing with one epilogue group (always valid), kept as the fall-back
   int grid_one = 0, CL_one = 1, CG_one = 1, sub_one = 0, stg_one = 0;
-  for (int eg = 1; eg <= (g_epi_groups == 2 ? 2 : 1); ++eg) {
+  const int epi_max = d->epi_groups > 0 ? d->epi_groups : tn.epi_groups;
+  for (int eg = split ? 2 : 1; eg <= ((epi_max == 2 || split) ? 2 : 1); ++eg) {   // split kernels exist with two groups only
   EG = eg;
   p.ny = ny_req;
   want_ms = ms_req;
@@ -246,9 +281,10 @@ static int plan_conv(const rn_conv_desc* d, IgemmParams& p, ConvPlan& pl) {
     const int m_tiles = p.num_tiles / p.n_tiles;
     CL = 1; CG = 1;
     if (BN >= 128) {
-      const int want = d->cluster > 0 ? d->cluster : g_default_cluster;
-      const int want_cg = d->cta_group > 0 ? d->cta_group : g_default_cta_group;
+      const int want = d->cluster > 0 ? d->cluster : tn.cluster;
+      const int want_cg = d->cta_group > 0 ? d->cta_group : tn.cta_group;
       if (want_cg == 2 && m_tiles % 2 == 0 && grid >= 2) { CL = 2; CG = 2; }
+      else if (split) CL = 1;                     // split variants: CTA pairs or single CTAs
       else if (want >= 4 && m_tiles % 4 == 0 && grid >= 4) CL = 4;
       else if (want >= 2 && m_tiles % 2 == 0 && grid >= 2) CL = 2;
     }
@@ -263,7 +299,7 @@ static int plan_conv(const rn_conv_desc* d, IgemmParams& p, ConvPlan& pl) {
     if (p.kps > 8) p.kps = 8;
     if (p.kps > total_k) p.kps = total_k;
     if (d->force_kps > 0) p.kps = d->force_kps;
-    else if (g_default_kps > 0) p.kps = g_default_kps < total_k ? g_default_kps : total_k;
+    else if (tn.kps > 0) p.kps = tn.kps < total_k ? tn.kps : total_k;
     p.stages = budget / (p.kps * sub);
     if (p.stages > 12) p.stages = 12;
     while (p.stages < 3 && p.kps > 1) {   // keep at least 3 stages in flight
@@ -276,7 +312,7 @@ static int plan_conv(const rn_conv_desc* d, IgemmParams& p, ConvPlan& pl) {
   }
   if (eg == 1) {
     p_one = p; grid_one = grid; CL_one = CL; CG_one = CG; sub_one = sub; stg_one = stg_bytes;
-  } else {
+  } else if (!split) {
     const bool have_variant = (BN == 256 && CG == 2) || (BN == 128 && (CG == 2 || (CG == 1 && CL == 2))) ||
                               (BN < 128 && p.ms == 2);
     const bool same_shape = p.ms == p_one.ms && p.ny == p_one.ny && CL == CL_one && CG == CG_one;
@@ -317,7 +353,10 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   const size_t smem = pl.smem;
 
 
-  const CUtensorMapDataType dt = d->fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = d->fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const bool split = d->fmt == 2;
+  const uint16_t* x_lo = split ? static_cast<const uint16_t*>(d->x) + d->x_plane : nullptr;
+  const uint16_t* w_lo = split ? static_cast<const uint16_t*>(d->w_packed) + d->w_plane : nullptr;
   const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r;
   const cuuint64_t Cx = d->x_channels > 0 ? d->x_channels : d->Cin;  // channel extent of x (>= K per tap)
@@ -330,12 +369,18 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
     const cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)p.BW, (cuuint32_t)(p.BH * p.ms + p.ny - 1), 1};
     r = enc(&p.tmA, dt, 4, const_cast<void*>(d->x), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && split)
+      r = enc(&p.tmA2, dt, 4, const_cast<uint16_t*>(x_lo), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     const cuuint64_t dims[5] = {Cx, (cuuint64_t)D, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     const cuuint64_t strides[4] = {Cx * 2, Cx * 2 * D, Cx * 2 * D * d->W, Cx * 2 * D * d->W * d->H};
     const cuuint32_t box[5] = {(cuuint32_t)KB, (cuuint32_t)p.BD, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
     r = enc(&p.tmA, dt, 5, const_cast<void*>(d->x), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && split)
+      r = enc(&p.tmA2, dt, 5, const_cast<uint16_t*>(x_lo), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) return 1000 + static_cast<int>(r);
   if (d->w_banded) {  // [ntaps*kblocks][BN][KB], identical for every N tile
@@ -344,12 +389,18 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
     const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)(BN / CL), 1};  // CL == 2 also for the paired MMA
     r = enc(&p.tmB, dt, 3, const_cast<void*>(d->w_packed), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && split)
+      r = enc(&p.tmB2, dt, 3, const_cast<uint16_t*>(w_lo), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     const cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->cout_pad, (cuuint64_t)d->ntaps};
     const cuuint64_t strides[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * d->cout_pad};
     const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)(BN / CL), 1};  // CL == 2 also for the paired MMA
     r = enc(&p.tmB, dt, 3, const_cast<void*>(d->w_packed), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && split)
+      r = enc(&p.tmB2, dt, 3, const_cast<uint16_t*>(w_lo), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) return 2000 + static_cast<int>(r);
 
@@ -372,7 +423,8 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   }
   // residual L2 prefetch: 16-bit residual laid out exactly like the dense 16-bit output (same map, other base pointer)
   p.res_l2_prefetch = 0;
-  if (g_res_prefetch && p.tma_store == 1 && d->residual != nullptr && !d->residual_is_f32 &&
+  const bool res_pre = d->res_prefetch > 0 || (d->res_prefetch == 0 && tuning().res_prefetch);
+  if (res_pre && p.tma_store == 1 && d->residual != nullptr && !d->residual_is_f32 &&
       (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) {
     const cuuint64_t Ct = static_cast<cuuint64_t>(d->cout_pad);
     const cuuint64_t dims[4] = {Ct, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
@@ -387,19 +439,14 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   p.bias = d->bias; p.alpha = d->alpha; p.act = d->act; p.n_valid = d->Cout;
   p.o_base = d->o_base; p.o_b = d->o_b; p.o_y = d->o_y; p.o_x = d->o_x; p.o_z = d->o_z;
   p.o_nsplit = d->o_nsplit; p.o_nhi = d->o_nhi;
-  p.res_prefetch = g_res_prefetch;
+  p.res_prefetch = res_pre ? 1 : 0;
+  p.o_plane = d->o_plane;
   if (d->o_nsplit > 0 && (d->o_nsplit % 32 != 0 || d->o_nhi % 8 != 0)) return -15;
   const bool strides8 = (d->o_base % 8 == 0) && (d->o_b % 8 == 0) && (d->o_y % 8 == 0) && (d->o_x % 8 == 0) &&
                         (d->o_z % 8 == 0);
   auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_ok = strides8 && al16(d->out16) && al16(d->out32) && al16(d->residual) ? 1 : 0;
 
-  cudaError_t e;
-  if (EG == 2 && BN == 256) e = launch_eg2_256(p, grid, smem, stream);
-  else if (EG == 2 && BN == 128) e = launch_eg2_128(CG, p, grid, smem, stream);
-  else if (EG == 2) e = launch_small_eg2(BN, p, grid, smem, stream);
-  else if (BN == 256) e = launch_bn256(CL, CG, p, grid, smem, stream);
-  else if (BN == 128) e = (p.ms == 2) ? launch_bn128_ms2(CL, CG, p, grid, smem, stream) : launch_bn128(CL, CG, p, grid, smem, stream);
-  else e = launch_small(BN, p, grid, smem, stream);
+  const cudaError_t e = launch_variant(BN, CL, CG, p.ms, EG, p.split, p, grid, smem, stream);
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }

@@ -5,7 +5,7 @@
 
 namespace rn {
 
-constexpr int kMaxTaps = 28;
+constexpr int kMaxTaps = 48;   // 16 filter taps x 3 operand-split terms (fmt 2)
 constexpr int kTileM = 128;  // rows (pixels / voxels) per CTA tile == TMEM lanes
 
 enum Act : int { ACT_NONE = 0, ACT_PRELU = 1, ACT_SIGMOID = 2 };
@@ -15,6 +15,8 @@ struct alignas(64) IgemmParams {
   CUtensorMap tmB;  // weights [tap][CoutPad][Cin]: rank 3 {Cin,CoutPad,taps}; box {KB,BN,1}
   CUtensorMap tmR;  // 16-bit residual, same geometry and box as tmO (dense output): L2 prefetch of the next tile's rows
   CUtensorMap tmO;  // 16-bit output {Cout,W,H,B}; box {panel cols (<=64), BW, BH, 1}: TMA-store epilogue (tma_store != 0)
+  CUtensorMap tmA2; // split mode (fmt 2): the LO plane of the activations, same geometry as tmA
+  CUtensorMap tmB2; // split mode: the LO plane of the packed weights, same geometry as tmB
   int rank;
   int W, H, D, B;                 // extents of the output (== input) pixel space; D = 1 for rank 4
   int BW, BH, BD;                 // M (sub-)tile box, BW*BH*BD == 128
@@ -33,7 +35,15 @@ struct alignas(64) IgemmParams {
                                   // every weight (B) stage is used for ms accumulators, halving B traffic per MAC (BN <= 128)
   int ny;                         // y-halo sharing: taps are ordered tap = ky*nx + kx with dy consecutive; the ny taps of a
                                   // column share ONE A load of BH+ny-1 image rows (operand ky starts ky*BW rows into it)
-  int8_t tap[kMaxTaps][4];        // (dx, dy, dz, _) input offset of each filter tap
+  int8_t tap[kMaxTaps][4];        // (dx, dy, dz, sel) input offset of each filter tap; sel bit 0: A operand comes from the
+                                  // LO plane (tmA2), bit 1: B operand comes from the LO plane (tmB2) -- split mode only
+  uint8_t tap_b[kMaxTaps];        // tap coordinate of pseudo-tap t in the packed filter (== t unless split)
+  // Split mode (fmt 2, "exact"): every 16-bit tensor is a PAIR of fp16 planes, hi = fp16(v), lo = fp16(v - hi), ~22
+  // mantissa bits together.  Each filter tap becomes three pseudo-taps accumulated into the same TMEM tile:
+  // x_hi.w_hi + x_lo.w_hi + x_hi.w_lo (the lo.lo term is below fp32 resolution); the epilogue reads a hi+lo residual and
+  // writes hi and lo planes.  The reference computes these convolutions in fp32 (tools/layer_util.py:171,212,253).
+  int split;
+  long long o_plane;              // element offset of the LO plane of out16 / of a 16-bit residual
   // fused epilogue: v = acc + bias; v = act(v); v += residual; store
   void* out16;                    // 16-bit output or nullptr
   float* out32;                   // fp32 output or nullptr
@@ -51,5 +61,18 @@ struct alignas(64) IgemmParams {
   int o_nsplit;                   // > 0: column n lands at (n / o_nsplit) * o_nhi + (n % o_nsplit) instead of n (merged
   long long o_nhi;                //      phases of a stride-2 transposed conv: n = (ay, ax, co))
 };
+
+// launch-heuristic defaults (immutable after first use; RN_TUNE environment override -- rn_igemm.cu)
+struct Tuning {
+  int cluster = 2;        // B-multicast cluster size when the descriptor says 0
+  int cta_group = 2;      // 2: paired tcgen05.mma.cta_group::2 tiles where the shape allows
+  int kps = 0;            // k-groups per pipeline stage (0 = heuristic)
+  int msub = 0;           // M sub-tiles per CTA tile (0 = heuristic)
+  int epi_groups = 2;     // epilogue warp groups where a two-group kernel variant exists
+  int res_prefetch = 1;   // fetch 16-bit residual rows one panel ahead in the epilogue
+  int tma_store = 1;      // TMA-store epilogue where the output is a dense 16-bit NHWC tensor
+  int yhalo = 1;          // y-halo sharing of the activation operand (3x3, banded 3^3, merged / x-folded transposed)
+};
+const Tuning& tuning();
 
 }  // namespace rn

@@ -16,9 +16,10 @@
 //   * Persistent: grid = #SMs, static round-robin tile schedule with N fastest so concurrently running
 //     CTAs share the same activation rows in L2.
 //
-// This header holds the device code and the per-variant launcher template.  It is included by the instantiation units
-// rn_igemm_inst_*.cu (one per group of <BN, CL, CG, MS> variants, so that `make -j` compiles them in parallel) --
-// rn_igemm.cu (host side: validation, tile/pipeline sizing, tensor maps) only sees `launch_variant`.
+// This header holds the device code and the per-variant launcher template `launch_ms`.  It is included only by
+// rn_igemm_inst.cu, which the Makefile compiles once per <BN, CL, CG, MS, EG, SPLIT> variant (one object each, so that
+// `make -j` spreads them over the cores); rn_igemm.cu (host side: validation, tile/pipeline sizing, tensor maps) declares
+// the template and dispatches to the instantiated variants.
 #pragma once
 #include <atomic>
 #include <type_traits>
@@ -34,6 +35,7 @@ namespace rn {
 extern std::atomic<long long> g_launch_count;   // kernels launched by this library (bench.py's gpu_launches)
 
 constexpr int kNumThreads = 192;
+constexpr int kMaxDevices = 64;   // device ordinals with cached per-device state
 
 struct TileCoord {
   int b, x0, y0, z0, n0;
@@ -59,7 +61,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile,
 
 // stg != 0: the 16-bit result goes to the shared-memory staging panel (row `m`, 16-byte chunk index `chunk0`..) in the
 // TMA swizzle of a `prow`-byte row instead of to global memory (the residual is still read from global).
-template <int CW>
+template <int CW, bool SPLIT = false>
 __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint32_t* __restrict__ r, int n0,
                                                long long off, bool row_valid, uint32_t stg = 0, int m = 0,
                                                int chunk0 = 0, int prow = 128, const uint4* rpre = nullptr) {
@@ -102,13 +104,25 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
         for (int i = 0; i < CW / 8; ++i) {
           const uint4 q = rpre != nullptr ? rpre[i] : __ldg(rp + i);   // rpre: fetched a panel ahead by the caller
           const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+          if constexpr (SPLIT) {      // residual = hi + lo (exact in fp32: <= 22 significant bits)
+            const uint4 ql = __ldg(rp + i + (p.o_plane >> 3));
+            const uint32_t wl[4] = {ql.x, ql.y, ql.z, ql.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float2 f;
-            if (p.ab_fmt == 0) f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-            else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-            v[8 * i + 2 * j] += f.x;
-            v[8 * i + 2 * j + 1] += f.y;
+            for (int j = 0; j < 4; ++j) {
+              const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+              const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&wl[j]));
+              v[8 * i + 2 * j] += fh.x + fl.x;
+              v[8 * i + 2 * j + 1] += fh.y + fl.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f;
+              if (p.ab_fmt == 0) f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+              else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+              v[8 * i + 2 * j] += f.x;
+              v[8 * i + 2 * j + 1] += f.y;
+            }
           }
         }
       }
@@ -119,18 +133,32 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
 #pragma unroll
       for (int i = 0; i < CW / 8; ++i) {
         uint32_t w[4];
+        if constexpr (SPLIT) {        // hi = fp16(v), lo = fp16(v - hi): two planes, direct stores (tma_store is off in split mode)
+          uint32_t wl[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (p.ab_fmt == 0) {
-            __half2 h = __floats2half2_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
-            w[j] = *reinterpret_cast<uint32_t*>(&h);
-          } else {
-            __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
-            w[j] = *reinterpret_cast<uint32_t*>(&h);
+          for (int j = 0; j < 4; ++j) {
+            const __half2 h = __floats2half2_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(v[8 * i + 2 * j] - hf.x, v[8 * i + 2 * j + 1] - hf.y);
+            w[j] = *reinterpret_cast<const uint32_t*>(&h);
+            wl[j] = *reinterpret_cast<const uint32_t*>(&l);
           }
+          op[i] = make_uint4(w[0], w[1], w[2], w[3]);
+          op[i + (p.o_plane >> 3)] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (p.ab_fmt == 0) {
+              __half2 h = __floats2half2_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+              w[j] = *reinterpret_cast<uint32_t*>(&h);
+            } else {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+              w[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          }
+          if (stg != 0) st_shared_v4(stg + m * prow + (((chunk0 + i) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+          else op[i] = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        if (stg != 0) st_shared_v4(stg + m * prow + (((chunk0 + i) ^ sw) << 4), w[0], w[1], w[2], w[3]);
-        else op[i] = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
     if (p.out32 != nullptr) {
@@ -147,11 +175,17 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
         float x = v[i];
         if (p.res != nullptr) {
           if (p.res_is_f32) x += static_cast<const float*>(p.res)[off + n];
+          else if (SPLIT) x += __half2float(static_cast<const __half*>(p.res)[off + n]) +
+                                 __half2float(static_cast<const __half*>(p.res)[off + n + p.o_plane]);
           else if (p.ab_fmt == 0) x += __half2float(static_cast<const __half*>(p.res)[off + n]);
           else x += __bfloat162float(static_cast<const __nv_bfloat16*>(p.res)[off + n]);
         }
         if (p.out16 != nullptr) {
-          if (p.ab_fmt == 0) static_cast<__half*>(p.out16)[off + n] = __float2half_rn(x);
+          if (SPLIT) {
+            const __half h = __float2half_rn(x);
+            static_cast<__half*>(p.out16)[off + n] = h;
+            static_cast<__half*>(p.out16)[off + n + p.o_plane] = __float2half_rn(x - __half2float(h));
+          } else if (p.ab_fmt == 0) static_cast<__half*>(p.out16)[off + n] = __float2half_rn(x);
           else static_cast<__nv_bfloat16*>(p.out16)[off + n] = __float2bfloat16_rn(x);
         }
         if (p.out32 != nullptr) p.out32[off + n] = x;
@@ -176,10 +210,12 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
 // quadrants, each drains half of the tile's panels (its own M sub-tile, or its own half of the columns) through its own
 // staging buffer and named barrier.  For the short-K tiles (1x1 projection unit, banded 3^3 convs, thin decoder layers)
 // the epilogue is latency-bound (tcgen05.ld behind queued MMAs, residual rows from L2) and was the critical path.
-template <int BN, int CL, int CG, int MS, int EG>
+// SPLIT = operand-split "exact" mode (fmt 2, see IgemmParams::split): compiled only for the two-epilogue-group variants.
+template <int BN, int CL, int CG, int MS, int EG, bool SPLIT>
 __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   static_assert(CG == 1 || (CG == 2 && CL == 2), "cta_group::2 runs on a 2-CTA cluster");
   static_assert(EG == 1 || EG == 2, "one or two epilogue warp groups");
+  static_assert(!SPLIT || EG == 2, "split mode is instantiated for the two-group epilogue only");
   static_assert(MS == 1 || (MS == 2 && BN <= 128), "two accumulators per tile need 4 x BN <= 512 TMEM columns");
   constexpr int CW = (BN >= 32) ? 32 : 16;                     // epilogue column chunk
   constexpr int ms = MS;                                       // M sub-tiles (accumulators) per tile (== p.ms)
@@ -205,6 +241,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
     tma_prefetch_desc(&p.tmB);
     if (p.tma_store) tma_prefetch_desc(&p.tmO);
     if (p.res_l2_prefetch) tma_prefetch_desc(&p.tmR);
+    if constexpr (SPLIT) { tma_prefetch_desc(&p.tmA2); tma_prefetch_desc(&p.tmB2); }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], CG == 2 ? 1 : CL);
@@ -249,7 +286,9 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
       const uint32_t kit_tx = (CG == 2 ? 2u : 1u) * (a_tx + static_cast<uint32_t>(ny) * b_tx);
       const uint32_t b_off = (CL > 1 && CG == 1) ? static_cast<uint32_t>(cta_rank * kBRows * p.row_bytes) : 0u;
       const int b_row = (CG == 2) ? cta_rank * (BN / 2) : ((CL > 1) ? cta_rank * kBRows : 0);
-      const uint64_t mapA = reinterpret_cast<uint64_t>(&p.tmA), mapB = reinterpret_cast<uint64_t>(&p.tmB);
+      const uint64_t mapA_hi = reinterpret_cast<uint64_t>(&p.tmA), mapB_hi = reinterpret_cast<uint64_t>(&p.tmB);
+      const uint64_t mapA_lo = reinterpret_cast<uint64_t>(&p.tmA2), mapB_lo = reinterpret_cast<uint64_t>(&p.tmB2);
+      constexpr bool split = SPLIT;          // pseudo-taps pick the hi / lo plane of either operand (tap[.][3])
       int stage = 0;
       uint32_t phase = 0;
       for (int ct = cl_id; ct < num_ct; ct += ncl) {
@@ -260,6 +299,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
         uint32_t dst = 0, bar = 0;
         for (int kx = 0; kx < nx; ++kx) {      // tap(ky, kx) = ky*nx + kx; entry kx holds (dx, dy of ky = 0, dz)
           const int cx = t.x0 + p.tap[kx][0], cy = t.y0 + p.tap[kx][1], cz = t.z0 + p.tap[kx][2];
+          const uint64_t mapA = (split && (p.tap[kx][3] & 1)) ? mapA_lo : mapA_hi;
           int ac = a_c0, bk = 0;
           for (int kb = 0; kb < kblocks; ++kb) {
             if (j == 0) {
@@ -273,7 +313,9 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
             else tma_a_4d<CG == 2>(dst, mapA, bar, ac, cx, cy, t.b);
             uint32_t bdst = dst + a_sub;
             for (int ky = 0; ky < ny; ++ky) {
-              const int tap = ky * nx + kx;
+              int tap = ky * nx + kx;
+              const uint64_t mapB = (split && (p.tap[tap][3] & 2)) ? mapB_lo : mapB_hi;
+              if (split) tap = p.tap_b[tap];
               if constexpr (CL > 1 && CG == 1) {
                 if (banded) tma_a_3d_mc(bdst + b_off, mapB, bar, kMask, 0, b_row, tap * kblocks + kb);
                 else tma_a_3d_mc(bdst + b_off, mapB, bar, kMask, bk, bn0, tap);
@@ -384,7 +426,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
           if (ct == cl_id) l2_prefetch_tile(t);
           if (ct + ncl < num_ct) l2_prefetch_tile(decode_tile(p, tile_of(ct + ncl), BN));
         }
-        const bool want_pre = p.res_prefetch && (p.res != nullptr) && !p.res_is_f32 && p.vec_ok && (p.o_nsplit == 0) &&
+        const bool want_pre = p.res_prefetch && !SPLIT && (p.res != nullptr) && !p.res_is_f32 && p.vec_ok && (p.o_nsplit == 0) &&
                               (t.n0 + BN <= p.n_valid);
         auto drain = [&](auto pre_tag) {
           constexpr bool res_pre = decltype(pre_tag)::value;
@@ -431,14 +473,14 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
               for (int c = 0; c < PC; c += CW) {
                 const int nc = t.n0 + pc + c;
                 const long long offc = p.o_nsplit > 0 ? off + (nc / p.o_nsplit) * p.o_nhi + (nc % p.o_nsplit) - nc : off;
-                epilogue_chunk<CW>(p, r + c, nc, offc, row_valid, 0, 0, 0, 128, res_pre ? res + c / 8 : nullptr);
+                epilogue_chunk<CW, SPLIT>(p, r + c, nc, offc, row_valid, 0, 0, 0, 128, res_pre ? res + c / 8 : nullptr);
               }
               if constexpr (res_pre) { if (q + 1 < q_hi) prefetch_res(q + 1); }
             } else {
               named_bar_sync(bar_id, 128);               // this group's previous store has finished reading its staging buffer
 #pragma unroll
               for (int c = 0; c < PC; c += CW)
-                epilogue_chunk<CW>(p, r + c, t.n0 + pc + c, off, row_valid, stg, m, c / 8, PC * 2,
+                epilogue_chunk<CW, SPLIT>(p, r + c, t.n0 + pc + c, off, row_valid, stg, m, c / 8, PC * 2,
                                    res_pre ? res + c / 8 : nullptr);
               if constexpr (res_pre) { if (q + 1 < q_hi) prefetch_res(q + 1); }
               fence_proxy_async();
@@ -488,7 +530,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
         if (ct == cl_id) l2_prefetch_tile(t);
         if (ct + ncl < num_ct) l2_prefetch_tile(decode_tile(p, tile_of(ct + ncl), BN));
       }
-      const bool want_pre = p.res_prefetch && (p.res != nullptr) && !p.res_is_f32 && p.vec_ok && (p.o_nsplit == 0) &&
+      const bool want_pre = p.res_prefetch && !SPLIT && (p.res != nullptr) && !p.res_is_f32 && p.vec_ok && (p.o_nsplit == 0) &&
                             (t.n0 + BN <= p.n_valid);
       // Two copies of the drain loop, selected per tile: the one without a residual keeps no prefetch registers alive
       // (the 1x1 projection kernel is epilogue-bound and measurably slower with them: profiles/r01_ab_oldnew.log).
@@ -539,7 +581,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
               for (int c = 0; c < PC; c += CW) {
                 const int nc = t.n0 + sc + pc + c;
                 const long long offc = p.o_nsplit > 0 ? off + (nc / p.o_nsplit) * p.o_nhi + (nc % p.o_nsplit) - nc : off;
-                epilogue_chunk<CW>(p, r + pc + c, nc, offc, row_valid, 0, 0, 0, 128, res_pre ? res + c / 8 : nullptr);
+                epilogue_chunk<CW, SPLIT>(p, r + pc + c, nc, offc, row_valid, 0, 0, 0, 128, res_pre ? res + c / 8 : nullptr);
               }
               ++q;
               if constexpr (res_pre) { if (q < nq) prefetch_res(q); }
@@ -548,7 +590,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
               named_bar_sync(1, 128);                    // the previous panel's store has finished reading the staging buffer
 #pragma unroll
               for (int c = 0; c < PC; c += CW)
-                epilogue_chunk<CW>(p, r + pc + c, t.n0 + sc + pc + c, off, row_valid, stg_base, m, c / 8, PC * 2,
+                epilogue_chunk<CW, SPLIT>(p, r + pc + c, t.n0 + sc + pc + c, off, row_valid, stg_base, m, c / 8, PC * 2,
                                    res_pre ? res + c / 8 : nullptr);
               ++q;
               if constexpr (res_pre) { if (q < nq) prefetch_res(q); }   // next panel's residual: in flight across the store + barrier
@@ -583,17 +625,23 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
   if (warp == 1) tmem_dealloc<CG>(tmem_base, kTmemCols);
 }
 
-template <int BN, int CL, int CG, int MS, int EG = 1>
-static cudaError_t launch_ms(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, CL, CG, MS, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+// One explicit instantiation per kernel variant lives in its own object file (rn_igemm_inst.cu compiled with
+// -DRN_BN=.. etc., see the Makefile's VARIANTS list); rn_igemm.cu holds the matching dispatch table.
+template <int BN, int CL, int CG, int MS, int EG, bool SPLIT>
+cudaError_t launch_ms(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+  // cudaFuncSetAttribute is per DEVICE (and per kernel variant): one flag per device ordinal
+  static std::atomic<bool> attr_set[kMaxDevices];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, CL, CG, MS, EG, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev].store(true, std::memory_order_release);
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if constexpr (CL == 1) {
-    igemm_kernel<BN, 1, 1, MS, EG><<<grid, 64 + 128 * EG, smem, stream>>>(p);
+    igemm_kernel<BN, 1, 1, MS, EG, SPLIT><<<grid, 64 + 128 * EG, smem, stream>>>(p);
     return cudaGetLastError();
   } else {
     cudaLaunchConfig_t cfg;
@@ -609,16 +657,8 @@ static cudaError_t launch_ms(const IgemmParams& p, int grid, size_t smem, cudaSt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, igemm_kernel<BN, CL, CG, MS, EG>, p);
+    return cudaLaunchKernelEx(&cfg, igemm_kernel<BN, CL, CG, MS, EG, SPLIT>, p);
   }
-}
-
-template <int BN, int CL, int CG>
-static cudaError_t launch_bn(const IgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
-  if constexpr (BN <= 128) {
-    if (p.ms == 2) return launch_ms<BN, CL, CG, 2>(p, grid, smem, stream);
-  }
-  return launch_ms<BN, CL, CG, 1>(p, grid, smem, stream);
 }
 
 }  // namespace rn

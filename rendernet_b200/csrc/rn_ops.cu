@@ -15,13 +15,50 @@
 #include "../../include/rendernet_b200.h"
 
 #include <atomic>
-namespace rn {
-extern int g_epi_groups;   // rn_igemm.cu: epilogue warp groups (rn_set_epilogue_groups)
-}
+#include "rn_igemm.cuh"
 namespace rn {
 extern std::atomic<long long> g_launch_count;
 #define RN_COUNT_LAUNCH() rn::g_launch_count.fetch_add(1, std::memory_order_relaxed)
-int g_yhalo = 1;   // share one activation halo load between the 3 ky taps of 3x3 / banded 3^3 convs
+
+// 16-bit storage in the three formats of the C ABI (RN_FMT_*): fp16, bf16, or an fp16 hi/lo pair whose LO plane lives
+// `plane` elements after the HI plane (hi = fp16(v), lo = fp16(v - hi)).
+__device__ __forceinline__ void store16(uint16_t* __restrict__ p, long long i, float v, int fmt, long long plane) {
+  if (fmt == 1) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    p[i] = *reinterpret_cast<const uint16_t*>(&h);
+  } else {
+    const __half h = __float2half_rn(v);
+    p[i] = *reinterpret_cast<const uint16_t*>(&h);
+    if (fmt == 2) {
+      const __half l = __float2half_rn(v - __half2float(h));
+      p[i + plane] = *reinterpret_cast<const uint16_t*>(&l);
+    }
+  }
+}
+// two values -> one packed 32-bit word of the HI plane (and of the LO plane for fmt 2)
+__device__ __forceinline__ void pack16x2(float v0, float v1, int fmt, uint32_t* hi, uint32_t* lo) {
+  if (fmt == 1) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    *hi = *reinterpret_cast<const uint32_t*>(&h);
+    *lo = 0u;
+  } else {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    *hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    *lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+__device__ __forceinline__ float load16(const uint16_t* __restrict__ p, long long i, int fmt, long long plane) {
+  const uint16_t u = p[i];
+  if (fmt == 1) return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
+  float v = __half2float(*reinterpret_cast<const __half*>(&u));
+  if (fmt == 2) {
+    const uint16_t l = p[i + plane];
+    v += __half2float(*reinterpret_cast<const __half*>(&l));
+  }
+  return v;
+}
 
 // ------------------------------------------------------------------------------------------ resampler
 // One warp per output row (innermost output axis); each lane owns 4 consecutive points per iteration so
@@ -115,7 +152,7 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
 struct TapSel { int n; int idx[64]; };
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ packed, int Cin, int Cout,
-                                    int cout_pad, int transposed, TapSel sel, int fmt) {
+                                    int cout_pad, int transposed, TapSel sel, int fmt, long long plane) {
   const long long total = static_cast<long long>(sel.n) * cout_pad * Cin;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -127,8 +164,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
       const long long base = static_cast<long long>(sel.idx[t]) * Cin * Cout;
       v = transposed ? w[base + static_cast<long long>(co) * Cin + ci] : w[base + static_cast<long long>(ci) * Cout + co];
     }
-    if (fmt == 0) { __half h = __float2half_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
-    else { __nv_bfloat16 h = __float2bfloat16_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
+    store16(packed, i, v, fmt, plane);
   }
 }
 
@@ -137,17 +173,14 @@ __global__ void cast_f32_to_16_kernel(const float* __restrict__ s, uint16_t* __r
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_pad;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float v = i < n ? s[i] : 0.f;
-    if (fmt == 0) { __half h = __float2half_rn(v); d[i] = *reinterpret_cast<uint16_t*>(&h); }
-    else { __nv_bfloat16 h = __float2bfloat16_rn(v); d[i] = *reinterpret_cast<uint16_t*>(&h); }
+    store16(d, i, v, fmt, n_pad);
   }
 }
 
 __global__ void cast_16_to_f32_kernel(const uint16_t* __restrict__ s, float* __restrict__ d, long long n, int fmt) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const uint16_t u = s[i];
-    d[i] = fmt == 0 ? __half2float(*reinterpret_cast<const __half*>(&u))
-                    : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
+    d[i] = load16(s, i, fmt, n);
   }
 }
 
@@ -170,8 +203,7 @@ __global__ void pack_banded_kernel(const float* __restrict__ w, uint16_t* __rest
     const int kz = kb * (64 / Cin) + zi_l - sz * zo_l;
     float v = 0.f;
     if (kz >= 0 && kz <= 2) v = w[((static_cast<long long>(tap) * 3 + kz) * Cin + ci) * Cout + co];
-    if (fmt == 0) { __half h = __float2half_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
-    else { __nv_bfloat16 h = __float2bfloat16_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
+    store16(packed, i, v, fmt, total);
   }
 }
 
@@ -189,21 +221,12 @@ __global__ void bias_act_kernel(const uint16_t* __restrict__ x, const float* __r
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C);
-    const uint16_t u = x[i];
-    float v = fmt == 0 ? __half2float(*reinterpret_cast<const __half*>(&u))
-                       : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
+    float v = load16(x, i, fmt, n);
     if (bias != nullptr) v += bias[c];
     if (act == 1) v = fmaxf(v, 0.f) + alpha[c] * fminf(v, 0.f);
     else if (act == 2) v = 1.f / (1.f + __expf(-v));
-    if (res != nullptr) {
-      const uint16_t r = res[i];
-      v += fmt == 0 ? __half2float(*reinterpret_cast<const __half*>(&r))
-                    : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&r));
-    }
-    if (out != nullptr) {
-      if (fmt == 0) { __half h = __float2half_rn(v); out[i] = *reinterpret_cast<uint16_t*>(&h); }
-      else { __nv_bfloat16 h = __float2bfloat16_rn(v); out[i] = *reinterpret_cast<uint16_t*>(&h); }
-    }
+    if (res != nullptr) v += load16(res, i, fmt, n);
+    if (out != nullptr) store16(out, i, v, fmt, n);
     if (out32 != nullptr) out32[i] = v;
   }
 }
@@ -251,15 +274,21 @@ __global__ void __launch_bounds__(256) conv3d_direct_kernel(const void* __restri
         } else {
           static_assert(X_F32 || CIN % 8 == 0, "16-bit input needs CIN % 8 == 0");
           const uint4* xp = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(xv) + (rowbase + iz) * CIN);
+          const long long xplane8 = (static_cast<long long>(B) * H * W * D * CIN) >> 3;   // fmt 2: LO plane, in uint4 units
 #pragma unroll
           for (int v = 0; v < CIN / 8; ++v) {
             const uint4 q = __ldg(xp + v);
             const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+            uint32_t ul[4] = {0u, 0u, 0u, 0u};
+            if (fmt == 2) { const uint4 ql = __ldg(xp + v + xplane8); ul[0] = ql.x; ul[1] = ql.y; ul[2] = ql.z; ul[3] = ql.w; }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float2 f;
-              if (fmt == 0) f = __half22float2(*reinterpret_cast<const __half2*>(&u[j]));
-              else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[j]));
+              if (fmt == 1) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[j]));
+              else {
+                f = __half22float2(*reinterpret_cast<const __half2*>(&u[j]));
+                if (fmt == 2) { const float2 g = __half22float2(*reinterpret_cast<const __half2*>(&ul[j])); f.x += g.x; f.y += g.y; }
+              }
               xin[v * 8 + 2 * j] = f.x;
               xin[v * 8 + 2 * j + 1] = f.y;
             }
@@ -280,7 +309,7 @@ __global__ void __launch_bounds__(256) conv3d_direct_kernel(const void* __restri
       }
     }
   }
-  uint32_t pk[COUT / 2];
+  uint32_t pk[COUT / 2], pl[COUT / 2];
 #pragma unroll
   for (int c = 0; c < COUT; c += 2) {
     float v0 = acc[c] + __ldg(bias + c), v1 = acc[c + 1] + __ldg(bias + c + 1);
@@ -288,12 +317,16 @@ __global__ void __launch_bounds__(256) conv3d_direct_kernel(const void* __restri
       v0 = fmaxf(v0, 0.f) + __ldg(alpha + c) * fminf(v0, 0.f);
       v1 = fmaxf(v1, 0.f) + __ldg(alpha + c + 1) * fminf(v1, 0.f);
     }
-    if (fmt == 0) { __half2 h = __floats2half2_rn(v0, v1); pk[c / 2] = *reinterpret_cast<uint32_t*>(&h); }
-    else { __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1); pk[c / 2] = *reinterpret_cast<uint32_t*>(&h); }
+    pack16x2(v0, v1, fmt, &pk[c / 2], &pl[c / 2]);
   }
   uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(idx) * COUT);
 #pragma unroll
   for (int v = 0; v < COUT / 8; ++v) op[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+  if (fmt == 2) {
+    uint4* ol = op + ((total * COUT) >> 3);      // LO plane
+#pragma unroll
+    for (int v = 0; v < COUT / 8; ++v) ol[v] = make_uint4(pl[4 * v], pl[4 * v + 1], pl[4 * v + 2], pl[4 * v + 3]);
+  }
 }
 
 
@@ -430,7 +463,7 @@ __global__ void __launch_bounds__(256) resample_conv1_kernel(const float* __rest
       }
     }
   }
-  uint32_t pk0[4], pk1[4];
+  uint32_t pk0[4], pk1[4], pl0[4], pl1[4];
 #pragma unroll
   for (int c = 0; c < 8; c += 2) {
     const float b0 = __ldg(bias + c), b1 = __ldg(bias + c + 1);
@@ -442,17 +475,18 @@ __global__ void __launch_bounds__(256) resample_conv1_kernel(const float* __rest
       v0 = fmaxf(v0, 0.f) + al0 * fminf(v0, 0.f);
       v1 = fmaxf(v1, 0.f) + al1 * fminf(v1, 0.f);
     }
-    if (fmt == 0) {
-      __half2 h = __floats2half2_rn(u0, u1); pk0[c / 2] = *reinterpret_cast<uint32_t*>(&h);
-      h = __floats2half2_rn(v0, v1); pk1[c / 2] = *reinterpret_cast<uint32_t*>(&h);
-    } else {
-      __nv_bfloat162 h = __floats2bfloat162_rn(u0, u1); pk0[c / 2] = *reinterpret_cast<uint32_t*>(&h);
-      h = __floats2bfloat162_rn(v0, v1); pk1[c / 2] = *reinterpret_cast<uint32_t*>(&h);
-    }
+    pack16x2(u0, u1, fmt, &pk0[c / 2], &pl0[c / 2]);
+    pack16x2(v0, v1, fmt, &pk1[c / 2], &pl1[c / 2]);
   }
   const size_t o0 = (((static_cast<size_t>(b) * No + (ty * RC_T + oy)) * No + (tx * RC_T + ox)) * No + (tz * RC_T + oz)) * 8;
+  const size_t o1 = o0 + static_cast<size_t>(4) * No * No * 8;
   *reinterpret_cast<uint4*>(out + o0) = make_uint4(pk0[0], pk0[1], pk0[2], pk0[3]);
-  *reinterpret_cast<uint4*>(out + o0 + static_cast<size_t>(4) * No * No * 8) = make_uint4(pk1[0], pk1[1], pk1[2], pk1[3]);
+  *reinterpret_cast<uint4*>(out + o1) = make_uint4(pk1[0], pk1[1], pk1[2], pk1[3]);
+  if (fmt == 2) {    // LO plane of the fp16 hi/lo pair
+    const size_t plane = static_cast<size_t>(B) * No * No * No * 8;
+    *reinterpret_cast<uint4*>(out + plane + o0) = make_uint4(pl0[0], pl0[1], pl0[2], pl0[3]);
+    *reinterpret_cast<uint4*>(out + plane + o1) = make_uint4(pl1[0], pl1[1], pl1[2], pl1[3]);
+  }
 }
 
 
@@ -487,10 +521,7 @@ __global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ x, co
       if (alpha != nullptr) v = fmaxf(v, 0.f) + av * fminf(v, 0.f);
       const size_t o = static_cast<size_t>(b) * N + n;
       if (out32 != nullptr) out32[o] = v;
-      if (out16 != nullptr) {
-        if (fmt == 0) { __half h = __float2half_rn(v); out16[o] = *reinterpret_cast<uint16_t*>(&h); }
-        else { __nv_bfloat16 h = __float2bfloat16_rn(v); out16[o] = *reinterpret_cast<uint16_t*>(&h); }
-      }
+      if (out16 != nullptr) store16(out16, o, v, fmt, static_cast<long long>(B) * N);
     }
   }
 }
@@ -538,11 +569,7 @@ __global__ void __launch_bounds__(256) conv3d_small_kernel(const void* __restric
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
           if (x_is_f32) xin[ci] = __ldg(static_cast<const float*>(xv) + xi + ci);
-          else {
-            const uint16_t u = __ldg(static_cast<const uint16_t*>(xv) + xi + ci);
-            xin[ci] = fmt == 0 ? __half2float(*reinterpret_cast<const __half*>(&u))
-                               : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
-          }
+          else xin[ci] = load16(static_cast<const uint16_t*>(xv), xi + ci, fmt, static_cast<long long>(B) * H * W * D * CIN);
         }
         const float* wt = wsm + ((ky * K + kx) * K + kz) * CIN * COUT;
 #pragma unroll
@@ -559,10 +586,7 @@ __global__ void __launch_bounds__(256) conv3d_small_kernel(const void* __restric
     if (alpha != nullptr) v = fmaxf(v, 0.f) + __ldg(alpha + co) * fminf(v, 0.f);
     const size_t o = static_cast<size_t>(idx) * COUT + co;
     if (out32 != nullptr) out32[o] = v;
-    if (out16 != nullptr) {
-      if (fmt == 0) { __half h = __float2half_rn(v); out16[o] = *reinterpret_cast<uint16_t*>(&h); }
-      else { __nv_bfloat16 h = __float2bfloat16_rn(v); out16[o] = *reinterpret_cast<uint16_t*>(&h); }
-    }
+    if (out16 != nullptr) store16(out16, o, v, fmt, total * COUT);
   }
 }
 
@@ -600,8 +624,7 @@ __global__ void pack_xfold_kernel(const float* __restrict__ w, uint16_t* __restr
       const int kx = pb - (F * dq + p - r);
       if (kx >= 0 && kx < kw) v = w[((static_cast<long long>(ky) * kw + kx) * Cout + co) * Cin + ci];
     }
-    if (fmt == 0) { __half h = __float2half_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
-    else { __nv_bfloat16 h = __float2bfloat16_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
+    store16(packed, i, v, fmt, total);
   }
 }
 
@@ -624,8 +647,7 @@ __global__ void pack_tconv_s2_merged_kernel(const float* __restrict__ w, uint16_
     const int ky = ay + 1 - 2 * dy, kx = ax + 1 - 2 * dx;
     float v = 0.f;
     if (ky >= 0 && ky < 4 && kx >= 0 && kx < 4) v = w[((static_cast<long long>(ky) * 4 + kx) * Cout + co) * Cin + ci];
-    if (fmt == 0) { __half h = __float2half_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
-    else { __nv_bfloat16 h = __float2bfloat16_rn(v); packed[i] = *reinterpret_cast<uint16_t*>(&h); }
+    store16(packed, i, v, fmt, total);
   }
 }
 
@@ -708,12 +730,6 @@ using namespace rn;
 
 extern "C" int rn_version(void) { return 100; }
 
-extern "C" int rn_set_yhalo(int on) {
-  const int prev = rn::g_yhalo;
-  rn::g_yhalo = on ? 1 : 0;
-  return prev;
-}
-
 extern "C" const char* rn_error_string(int code) {
   if (code == 0) return "ok";
   if (code < 0) return "rendernet_b200: invalid argument";
@@ -739,9 +755,10 @@ extern "C" int rn_resample_f32(const float* vox, const float* minv, float* out, 
   return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int rn_pack_conv_weights(const float* w, void* packed, int ntaps_total, int Cin, int Cout, int cout_pad,
-                                    int transposed, const int* tap_sel, int n_sel, int fmt, void* stream) {
-  if (!w || !packed || Cin < 1 || Cout < 1 || cout_pad < Cout) return -1;
+// plane: element offset of the LO plane for fmt 2 (0 = right after this call's own output)
+static int pack_conv_weights_impl(const float* w, void* packed, int ntaps_total, int Cin, int Cout, int cout_pad,
+                                  int transposed, const int* tap_sel, int n_sel, int fmt, long long plane, void* stream) {
+  if (!w || !packed || Cin < 1 || Cout < 1 || cout_pad < Cout || fmt < 0 || fmt > 2) return -1;
   TapSel sel;
   if (tap_sel == nullptr) {
     if (ntaps_total > 64) return -2;
@@ -757,9 +774,14 @@ extern "C" int rn_pack_conv_weights(const float* w, void* packed, int ntaps_tota
   }
   const long long total = static_cast<long long>(sel.n) * cout_pad * Cin;
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, static_cast<uint16_t*>(packed), Cin, Cout, cout_pad, transposed, sel, fmt);
+      w, static_cast<uint16_t*>(packed), Cin, Cout, cout_pad, transposed, sel, fmt, plane > 0 ? plane : total);
   RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_pack_conv_weights(const float* w, void* packed, int ntaps_total, int Cin, int Cout, int cout_pad,
+                                    int transposed, const int* tap_sel, int n_sel, int fmt, void* stream) {
+  return pack_conv_weights_impl(w, packed, ntaps_total, Cin, Cout, cout_pad, transposed, tap_sel, n_sel, fmt, 0, stream);
 }
 
 extern "C" int rn_cast_f32_to_16(const float* src, void* dst, long long n, long long n_pad, int fmt, void* stream) {
@@ -796,8 +818,8 @@ extern "C" int rn_bias_act_16(const void* x, const float* bias, const float* alp
 extern "C" int rn_conv2d_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
                               const void* residual, int residual_is_f32, void* out16, float* out32, int B, int H,
                               int W, int Cin, int Cout, int cout_pad, int kh, int kw, int fmt, void* stream) {
-  if (kh * kw > 28 || kh < 1 || kw < 1) return -20;
-  int8_t taps[28 * 3];
+  if (kh * kw > kMaxTaps || kh < 1 || kw < 1) return -20;
+  int8_t taps[kMaxTaps * 3];
   const int pby = (kh - 1) / 2, pbx = (kw - 1) / 2;  // SAME, stride 1: before = (k-1)//2
   for (int ky = 0; ky < kh; ++ky)
     for (int kx = 0; kx < kw; ++kx) {
@@ -811,15 +833,20 @@ extern "C" int rn_conv2d_same(const void* x, const void* w_packed, const float* 
   d.residual = residual; d.residual_is_f32 = residual_is_f32; d.out16 = out16; d.out32 = out32;
   d.o_base = 0; d.o_x = Cout; d.o_y = static_cast<long long>(W) * Cout; d.o_b = static_cast<long long>(H) * W * Cout;
   d.o_z = 0; d.fmt = fmt;
-  if (kh == 3 && Cin % 64 == 0 && g_yhalo) d.ny = 3;   // taps are already ordered ky*kw + kx with dy = ky - 1
+  if (fmt == 2) {   // fp16 hi/lo pairs: [2][numel]
+    d.x_plane = static_cast<long long>(B) * H * W * Cin;
+    d.w_plane = static_cast<long long>(kh) * kw * cout_pad * Cin;
+    d.o_plane = static_cast<long long>(B) * H * W * Cout;
+  }
+  if (kh == 3 && Cin % 64 == 0 && tuning().yhalo) d.ny = 3;   // taps are already ordered ky*kw + kx with dy = ky - 1
   return rn_conv_igemm(&d, stream);
 }
 
 extern "C" int rn_conv3d_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
                               const void* residual, int residual_is_f32, void* out16, float* out32, int B, int H,
                               int W, int D, int Cin, int Cout, int cout_pad, int k, int fmt, void* stream) {
-  if (k * k * k > 28 || k < 1) return -20;
-  int8_t taps[28 * 3];
+  if (k * k * k > kMaxTaps || k < 1) return -20;
+  int8_t taps[kMaxTaps * 3];
   const int pb = (k - 1) / 2;
   for (int k0 = 0; k0 < k; ++k0)
     for (int k1 = 0; k1 < k; ++k1)
@@ -834,13 +861,18 @@ extern "C" int rn_conv3d_same(const void* x, const void* w_packed, const float* 
   d.residual = residual; d.residual_is_f32 = residual_is_f32; d.out16 = out16; d.out32 = out32;
   d.o_base = 0; d.o_z = Cout; d.o_x = static_cast<long long>(D) * Cout; d.o_y = static_cast<long long>(W) * D * Cout;
   d.o_b = static_cast<long long>(H) * W * D * Cout; d.fmt = fmt;
+  if (fmt == 2) {
+    d.x_plane = static_cast<long long>(B) * H * W * D * Cin;
+    d.w_plane = static_cast<long long>(k) * k * k * cout_pad * Cin;
+    d.o_plane = static_cast<long long>(B) * H * W * D * Cout;
+  }
   return rn_conv_igemm(&d, stream);
 }
 
 // Transposed SAME conv: o = i*s + kk - pb, pb = max(k-s,0)/2.  Output phase a (o = j*s + a) receives the
 // filter taps kk == (a+pb) mod s, read at input offset d = (a + pb - kk)/s.
 namespace {
-struct PhaseTaps { int n; int src[28]; int8_t d[28 * 3]; };
+struct PhaseTaps { int n; int src[kMaxTaps]; int8_t d[kMaxTaps * 3]; };
 void phase_taps(int kh, int kw, int s, int ay, int ax, PhaseTaps* pt) {
   const int pby = (kh - s > 0 ? kh - s : 0) / 2, pbx = (kw - s > 0 ? kw - s : 0) / 2;
   pt->n = 0;
@@ -863,15 +895,16 @@ void phase_taps(int kh, int kw, int s, int ay, int ax, PhaseTaps* pt) {
 
 extern "C" int rn_pack_conv2d_transpose_weights(const float* w, void* packed, int kh, int kw, int Cin, int Cout,
                                                 int cout_pad, int stride, int fmt, void* stream) {
-  if (kh * kw > 28 || stride < 1) return -20;
+  if (kh * kw > kMaxTaps || stride < 1) return -20;
   size_t off = 0;
   for (int ay = 0; ay < stride; ++ay)
     for (int ax = 0; ax < stride; ++ax) {
       PhaseTaps pt;
       phase_taps(kh, kw, stride, ay, ax, &pt);
       if (pt.n == 0) continue;
-      int r = rn_pack_conv_weights(w, static_cast<uint16_t*>(packed) + off, kh * kw, Cin, Cout, cout_pad, 1, pt.src,
-                                   pt.n, fmt, stream);
+      // fmt 2: [all phases, hi][all phases, lo] -- the LO plane starts after the kh*kw taps of the HI plane
+      int r = pack_conv_weights_impl(w, static_cast<uint16_t*>(packed) + off, kh * kw, Cin, Cout, cout_pad, 1, pt.src, pt.n,
+                                     fmt, static_cast<long long>(kh) * kw * cout_pad * Cin, stream);
       if (r != 0) return r;
       off += static_cast<size_t>(pt.n) * cout_pad * Cin;
     }
@@ -881,7 +914,7 @@ extern "C" int rn_pack_conv2d_transpose_weights(const float* w, void* packed, in
 extern "C" int rn_conv2d_transpose_same(const void* x, const void* w_packed, const float* bias, const float* alpha,
                                         int act, void* out16, float* out32, int B, int H, int W, int Cin, int Cout,
                                         int cout_pad, int kh, int kw, int stride, int fmt, void* stream) {
-  if (kh * kw > 28 || stride < 1) return -20;
+  if (kh * kw > kMaxTaps || stride < 1) return -20;
   const int Ho = H * stride, Wo = W * stride;
   size_t off = 0;
   for (int ay = 0; ay < stride; ++ay)
@@ -900,6 +933,11 @@ extern "C" int rn_conv2d_transpose_same(const void* x, const void* w_packed, con
       d.o_y = static_cast<long long>(stride) * Wo * Cout;
       d.o_b = static_cast<long long>(Ho) * Wo * Cout;
       d.fmt = fmt;
+      if (fmt == 2) {
+        d.x_plane = static_cast<long long>(B) * H * W * Cin;
+        d.w_plane = static_cast<long long>(kh) * kw * cout_pad * Cin;   // LO plane follows ALL phases of the HI plane
+        d.o_plane = static_cast<long long>(B) * Ho * Wo * Cout;
+      }
       int r = rn_conv_igemm(&d, stream);
       if (r != 0) return r;
       off += static_cast<size_t>(pt.n) * cout_pad * Cin;
@@ -964,14 +1002,19 @@ extern "C" int rn_conv3d_banded_same(const void* x, const void* w_banded, const 
   d.a_c_base = -pz * Cin;                           // first input depth of N tile 0 is z = -pz (zero filled)
   d.a_c_ntile = (128 / Cout) * sz * Cin;            // each N tile advances 128/Cout output = sz*128/Cout input depths
   d.w_banded = 1;
-  if (g_yhalo) d.ny = 3;
+  if (fmt == 2) {
+    d.x_plane = static_cast<long long>(B) * H * W * Fi;
+    d.w_plane = rn_conv3d_banded_bytes(Cin, Cout, sz) / 2;
+    d.o_plane = static_cast<long long>(B) * H * W * Fo;
+  }
+  if (tuning().yhalo) d.ny = 3;
   // With a residual the epilogue is the critical path of these short-K tiles, and the paired (cta_group::2) form couples
   // the two CTAs' epilogues through the shared accumulator hand-over: multicast clusters of independent CTAs are 17 %
   // faster there (0.296 vs 0.355 ms), while the PReLU-only convs prefer the pair (0.238 vs 0.270 ms);
   // profiles/r01_probe_res1_cg.log.  Results are bit-identical either way.
   // (With two epilogue warp groups the pair form drains fast enough again, so the override only applies to the
   // single-group configuration.)
-  if (residual != nullptr && rn::g_epi_groups == 1) d.cta_group = 1;
+  if (residual != nullptr && tuning().epi_groups == 1) d.cta_group = 1;
   return rn_conv_igemm(&d, stream);
 }
 
@@ -1046,7 +1089,7 @@ extern "C" int rn_xfold_factor(int Cin, int W) {
 
 extern "C" int rn_pack_conv2d_transpose_xfold(const float* w, void* packed, int kh, int kw, int Cin, int Cout, int F,
                                               int cout_pad, int fmt, void* stream) {
-  if (!w || !packed || F < 2 || kw > 2 * F || cout_pad < F * Cout || kh * 3 > 28) return -1;
+  if (!w || !packed || F < 2 || kw > 2 * F || cout_pad < F * Cout || kh * 3 > kMaxTaps) return -1;
   const long long total = static_cast<long long>(kh) * 3 * cout_pad * F * Cin;
   pack_xfold_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, static_cast<uint16_t*>(packed), kh, kw, Cin, Cout, F, cout_pad, fmt);
@@ -1059,8 +1102,8 @@ extern "C" int rn_pack_conv2d_transpose_xfold(const float* w, void* packed, int 
 extern "C" int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, const float* bias_x, const float* alpha_x,
                                             int act, void* out16, float* out32, int B, int H, int W, int Cin, int Cout,
                                             int kh, int kw, int F, int cout_pad, int fmt, void* stream) {
-  if (F < 2 || W % F != 0 || kh * 3 > 28) return -20;
-  int8_t taps[28 * 3];
+  if (F < 2 || W % F != 0 || kh * 3 > kMaxTaps) return -20;
+  int8_t taps[kMaxTaps * 3];
   const int pby = (kh - 1) / 2;                     // SAME stride-1 transposed: dy = pb - ky
   for (int kyr = 0; kyr < kh; ++kyr)                // ky-reversed order (see pack_xfold_kernel): dy = kyr - (kh-1-pby)
     for (int j = 0; j < 3; ++j) {
@@ -1074,7 +1117,12 @@ extern "C" int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, 
   d.out16 = out16; d.out32 = out32;
   d.o_base = 0; d.o_x = static_cast<long long>(F) * Cout; d.o_y = static_cast<long long>(W) * Cout;
   d.o_b = static_cast<long long>(H) * W * Cout; d.fmt = fmt;
-  if (g_yhalo && (F * Cin) % 64 == 0) d.ny = kh;    // tap = kyr*3 + j, dy consecutive in kyr: the kh taps share one halo load
+  if (fmt == 2) {
+    d.x_plane = static_cast<long long>(B) * H * W * Cin;
+    d.w_plane = static_cast<long long>(kh) * 3 * cout_pad * F * Cin;
+    d.o_plane = static_cast<long long>(B) * H * W * Cout;
+  }
+  if (tuning().yhalo && (F * Cin) % 64 == 0) d.ny = kh;    // tap = kyr*3 + j, dy consecutive in kyr: the kh taps share one halo load
   return rn_conv_igemm(&d, stream);
 }
 
@@ -1108,7 +1156,12 @@ extern "C" int rn_conv2d_transpose_s2_merged(const void* x, const void* w_merged
   d.o_base = 0; d.o_x = 2LL * Cout; d.o_y = 2LL * Wo * Cout; d.o_b = Ho * Wo * Cout;
   d.o_nsplit = 2 * Cout; d.o_nhi = Wo * Cout;      // n = (ay, ax, co): row 2y+ay, columns (2x+ax)*Cout + co
   d.fmt = fmt;
-  if (Cin % 64 == 0 && g_yhalo) d.ny = 3;
+  if (fmt == 2) {
+    d.x_plane = static_cast<long long>(B) * H * W * Cin;
+    d.w_plane = 9LL * 4 * Cout * Cin;
+    d.o_plane = static_cast<long long>(B) * Ho * Wo * Cout;
+  }
+  if (Cin % 64 == 0 && tuning().yhalo) d.ny = 3;
   return rn_conv_igemm(&d, stream);
 }
 

@@ -35,10 +35,10 @@ def _store():
 
 def _packed(wvar: torch.Tensor, bvar: Optional[torch.Tensor], kind: str, stride: int = 1):
     st = _store()
-    key = (getattr(wvar, "_rn_name", id(wvar)), kind, stride, tf.COMPUTE_DTYPE)
+    key = (getattr(wvar, "_rn_name", id(wvar)), kind, stride, tf.COMPUTE_DTYPE, st.fmt)
     L = st.packed.get(key)
     if L is None:
-        L = ops.pack_conv(kind, wvar, bvar, None, stride=stride, dtype=tf.COMPUTE_DTYPE, device=st.device)
+        L = ops.pack_conv(kind, wvar, bvar, None, stride=stride, dtype=tf.COMPUTE_DTYPE, device=st.device, fmt=st.fmt)
         st.packed[key] = L
     return L
 
@@ -57,14 +57,21 @@ def _dev_vec(v, n_pad: Optional[int] = None) -> torch.Tensor:
     return d
 
 
-def _as16(x: torch.Tensor) -> torch.Tensor:
+def _as16(x):
+    """Activation in the current store's 16-bit format (fp16 tensor, or a Split16 hi/lo pair in the exact mode)."""
     x = realize(x)
+    if isinstance(x, ops.Split16):
+        if _store().fmt != 2:
+            raise TypeError("fp16 hi/lo activation fed to a fast-precision store")
+        return x
     if not isinstance(x, torch.Tensor):
         x = torch.as_tensor(np.asarray(x))
     if not x.is_cuda:
         x = x.to(_store().device)
     if x.dtype == torch.float32:
-        return ops.cast_to_16(x.contiguous(), tf.COMPUTE_DTYPE)
+        return ops.cast_to_16(x.contiguous(), tf.COMPUTE_DTYPE, fmt=_store().fmt)
+    if _store().fmt == 2:
+        return ops.cast_to_16(x.float().contiguous(), fmt=2)
     return x
 
 
@@ -93,7 +100,7 @@ def lrelu(x, leak=0.2, name="lrelu"):
     """layer_util.py:24-25 (dead code in the reference; kept for API completeness)."""
     x = realize(x)
     a = torch.full((x.shape[-1],), float(leak), dtype=torch.float32)
-    return ops.bias_act(_as16(x), None, a.to(x.device), "prelu")
+    return ops.bias_act(_as16(x), None, a.to(_store().device), "prelu")
 
 
 def prelu(x, trainable=True, alpha=None):
@@ -364,18 +371,18 @@ def _deferred_conv(kind, x, w, b, stride):
             return ops.conv2d(xt, L, act=act, residual=residual, want16=want16, want32=want32, alpha=a)
         if kind == "conv3d":
             if banded:
-                Lb = _store().packed.get(("banded", w._rn_name, stride))
+                Lb = _store().packed.get(("banded", w._rn_name, stride, _store().fmt))
                 if Lb is None:
-                    Lb = ops.BandedConv3d(w, b, dtype=tf.COMPUTE_DTYPE, device=_store().device, sz=stride)
-                    _store().packed[("banded", w._rn_name, stride)] = Lb
+                    Lb = ops.BandedConv3d(w, b, dtype=tf.COMPUTE_DTYPE, device=_store().device, sz=stride, fmt=_store().fmt)
+                    _store().packed[("banded", w._rn_name, stride, _store().fmt)] = Lb
                 return ops.conv3d_banded(xt, Lb, act=act, residual=residual, alpha=a,
                                          alpha_tag=getattr(alpha, "_rn_name", None), want16=want16, want32=want32)
             return ops.conv3d(xt, L, act=act, residual=residual, want16=want16, want32=want32, alpha=a)
         if merged:
-            Lm = _store().packed.get(("merged", w._rn_name))
+            Lm = _store().packed.get(("merged", w._rn_name, _store().fmt))
             if Lm is None:
-                Lm = ops.MergedConvT2(w, b, dtype=tf.COMPUTE_DTYPE, device=_store().device)
-                _store().packed[("merged", w._rn_name)] = Lm
+                Lm = ops.MergedConvT2(w, b, dtype=tf.COMPUTE_DTYPE, device=_store().device, fmt=_store().fmt)
+                _store().packed[("merged", w._rn_name, _store().fmt)] = Lm
             al = None
             if act == "prelu":
                 al = _dev_vec(alpha) if not isinstance(alpha, str) else torch.zeros(int(w.shape[2]), device=xt.device)
@@ -383,10 +390,10 @@ def _deferred_conv(kind, x, w, b, stride):
                                                   want16=want16, want32=want32)
         if xfold > 1:
             F = xfold
-            Lx = _store().packed.get(("xfold", w._rn_name, F))
+            Lx = _store().packed.get(("xfold", w._rn_name, F, _store().fmt))
             if Lx is None:
-                Lx = ops.XFoldConvT(w, b, F, dtype=tf.COMPUTE_DTYPE, device=_store().device)
-                _store().packed[("xfold", w._rn_name, F)] = Lx
+                Lx = ops.XFoldConvT(w, b, F, dtype=tf.COMPUTE_DTYPE, device=_store().device, fmt=_store().fmt)
+                _store().packed[("xfold", w._rn_name, F, _store().fmt)] = Lx
             al = None
             if act == "prelu":
                 al = _dev_vec(alpha) if not isinstance(alpha, str) else torch.zeros(int(w.shape[2]), device=xt.device)
@@ -457,17 +464,17 @@ def _deferred_direct3d(x, w, b, stride):
             # resample + axis transform + e_conv1 + bias + PReLU in one kernel; the 128^3 grid is never written
             bd = _dev_vec(b) if b is not None else torch.zeros(cout, device=wd.device, dtype=torch.float32)
             ad = _alpha_arg(alpha, cout) if act == "prelu" else None
-            return ops.resample_conv1(xin.voxel, xin.minv, xin.new_size, wd, bd, ad, tf.COMPUTE_DTYPE)
+            return ops.resample_conv1(xin.voxel, xin.minv, xin.new_size, wd, bd, ad, tf.COMPUTE_DTYPE, fmt=_store().fmt)
         xt = realize(xin)
         if not xt.is_cuda:
             xt = xt.to(_store().device)
         bd = _dev_vec(b) if b is not None else torch.zeros(cout, device=xt.device, dtype=torch.float32)
         if act == "prelu":
             ad = _alpha_arg(alpha, cout)
-            y = ops.conv3d_direct(xt.contiguous(), wd, bd, ad, stride, tf.COMPUTE_DTYPE)
+            y = ops.conv3d_direct(xt if isinstance(xt, ops.Split16) else xt.contiguous(), wd, bd, ad, stride, tf.COMPUTE_DTYPE, fmt=_store().fmt)
             act = None
         else:
-            y = ops.conv3d_direct(xt.contiguous(), wd, bd, None, stride, tf.COMPUTE_DTYPE)
+            y = ops.conv3d_direct(xt if isinstance(xt, ops.Split16) else xt.contiguous(), wd, bd, None, stride, tf.COMPUTE_DTYPE, fmt=_store().fmt)
         if act is not None or residual is not None or want32:
             return ops.bias_act(y, None, None, act, residual=residual, want32=want32)
         return y

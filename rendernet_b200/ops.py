@@ -24,13 +24,62 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _cuda(t: torch.Tensor, dtype=None) -> torch.Tensor:
-    if not isinstance(t, torch.Tensor) and hasattr(t, "realize"):
+class Split16:
+    """Activation of the "exact" precision mode (RN_FMT_F16X2): a pair of fp16 planes stored back to back, `planes` = [2, *shape],
+    plane 0 = hi = fp16(v), plane 1 = lo = fp16(v - hi) (~22 significant bits together).  Behaves like a tensor of the
+    logical `shape` for the handful of things the model functions do with activations."""
+
+    __slots__ = ("planes",)
+
+    def __init__(self, planes: torch.Tensor):
+        assert planes.dtype == torch.float16 and planes.shape[0] == 2 and planes.is_contiguous()
+        self.planes = planes
+
+    @property
+    def shape(self):
+        return tuple(self.planes.shape[1:])
+
+    @property
+    def dtype(self):
+        return torch.float16
+
+    @property
+    def is_cuda(self):
+        return self.planes.is_cuda
+
+    @property
+    def device(self):
+        return self.planes.device
+
+    def reshape(self, *shape):
+        shape = shape[0] if len(shape) == 1 and isinstance(shape[0], (tuple, list)) else shape
+        return Split16(self.planes.reshape(2, *shape))
+
+    def numel(self):
+        return self.planes.numel() // 2
+
+    def data_ptr(self):
+        return self.planes.data_ptr()
+
+    def float(self) -> torch.Tensor:
+        return self.planes[0].float() + self.planes[1].float()
+
+    def get_shape(self):
+        return list(self.shape)
+
+    def realize(self):
+        return self
+
+
+def _cuda(t, dtype=None):
+    if not isinstance(t, (torch.Tensor, Split16)) and hasattr(t, "realize"):
         t = t.realize()            # deferred conv output / deferred resampled grid
     if not t.is_cuda:
         raise RuntimeError("rendernet_b200 kernels need CUDA tensors (there is no CPU fallback)")
     if dtype is not None and t.dtype != dtype:
         raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if isinstance(t, Split16):
+        return t
     return t if t.is_contiguous() else t.contiguous()
 
 
@@ -40,6 +89,34 @@ def fmt_of(dtype: torch.dtype) -> int:
     if dtype == torch.bfloat16:
         return 1
     raise TypeError(f"16-bit dtype expected, got {dtype}")
+
+
+def _act_in(x, fmt: int, dtype):
+    """Validate a 16-bit activation argument against the layer's format; returns the tensor whose data_ptr is passed."""
+    x = _cuda(x)
+    if fmt == 2:
+        if not isinstance(x, Split16):
+            raise TypeError("this layer was packed for the exact mode (fp16 hi/lo pairs): pass a Split16 activation")
+        return x
+    if isinstance(x, Split16):
+        raise TypeError("fp16 hi/lo pair passed to a layer packed for single 16-bit operands")
+    if x.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {x.dtype}")
+    return x
+
+
+def _alloc16(shape, fmt: int, dtype, device):
+    if fmt == 2:
+        return torch.empty((2,) + tuple(shape), device=device, dtype=torch.float16)
+    return torch.empty(tuple(shape), device=device, dtype=dtype)
+
+
+def _wrap16(t, fmt: int):
+    return Split16(t) if (fmt == 2 and t is not None) else t
+
+
+def _unwrap(t):
+    return t.planes if isinstance(t, Split16) else t
 
 
 def round_up(v: int, m: int) -> int:
@@ -72,6 +149,7 @@ class PackedConv:
     bias: torch.Tensor             # fp32 [cout_pad]
     alpha: Optional[torch.Tensor]  # fp32 [cout_pad]
     dtype: torch.dtype
+    fmt: int = 0                   # RN_FMT_*: 0 fp16, 1 bf16, 2 fp16 hi/lo pairs (w then holds [2][...])
 
 
 def _pad_vec(v: Optional[torch.Tensor], n: int, n_pad: int, device) -> Optional[torch.Tensor]:
@@ -83,11 +161,11 @@ def _pad_vec(v: Optional[torch.Tensor], n: int, n_pad: int, device) -> Optional[
 
 
 def pack_conv(kind: str, w_tf: torch.Tensor, bias: Optional[torch.Tensor], alpha: Optional[torch.Tensor],
-              stride: int = 1, dtype: torch.dtype = torch.float16, device="cuda") -> PackedConv:
+              stride: int = 1, dtype: torch.dtype = torch.float16, device="cuda", fmt: Optional[int] = None) -> PackedConv:
     """w_tf in TF filter layout: conv2d [kh,kw,Cin,Cout]; conv3d [k,k,k,Cin,Cout];
     conv2d_transpose [kh,kw,Cout,Cin]."""
     w_tf = torch.as_tensor(w_tf, dtype=torch.float32).to(device).contiguous()
-    fmt = fmt_of(dtype)
+    fmt = fmt_of(dtype) if fmt is None else int(fmt)
     if kind == "conv2d_transpose":
         kh, kw, cout, cin = w_tf.shape
         ks = (kh, kw)
@@ -103,7 +181,7 @@ def pack_conv(kind: str, w_tf: torch.Tensor, bias: Optional[torch.Tensor], alpha
     ntaps = 1
     for k in ks:
         ntaps *= k
-    packed = torch.empty((ntaps, cout_pad, cin), device=device, dtype=dtype)
+    packed = _alloc16((ntaps, cout_pad, cin), fmt, dtype, device)
     if kind == "conv2d_transpose":
         check(lib.rn_pack_conv2d_transpose_weights(w_tf.data_ptr(), packed.data_ptr(), ks[0], ks[1], cin, cout,
                                                    cout_pad, stride, fmt, _stream()), "pack transpose")
@@ -114,61 +192,79 @@ def pack_conv(kind: str, w_tf: torch.Tensor, bias: Optional[torch.Tensor], alpha
                                        fmt, _stream()), "pack")
     b = _pad_vec(bias if bias is not None else torch.zeros(cout), cout, cout_pad, device)
     a = _pad_vec(alpha, cout, cout_pad, device)
-    return PackedConv(kind, ks, stride, cin, cout, cout_pad, packed, b, a, dtype)
+    return PackedConv(kind, ks, stride, cin, cout, cout_pad, packed, b, a, dtype, fmt)
 
 
-def _out_buffers(shape, dtype, device, want16, want32, out16, out32):
+def _out_buffers(shape, dtype, device, want16, want32, out16, out32, fmt: int = 0):
     if want16 and out16 is None:
-        out16 = torch.empty(shape, device=device, dtype=dtype)
+        out16 = _alloc16(shape, fmt, dtype, device)
+    out16 = _unwrap(out16)
     if want32 and out32 is None:
         out32 = torch.empty(shape, device=device, dtype=torch.float32)
     return out16, out32
 
 
+def _residual(residual, fmt: int):
+    """-> (tensor or None, residual_is_f32).  16-bit residuals must be in the layer's format."""
+    if residual is None:
+        return None, 0
+    residual = _cuda(residual)
+    if isinstance(residual, Split16):
+        if fmt != 2:
+            raise TypeError("fp16 hi/lo residual for a layer packed for single 16-bit operands")
+        return residual.planes, 0
+    if residual.dtype == torch.float32:
+        return residual, 1
+    if fmt == 2:
+        raise TypeError("exact-mode layers take an fp32 or an fp16 hi/lo (Split16) residual")
+    return residual, 0
+
+
+def _ret(out16, out32, want16, want32, fmt):
+    out16 = _wrap16(out16, fmt)
+    return out16 if not want32 else ((out16, out32) if want16 else out32)
+
+
 def conv2d(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, residual: Optional[torch.Tensor] = None,
            want16: bool = True, want32: bool = False, out16=None, out32=None, alpha=None):
     """SAME stride-1 conv2d + bias (+PReLU/sigmoid) (+residual).  x [B,H,W,Cin] 16-bit."""
-    x = _cuda(x, L.dtype)
+    x = _act_in(x, L.fmt, L.dtype)
     B, H, W, Cin = x.shape
     assert Cin == L.cin and L.kind == "conv2d"
-    out16, out32 = _out_buffers((B, H, W, L.cout), L.dtype, x.device, want16, want32, out16, out32)
-    res_f32 = 0
+    out16, out32 = _out_buffers((B, H, W, L.cout), L.dtype, x.device, want16, want32, out16, out32, L.fmt)
+    residual, res_f32 = _residual(residual, L.fmt)
     if residual is not None:
-        residual = _cuda(residual)
-        res_f32 = 1 if residual.dtype == torch.float32 else 0
-        assert tuple(residual.shape) == (B, H, W, L.cout)
+        assert tuple(residual.shape[-4:]) == (B, H, W, L.cout)
     a = _ACT[act]
     check(lib.rn_conv2d_same(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(),
                              _ptr(alpha if alpha is not None else L.alpha) if a == ACT_PRELU else None, a, _ptr(residual), res_f32,
                              _ptr(out16), _ptr(out32), B, H, W, Cin, L.cout, L.cout_pad, L.ksize[0], L.ksize[1],
-                             fmt_of(L.dtype), _stream()), "rn_conv2d_same")
-    return out16 if not want32 else ((out16, out32) if want16 else out32)
+                             L.fmt, _stream()), "rn_conv2d_same")
+    return _ret(out16, out32, want16, want32, L.fmt)
 
 
 def conv3d(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, residual: Optional[torch.Tensor] = None,
            want16: bool = True, want32: bool = False, out16=None, out32=None, alpha=None):
     """SAME stride-1 k^3 conv3d on the tensor pipe.  x [B,H,W,D,Cin] 16-bit."""
-    x = _cuda(x, L.dtype)
+    x = _act_in(x, L.fmt, L.dtype)
     B, H, W, D, Cin = x.shape
     assert Cin == L.cin and L.kind == "conv3d"
-    out16, out32 = _out_buffers((B, H, W, D, L.cout), L.dtype, x.device, want16, want32, out16, out32)
-    res_f32 = 0
-    if residual is not None:
-        residual = _cuda(residual)
-        res_f32 = 1 if residual.dtype == torch.float32 else 0
+    out16, out32 = _out_buffers((B, H, W, D, L.cout), L.dtype, x.device, want16, want32, out16, out32, L.fmt)
+    residual, res_f32 = _residual(residual, L.fmt)
     a = _ACT[act]
     check(lib.rn_conv3d_same(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(),
                              _ptr(alpha if alpha is not None else L.alpha) if a == ACT_PRELU else None, a, _ptr(residual), res_f32,
                              _ptr(out16), _ptr(out32), B, H, W, D, Cin, L.cout, L.cout_pad, L.ksize[0],
-                             fmt_of(L.dtype), _stream()), "rn_conv3d_same")
-    return out16 if not want32 else ((out16, out32) if want16 else out32)
+                             L.fmt, _stream()), "rn_conv3d_same")
+    return _ret(out16, out32, want16, want32, L.fmt)
 
 
 class BandedConv3d:
     """Depth-folded 3^3 SAME conv3d (rn_conv3d_banded_same): kernel-ready banded filter + per-depth expanded
     bias / alpha vectors (cached per D)."""
 
-    def __init__(self, w_tf: torch.Tensor, bias: Optional[torch.Tensor], dtype=torch.float16, device="cuda", sz: int = 1):
+    def __init__(self, w_tf: torch.Tensor, bias: Optional[torch.Tensor], dtype=torch.float16, device="cuda", sz: int = 1,
+                 fmt: Optional[int] = None):
         w_tf = torch.as_tensor(w_tf, dtype=torch.float32).to(device).contiguous()
         assert tuple(w_tf.shape[:3]) == (3, 3, 3)
         self.cin, self.cout, self.sz = int(w_tf.shape[3]), int(w_tf.shape[4]), int(sz)
@@ -176,8 +272,9 @@ class BandedConv3d:
         if nbytes < 0:
             raise ValueError("banded conv3d needs Cin | 64 and Cout | 128")
         self.dtype = dtype
-        self.w = torch.empty(nbytes // 2, device=device, dtype=dtype)
-        check(lib.rn_pack_conv3d_banded(w_tf.data_ptr(), self.w.data_ptr(), self.cin, self.cout, self.sz, fmt_of(dtype),
+        self.fmt = fmt_of(dtype) if fmt is None else int(fmt)
+        self.w = _alloc16((nbytes // 2,), self.fmt, dtype, device)
+        check(lib.rn_pack_conv3d_banded(w_tf.data_ptr(), self.w.data_ptr(), self.cin, self.cout, self.sz, self.fmt,
                                         _stream()), "rn_pack_conv3d_banded")
         self.bias = (bias if bias is not None else torch.zeros(self.cout)).to(device=device, dtype=torch.float32)
         self._full = {}
@@ -202,51 +299,55 @@ def conv3d_banded(x: torch.Tensor, L: BandedConv3d, act: Optional[str] = None,
                   residual: Optional[torch.Tensor] = None, alpha: Optional[torch.Tensor] = None, alpha_tag=None,
                   want16: bool = True, want32: bool = False, out16=None, out32=None):
     """x [B,H,W,D,Cin] 16-bit -> [B,H,W,D,Cout]; alpha is the per-Cout PReLU slope (length Cout)."""
-    x = _cuda(x, L.dtype)
+    x = _act_in(x, L.fmt, L.dtype)
     B, H, W, D, Cin = x.shape
     assert Cin == L.cin
     Do = -(-D // L.sz)
-    out16, out32 = _out_buffers((B, H, W, Do, L.cout), L.dtype, x.device, want16, want32, out16, out32)
-    res_f32 = 0
-    if residual is not None:
-        residual = _cuda(residual)
-        res_f32 = 1 if residual.dtype == torch.float32 else 0
+    out16, out32 = _out_buffers((B, H, W, Do, L.cout), L.dtype, x.device, want16, want32, out16, out32, L.fmt)
+    residual, res_f32 = _residual(residual, L.fmt)
     a = _ACT[act]
     bias_full = L.expanded(L.bias, Do, "bias")
     alpha_full = None
     if a == ACT_PRELU:
-        alpha_full = L.expanded(alpha[:L.cout], Do, ("alpha", alpha_tag if alpha_tag is not None else alpha.data_ptr()))
+        if alpha_tag is not None:
+            alpha_full = L.expanded(alpha[:L.cout], Do, ("alpha", alpha_tag))
+        else:                      # untagged alpha: never cached (a freed tensor's address can be reused)
+            v = _cuda(alpha[:L.cout].to(device=x.device, dtype=torch.float32))
+            alpha_full = torch.empty(Do * L.cout, device=x.device, dtype=torch.float32)
+            check(lib.rn_expand_channels(v.data_ptr(), alpha_full.data_ptr(), L.cout, Do, _stream()), "rn_expand_channels")
     check(lib.rn_conv3d_banded_same(x.data_ptr(), L.w.data_ptr(), bias_full.data_ptr(), _ptr(alpha_full), a,
                                     _ptr(residual), res_f32, _ptr(out16), _ptr(out32), B, H, W, D, Cin, L.cout, L.sz,
-                                    fmt_of(L.dtype), _stream()), "rn_conv3d_banded_same")
-    return out16 if not want32 else ((out16, out32) if want16 else out32)
+                                    L.fmt, _stream()), "rn_conv3d_banded_same")
+    return _ret(out16, out32, want16, want32, L.fmt)
 
 
 def conv2d_transpose(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, want16: bool = True,
                      want32: bool = False, out16=None, out32=None, alpha=None):
     """SAME transposed conv, out = in*stride.  x [B,H,W,Cin] 16-bit."""
-    x = _cuda(x, L.dtype)
+    x = _act_in(x, L.fmt, L.dtype)
     B, H, W, Cin = x.shape
     assert Cin == L.cin and L.kind == "conv2d_transpose"
     s = L.stride
-    out16, out32 = _out_buffers((B, H * s, W * s, L.cout), L.dtype, x.device, want16, want32, out16, out32)
+    out16, out32 = _out_buffers((B, H * s, W * s, L.cout), L.dtype, x.device, want16, want32, out16, out32, L.fmt)
     a = _ACT[act]
     check(lib.rn_conv2d_transpose_same(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(),
                                        _ptr(alpha if alpha is not None else L.alpha) if a == ACT_PRELU else None, a, _ptr(out16), _ptr(out32),
                                        B, H, W, Cin, L.cout, L.cout_pad, L.ksize[0], L.ksize[1], s,
-                                       fmt_of(L.dtype), _stream()), "rn_conv2d_transpose_same")
-    return out16 if not want32 else ((out16, out32) if want16 else out32)
+                                       L.fmt, _stream()), "rn_conv2d_transpose_same")
+    return _ret(out16, out32, want16, want32, L.fmt)
 
 
 class MergedConvT2:
     """k=4 stride-2 SAME transposed conv as one launch (rn_conv2d_transpose_s2_merged)."""
 
-    def __init__(self, w_tf: torch.Tensor, bias: Optional[torch.Tensor], dtype=torch.float16, device="cuda"):
+    def __init__(self, w_tf: torch.Tensor, bias: Optional[torch.Tensor], dtype=torch.float16, device="cuda",
+                 fmt: Optional[int] = None):
         w_tf = torch.as_tensor(w_tf, dtype=torch.float32).to(device).contiguous()
         assert tuple(w_tf.shape[:2]) == (4, 4)
         self.cout, self.cin, self.dtype = int(w_tf.shape[2]), int(w_tf.shape[3]), dtype
-        self.w = torch.empty((9, 4 * self.cout, self.cin), device=device, dtype=dtype)
-        check(lib.rn_pack_conv2d_transpose_s2_merged(w_tf.data_ptr(), self.w.data_ptr(), self.cin, self.cout, fmt_of(dtype),
+        self.fmt = fmt_of(dtype) if fmt is None else int(fmt)
+        self.w = _alloc16((9, 4 * self.cout, self.cin), self.fmt, dtype, device)
+        check(lib.rn_pack_conv2d_transpose_s2_merged(w_tf.data_ptr(), self.w.data_ptr(), self.cin, self.cout, self.fmt,
                                                      _stream()), "pack merged tconv")
         b = bias if bias is not None else torch.zeros(self.cout)
         self.bias = b.to(device=device, dtype=torch.float32).reshape(-1).repeat(4).contiguous()
@@ -260,35 +361,37 @@ class MergedConvT2:
 def conv2d_transpose_s2_merged(x: torch.Tensor, L: MergedConvT2, act: Optional[str] = None,
                                alpha: Optional[torch.Tensor] = None, alpha_tag=None, want16: bool = True,
                                want32: bool = False, out16=None, out32=None):
-    x = _cuda(x, L.dtype)
+    x = _act_in(x, L.fmt, L.dtype)
     B, H, W, Cin = x.shape
     assert Cin == L.cin
-    out16, out32 = _out_buffers((B, 2 * H, 2 * W, L.cout), L.dtype, x.device, want16, want32, out16, out32)
+    out16, out32 = _out_buffers((B, 2 * H, 2 * W, L.cout), L.dtype, x.device, want16, want32, out16, out32, L.fmt)
     a = _ACT[act]
     alpha4 = None
     if a == ACT_PRELU:
-        key = alpha_tag if alpha_tag is not None else alpha.data_ptr()
-        alpha4 = L._alpha.get(key)
-        if alpha4 is None:
+        alpha4 = L._alpha.get(alpha_tag) if alpha_tag is not None else None
+        if alpha4 is None:     # untagged alphas are recomputed, never cached by address
             alpha4 = alpha.to(device=x.device, dtype=torch.float32).reshape(-1)[: L.cout].repeat(4).contiguous()
-            L._alpha[key] = alpha4
+            if alpha_tag is not None:
+                L._alpha[alpha_tag] = alpha4
     check(lib.rn_conv2d_transpose_s2_merged(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(), _ptr(alpha4), a, _ptr(out16),
-                                            _ptr(out32), B, H, W, Cin, L.cout, fmt_of(L.dtype), _stream()),
+                                            _ptr(out32), B, H, W, Cin, L.cout, L.fmt, _stream()),
           "rn_conv2d_transpose_s2_merged")
-    return out16 if not want32 else ((out16, out32) if want16 else out32)
+    return _ret(out16, out32, want16, want32, L.fmt)
 
 
 class XFoldConvT:
     """Stride-1 transposed conv with thin channels, x-folded (rn_conv2d_transpose_s1_xfold)."""
 
-    def __init__(self, w_tf: torch.Tensor, bias: Optional[torch.Tensor], F: int, dtype=torch.float16, device="cuda"):
+    def __init__(self, w_tf: torch.Tensor, bias: Optional[torch.Tensor], F: int, dtype=torch.float16, device="cuda",
+                 fmt: Optional[int] = None):
         w_tf = torch.as_tensor(w_tf, dtype=torch.float32).to(device).contiguous()
         self.kh, self.kw, self.cout, self.cin = (int(v) for v in w_tf.shape)
         self.F, self.dtype = F, dtype
+        self.fmt = fmt_of(dtype) if fmt is None else int(fmt)
         self.cout_pad = round_up(F * self.cout, 16)
-        self.w = torch.empty((self.kh * 3, self.cout_pad, F * self.cin), device=device, dtype=dtype)
+        self.w = _alloc16((self.kh * 3, self.cout_pad, F * self.cin), self.fmt, dtype, device)
         check(lib.rn_pack_conv2d_transpose_xfold(w_tf.data_ptr(), self.w.data_ptr(), self.kh, self.kw, self.cin, self.cout,
-                                                 F, self.cout_pad, fmt_of(dtype), _stream()), "pack xfold")
+                                                 F, self.cout_pad, self.fmt, _stream()), "pack xfold")
         b = bias if bias is not None else torch.zeros(self.cout)
         self.bias = self.tiled(b, device)
         self._alpha = {}
@@ -305,30 +408,32 @@ class XFoldConvT:
 
 def conv2d_transpose_xfold(x: torch.Tensor, L: XFoldConvT, act: Optional[str] = None, alpha: Optional[torch.Tensor] = None,
                            alpha_tag=None, want16: bool = True, want32: bool = False, out16=None, out32=None):
-    x = _cuda(x, L.dtype)
+    x = _act_in(x, L.fmt, L.dtype)
     B, H, W, Cin = x.shape
     assert Cin == L.cin and W % L.F == 0
-    out16, out32 = _out_buffers((B, H, W, L.cout), L.dtype, x.device, want16, want32, out16, out32)
+    out16, out32 = _out_buffers((B, H, W, L.cout), L.dtype, x.device, want16, want32, out16, out32, L.fmt)
     a = _ACT[act]
     alpha_x = None
     if a == ACT_PRELU:
-        key = alpha_tag if alpha_tag is not None else alpha.data_ptr()
-        alpha_x = L._alpha.get(key)
-        if alpha_x is None:
+        alpha_x = L._alpha.get(alpha_tag) if alpha_tag is not None else None
+        if alpha_x is None:    # untagged alphas are recomputed, never cached by address
             alpha_x = L.tiled(alpha, x.device)
-            L._alpha[key] = alpha_x
+            if alpha_tag is not None:
+                L._alpha[alpha_tag] = alpha_x
     check(lib.rn_conv2d_transpose_s1_xfold(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(), _ptr(alpha_x), a, _ptr(out16),
-                                           _ptr(out32), B, H, W, Cin, L.cout, L.kh, L.kw, L.F, L.cout_pad, fmt_of(L.dtype),
+                                           _ptr(out32), B, H, W, Cin, L.cout, L.kh, L.kw, L.F, L.cout_pad, L.fmt,
                                            _stream()), "rn_conv2d_transpose_s1_xfold")
-    return out16 if not want32 else ((out16, out32) if want16 else out32)
+    return _ret(out16, out32, want16, want32, L.fmt)
 
 
 def conv_igemm_raw(x, w_packed, bias, taps, ndim, B, H, W, D, Cin, Cout, cout_pad, out16=None, out32=None,
                    alpha=None, act=ACT_NONE, residual=None, o=None, fmt=0, force_bn=0, force_kps=0, max_ctas=0,
-                   cluster=0, cta_group=0, ny=0, tile_w=0, msub=0):
-    """Direct access to rn_conv_igemm for tests / tuning.  taps: list of (dx,dy,dz)."""
+                   cluster=0, cta_group=0, ny=0, tile_w=0, msub=0, epi_groups=0, res_prefetch=0, tma_store=0):
+    """Direct access to rn_conv_igemm for tests / tuning.  taps: list of (dx,dy,dz).  fmt 2: x, w_packed, out16 and a
+    16-bit residual are [2, ...] hi/lo plane tensors (or Split16)."""
     n = len(taps)
     arr = (C.c_int8 * (3 * n))(*[v for t in taps for v in t])
+    x, w_packed, out16, residual = _unwrap(x), _unwrap(w_packed), _unwrap(out16), _unwrap(residual)
     d = rn_conv_desc()
     d.ndim, d.B, d.H, d.W, d.D = ndim, B, H, W, D
     d.Cin, d.Cout, d.cout_pad, d.ntaps = Cin, Cout, cout_pad, n
@@ -348,15 +453,23 @@ def conv_igemm_raw(x, w_packed, bias, taps, ndim, B, H, W, D, Cin, Cout, cout_pa
     d.cluster = cluster
     d.cta_group = cta_group
     d.ny, d.tile_w, d.msub = ny, tile_w, msub
+    d.epi_groups, d.res_prefetch, d.tma_store = epi_groups, res_prefetch, tma_store
+    if fmt == 2:
+        d.x_plane = x.numel() // 2
+        d.w_plane = w_packed.numel() // 2
+        d.o_plane = (out16.numel() // 2) if out16 is not None else 0
     check(lib.rn_conv_igemm(C.byref(d), _stream()), "rn_conv_igemm")
 
 
 # --------------------------------------------------------------------------------------- thin conv3d
 def conv3d_direct(x: torch.Tensor, w_tf: torch.Tensor, bias: torch.Tensor, alpha: Optional[torch.Tensor],
-                  stride: Sequence[int], dtype: torch.dtype = torch.float16) -> torch.Tensor:
+                  stride: Sequence[int], dtype: torch.dtype = torch.float16, fmt: Optional[int] = None):
     """CUDA-core SAME conv3d + bias + PReLU for the thin first layers.  x fp32 or 16-bit
-    [B,H,W,D,Cin]; w_tf fp32 [k,k,k,Cin,Cout]; returns 16-bit."""
+    [B,H,W,D,Cin]; w_tf fp32 [k,k,k,Cin,Cout]; returns 16-bit (a Split16 pair for fmt 2)."""
     x = _cuda(x)
+    fmt = fmt_of(dtype) if fmt is None else int(fmt)
+    if isinstance(x, Split16) != (fmt == 2 and x.dtype != torch.float32):
+        raise TypeError("conv3d_direct: 16-bit input format does not match fmt")
     w_tf = _cuda(w_tf, torch.float32)
     bias = _cuda(bias, torch.float32)
     B, H, W, D, Cin = x.shape
@@ -364,15 +477,15 @@ def conv3d_direct(x: torch.Tensor, w_tf: torch.Tensor, bias: torch.Tensor, alpha
     Cout = w_tf.shape[4]
     sy, sx, sz = stride
     Ho, Wo, Do = -(-H // sy), -(-W // sx), -(-D // sz)
-    out = torch.empty((B, Ho, Wo, Do, Cout), device=x.device, dtype=dtype)
+    out = _alloc16((B, Ho, Wo, Do, Cout), fmt, dtype, x.device)
     check(lib.rn_conv3d_direct(x.data_ptr(), 1 if x.dtype == torch.float32 else 0, w_tf.data_ptr(),
                                bias.data_ptr(), _ptr(alpha), out.data_ptr(), B, H, W, D, Cin, Cout, k, sy, sx, sz,
-                               fmt_of(dtype), _stream()), "rn_conv3d_direct")
-    return out
+                               fmt, _stream()), "rn_conv3d_direct")
+    return _wrap16(out, fmt)
 
 
 def resample_conv1(vox: torch.Tensor, minv: torch.Tensor, new_size: int, w_tf: torch.Tensor, bias: torch.Tensor,
-                   alpha: Optional[torch.Tensor], dtype: torch.dtype = torch.float16) -> torch.Tensor:
+                   alpha: Optional[torch.Tensor], dtype: torch.dtype = torch.float16, fmt: Optional[int] = None):
     """Fused resampler + axis transform + e_conv1 (5^3 s2, 1->8) + bias + PReLU; empty tiles skip the conv.
     vox fp32 [B,S,S,S,1], minv fp32 [B,3,4], w_tf fp32 [5,5,5,1,8] -> 16-bit [B,new/2,new/2,new/2,8]."""
     vox = _cuda(vox, torch.float32)
@@ -383,11 +496,12 @@ def resample_conv1(vox: torch.Tensor, minv: torch.Tensor, new_size: int, w_tf: t
     if tuple(vox.shape) != (B, S, S, S, 1) or tuple(w_tf.shape) != (5, 5, 5, 1, 8) or tuple(minv.shape) != (B, 3, 4):
         raise ValueError(f"resample_conv1: unsupported shapes {tuple(vox.shape)}, {tuple(w_tf.shape)}")
     No = new_size // 2
-    out = torch.empty((B, No, No, No, 8), device=vox.device, dtype=dtype)
+    fmt = fmt_of(dtype) if fmt is None else int(fmt)
+    out = _alloc16((B, No, No, No, 8), fmt, dtype, vox.device)
     check(lib.rn_resample_conv1_fused(vox.data_ptr(), minv.data_ptr(), w_tf.data_ptr(), bias.data_ptr(), _ptr(alpha),
-                                      out.data_ptr(), B, S, new_size, fmt_of(dtype), _stream()),
+                                      out.data_ptr(), B, S, new_size, fmt, _stream()),
           "rn_resample_conv1_fused")
-    return out
+    return _wrap16(out, fmt)
 
 
 def binvox_decode(pairs_list, dims, fix_coords: bool = True, device="cuda") -> torch.Tensor:
@@ -416,17 +530,20 @@ def binvox_decode(pairs_list, dims, fix_coords: bool = True, device="cuda") -> t
 
 
 # --------------------------------------------------------------------------------------- misc
-def cast_to_16(x: torch.Tensor, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+def cast_to_16(x: torch.Tensor, dtype: torch.dtype = torch.float16, fmt: Optional[int] = None):
+    """fp32 -> 16-bit (fmt 2: fp16 hi/lo pair, returned as Split16)."""
     x = _cuda(x, torch.float32)
-    out = torch.empty(x.shape, device=x.device, dtype=dtype)
-    check(lib.rn_cast_f32_to_16(x.data_ptr(), out.data_ptr(), x.numel(), x.numel(), fmt_of(dtype), _stream()), "cast")
-    return out
+    fmt = fmt_of(dtype) if fmt is None else int(fmt)
+    out = _alloc16(x.shape, fmt, dtype, x.device)
+    check(lib.rn_cast_f32_to_16(x.data_ptr(), out.data_ptr(), x.numel(), x.numel(), fmt, _stream()), "cast")
+    return _wrap16(out, fmt)
 
 
-def cast_to_f32(x: torch.Tensor) -> torch.Tensor:
+def cast_to_f32(x) -> torch.Tensor:
     x = _cuda(x)
+    fmt = 2 if isinstance(x, Split16) else fmt_of(x.dtype)
     out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
-    check(lib.rn_cast_16_to_f32(x.data_ptr(), out.data_ptr(), x.numel(), fmt_of(x.dtype), _stream()), "cast")
+    check(lib.rn_cast_16_to_f32(x.data_ptr(), out.data_ptr(), x.numel(), fmt, _stream()), "cast")
     return out
 
 
@@ -449,12 +566,17 @@ def phong_composite(img: torch.Tensor, light_dir: torch.Tensor, light_col: torch
     return (out, u8) if want_u8 else out
 
 
-def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], alpha: Optional[torch.Tensor], act: Optional[str],
-             residual: Optional[torch.Tensor] = None, want32: bool = False):
-    """y = act(x + bias[c]) + residual on a 16-bit channel-last tensor (rn_bias_act_16)."""
+def bias_act(x, bias: Optional[torch.Tensor], alpha: Optional[torch.Tensor], act: Optional[str],
+             residual=None, want32: bool = False, fmt: int = 0):
+    """y = act(x + bias[c]) + residual on a 16-bit channel-last tensor (rn_bias_act_16).  An fp32 `x` is first cast to
+    the 16-bit format `fmt`; a Split16 `x` selects fmt 2."""
     x = _cuda(x)
-    if x.dtype == torch.float32:
-        x = cast_to_16(x)
+    if isinstance(x, Split16):
+        fmt = 2
+    elif x.dtype == torch.float32:
+        x = cast_to_16(x, fmt=fmt)
+    else:
+        fmt = fmt_of(x.dtype)
     C_ = x.shape[-1]
     a = _ACT[act]
     dev = x.device
@@ -464,13 +586,14 @@ def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], alpha: Optional[torc
         alpha = _cuda(alpha.to(device=dev, dtype=torch.float32))
     if residual is not None:
         residual = _cuda(residual)
-        if residual.dtype != x.dtype:
-            residual = cast_to_16(residual.float(), x.dtype) if residual.dtype == torch.float32 else residual.to(x.dtype)
-    out16 = None if want32 else torch.empty_like(x)
+        if isinstance(residual, Split16) != (fmt == 2) or (fmt != 2 and residual.dtype != x.dtype):
+            residual = cast_to_16(residual.float() if not isinstance(residual, torch.Tensor) or residual.dtype != torch.float32
+                                  else residual, fmt=fmt)
+    out16 = None if want32 else _alloc16(x.shape, fmt, torch.float16 if fmt != 1 else torch.bfloat16, dev)
     out32 = torch.empty(x.shape, device=dev, dtype=torch.float32) if want32 else None
     check(lib.rn_bias_act_16(x.data_ptr(), _ptr(bias), _ptr(alpha), a, _ptr(residual), _ptr(out16), _ptr(out32),
-                             x.numel(), C_, fmt_of(x.dtype), _stream()), "rn_bias_act_16")
-    return out32 if want32 else out16
+                             x.numel(), C_, fmt, _stream()), "rn_bias_act_16")
+    return out32 if want32 else _wrap16(out16, fmt)
 
 
 # --------------------------------------------------------------------------------------- texture decoder (config 4)

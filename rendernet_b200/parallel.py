@@ -50,15 +50,19 @@ def all_gather_images(local: torch.Tensor, n_total: Optional[int] = None, group=
 
 
 class PeerImageGather:
-    """All-gather of the per-rank image shards WITHOUT SM time: every rank owns a full [world*b, ...] buffer, exported to
-    its peers over CUDA IPC at start-up; each step a rank writes its shard into every peer's buffer with plain
-    device-to-device copies (copy engines over NVLink / NVSwitch) on a side stream.
+    """All-gather of the per-rank image shards WITHOUT SM time: every rank owns TWO full [world*b, ...] buffers (step parity),
+    exported to its peers over CUDA IPC at start-up; each step a rank writes its shard into every peer's buffer of that
+    parity with plain device-to-device copies (copy engines over NVLink / NVSwitch) on a side stream.
 
     An alternative to ncclAllGather that leaves all 148 SMs to the persistent convolution kernels of the next step (NCCL's
-    kernels hold a few SMs while they run).  Measured at 2 GPUs it makes no difference (41.6 vs 41.3 ms/step: the NCCL
-    gather already hides completely behind the step), so `bench.py` keeps NCCL as the default and offers this as
-    `--gather peer`.  Single node only (IPC); construction raises if peer access or IPC is unavailable, and the caller
-    falls back to `all_gather_images` (NCCL)."""
+    kernels hold a few SMs while they run); `ShardedRenderEngine(gather="peer")` / `bench.py --gather peer`.
+
+    Write-after-read safety across processes: a rank may only overwrite a peer's parity-p buffer with step i+2 after that
+    peer has finished consuming step i from it.  Every rank therefore (1) records `consumed` once it is done with the
+    buffer returned by the previous same-parity gather (`release()`), and (2) runs a one-element NCCL all-reduce on the side
+    stream, AFTER waiting for that event and BEFORE its copies: the all-reduce completes only when every rank has passed
+    its own `consumed` wait.  Single node only (IPC); construction raises if peer access or IPC is unavailable and the
+    caller falls back to `all_gather_images` (NCCL)."""
 
     def __init__(self, shard_shape, dtype=torch.float32, device=None, group=None):
         if not dist.is_initialized():
@@ -68,53 +72,187 @@ class PeerImageGather:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.b = int(shard_shape[0])
-        self.full = torch.empty((self.world * self.b,) + tuple(shard_shape[1:]), device=self.device, dtype=dtype)
-        handles = [None] * self.world
-        dist.all_gather_object(handles, reduce_tensor(self.full), group=group)
-        self.peers = []
-        for r, (rebuild, rargs) in enumerate(handles):
-            if r == self.rank:
-                self.peers.append(self.full)
-                continue
-            t = rebuild(*rargs)                                  # aliases rank r's buffer (cudaIpcOpenMemHandle)
-            if not torch.cuda.can_device_access_peer(self.device.index, t.device.index):
-                raise RuntimeError(f"no peer access {self.device} -> {t.device}")
-            self.peers.append(t)
+        shape = (self.world * self.b,) + tuple(shard_shape[1:])
+        self.full = [torch.empty(shape, device=self.device, dtype=dtype) for _ in range(2)]
+        self.peers = []                                          # peers[parity][rank] aliases that rank's buffer
+        for par in range(2):
+            handles = [None] * self.world
+            dist.all_gather_object(handles, reduce_tensor(self.full[par]), group=group)
+            views = []
+            for r, (rebuild, rargs) in enumerate(handles):
+                if r == self.rank:
+                    views.append(self.full[par])
+                    continue
+                t = rebuild(*rargs)                              # aliases rank r's buffer (cudaIpcOpenMemHandle)
+                if not torch.cuda.can_device_access_peer(self.device.index, t.device.index):
+                    raise RuntimeError(f"no peer access {self.device} -> {t.device}")
+                views.append(t)
+            self.peers.append(views)
         self.stream = torch.cuda.Stream(device=self.device)
         self.done = torch.cuda.Event()
         self.done.record(torch.cuda.current_stream(self.device))
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in self.consumed:
+            e.record(torch.cuda.current_stream(self.device))
+        self._flag = torch.zeros(1, device=self.device)
+        self.steps = 0
 
     def gather_async(self, local: torch.Tensor, ready: Optional[torch.cuda.Event] = None) -> torch.cuda.Event:
-        """Queue the copies of `local` ([b, ...], this rank's shard) into every rank's buffer on the side stream, after
-        `ready` (default: everything queued so far on the current stream).  Returns the event that marks this rank's
-        outgoing copies complete; incoming shards are complete once every rank's event has fired (`fence()`)."""
+        """Queue the copies of `local` ([b, ...], this rank's shard) into every rank's buffer of this step's parity on the
+        side stream, after `ready` (default: everything queued so far on the current stream).  Returns the event that marks
+        this rank's outgoing copies complete; incoming shards are complete once every rank's event has fired (`fence()`).
+        The gathered tensor of this step is `self.full[parity]` (`self.last`)."""
         if ready is None:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(self.device))
+        par = self.steps % 2
+        self.steps += 1
         lo = self.rank * self.b
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
+            self.stream.wait_event(self.consumed[par])           # this rank is done with the step-(i-2) contents ...
+            dist.all_reduce(self._flag, group=self.group)        # ... and so is every other rank (see class docstring)
             for k in range(self.world):                          # own copy first, then peers rank+1, rank+2, ...: no hot spot
-                self.peers[(self.rank + k) % self.world][lo:lo + self.b].copy_(local, non_blocking=True)
+                self.peers[par][(self.rank + k) % self.world][lo:lo + self.b].copy_(local, non_blocking=True)
             self.done = torch.cuda.Event()
             self.done.record(self.stream)
+        self.last = self.full[par]
         return self.done
 
+    def release(self, stream: Optional[torch.cuda.Stream] = None):
+        """The consumer has finished (stream-ordered on `stream`, default the current one) with the buffer of the most recent
+        gather: peers may overwrite it two steps from now."""
+        par = (self.steps - 1) % 2
+        self.consumed[par] = torch.cuda.Event()
+        self.consumed[par].record(stream if stream is not None else torch.cuda.current_stream(self.device))
+
     def fence(self):
-        """Block until every rank's outgoing copies have landed (so `self.full` is complete everywhere)."""
+        """Block until every rank's outgoing copies have landed (so `self.last` is complete everywhere)."""
         self.done.synchronize()
         dist.barrier(group=self.group)
 
     def gather(self, local: torch.Tensor) -> torch.Tensor:
         self.gather_async(local)
         self.fence()
-        return self.full
+        self.release()
+        return self.last
 
     def close(self):
         """Drop the peer mappings before the owners free their buffers."""
         self.fence()
-        self.peers = [self.full]
+        self.peers = [[self.full[0]], [self.full[1]]]
         dist.barrier(group=self.group)
+
+
+class ShardedRenderEngine:
+    """Batch-sharded rendering over the ranks of a process group: every rank renders ITS `engine.B` items
+    with its own weight replica (no data-path collective); the only exchange is the all-gather of the output image batch,
+    issued on a side stream so that it overlaps the next step's convolutions.
+
+        sh = ShardedRenderEngine(engine, gather="nccl")      # "nccl" | "peer" (copy engines over CUDA IPC) | "none"
+        sh.step()                    # inputs already resident: graph replay + async gather
+        sh.submit(vox, poses)        # or the pipelined host path: H2D -> graph -> gather (D2H of the local shard overlaps)
+        full = sh.wait()             # [world*B,512,512,3] of the LAST step, complete on this rank's current stream
+
+    With world == 1 (or no process group) it degenerates to the engine itself."""
+
+    def __init__(self, engine, gather: str = "nccl", group=None):
+        if gather not in ("nccl", "peer", "none"):
+            raise ValueError("gather must be nccl | peer | none")
+        self.engine, self.group = engine, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.kind = gather if self.world > 1 else "none"
+        self.dev = engine.device
+        outs = list(engine.outputs) if not isinstance(engine.out, torch.Tensor) else [engine.out]   # Texture engine: 2 images
+        self._multi = not isinstance(engine.out, torch.Tensor)
+        self.peer = None
+        self.kind_note = {"nccl": "NCCL all-gather", "none": "no gather (per-rank outputs only)"}.get(self.kind, "")
+        if self.kind == "peer" and len(outs) != 1:
+            self.kind, self.kind_note = "nccl", "NCCL all-gather (peer gather handles one output tensor)"
+        if self.kind == "peer":
+            ok = 1
+            try:
+                self.peer = PeerImageGather(tuple(outs[0].shape), outs[0].dtype, self.dev, group)
+            except Exception as e:  # noqa: BLE001
+                import sys
+                print(f"[ShardedRenderEngine] rank {self.rank}: peer gather unavailable ({type(e).__name__}: {e}); using NCCL",
+                      file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)          # all ranks must agree
+            if int(flag.item()) == 0:
+                self.peer, self.kind, self.kind_note = None, "nccl", "NCCL all-gather (peer gather unavailable)"
+            else:
+                self.kind_note = "copy-engine P2P writes over NVLink (CUDA IPC)"
+        if self.kind == "nccl":
+            self.comm = torch.cuda.Stream(device=self.dev)
+            self.gathered = [torch.empty((self.world * o.shape[0],) + tuple(o.shape[1:]), device=self.dev, dtype=o.dtype)
+                             for o in outs]
+        if self.kind != "none":
+            self.src = [torch.empty_like(o) for o in outs]       # the graph overwrites the engine's outputs every step
+            self.ev_ready, self.ev_done = torch.cuda.Event(), torch.cuda.Event()
+            self.ev_done.record(torch.cuda.current_stream(self.dev))
+
+    def _engine_outs(self):
+        return list(self.engine.out) if self._multi else [self.engine.out]
+
+    def verify_peer_against_nccl(self) -> bool:
+        """One-off check of the peer path against ncclAllGather on a recognisable pattern (all ranks call it)."""
+        if self.peer is None:
+            return True
+        b = self.src[0].shape[0]
+        pat = torch.full_like(self.src[0], float(self.rank + 1))
+        pat[:, 0, 0, 0] = torch.arange(b, device=self.dev, dtype=pat.dtype)
+        got = self.peer.gather(pat).clone()
+        want = torch.empty((self.world * b,) + tuple(pat.shape[1:]), device=self.dev, dtype=pat.dtype)
+        dist.all_gather_into_tensor(want, pat, group=self.group)
+        same = torch.tensor([int(torch.equal(got, want))], device=self.dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN, group=self.group)
+        return int(same.item()) == 1
+
+    def _gather(self):
+        if self.kind == "none":
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.ev_done)                 # the previous gather has consumed self.src
+        for s_, o in zip(self.src, self._engine_outs()):
+            s_.copy_(o)
+        self.ev_ready.record(cur)
+        if self.peer is not None:
+            self.peer.release(cur)                   # nothing on this rank reads the older same-parity buffer any more
+            self.ev_done = self.peer.gather_async(self.src[0], self.ev_ready)
+        else:
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(self.ev_ready)
+                for g, s_ in zip(self.gathered, self.src):
+                    dist.all_gather_into_tensor(g, s_, group=self.group)
+                self.ev_done = torch.cuda.Event()
+                self.ev_done.record(self.comm)
+
+    def step(self):
+        self.engine.step_device()
+        self._gather()
+
+    def submit(self, *host_inputs) -> int:
+        t = self.engine.submit(*host_inputs)
+        self._gather()
+        return t
+
+    def wait(self):
+        """Make the current stream wait for the last step's gather; returns the gathered batch (a tuple for the two-output
+        Texture engine; this rank's own images when there is no gather)."""
+        if self.kind == "none":
+            return self.engine.out
+        torch.cuda.current_stream(self.dev).wait_event(self.ev_done)
+        if self.peer is not None:
+            return self.peer.last
+        return tuple(self.gathered) if self._multi else self.gathered[0]
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
 
 def broadcast_weight_dict(weights: Optional[Dict[str, np.ndarray]], src: int = 0, device="cpu", group=None):

@@ -8,8 +8,9 @@ each convolution call returns a *deferred* tensor (`Deferred`) whose epilogue is
 into the convolution kernel's fused epilogue instead of becoming a separate pass over HBM.  A deferred
 tensor is realised (its kernel launched) the moment anything else consumes it.
 
-Variables live in a process-wide store keyed by the reference's scoped names
-("encoder/res2_3/con1_3X3/weights", ...); kernel-ready packed copies are cached per variable.
+Variables live in a `VariableStore` keyed by the reference's scoped names ("encoder/res2_3/con1_3X3/weights", ...);
+kernel-ready packed copies are cached per variable.  There is a default store (what `tf.reset_default_graph()` and the
+bare model functions use) and every engine owns its own, made current with `use_store` around its forward pass.
 """
 from __future__ import annotations
 
@@ -27,33 +28,83 @@ float16 = torch.float16
 bfloat16 = torch.bfloat16
 int32 = torch.int32
 
-COMPUTE_DTYPE = torch.float16   # operand / activation storage type of the tensor-core path
+COMPUTE_DTYPE = torch.float16   # element type of every 16-bit plane of the tensor-core path
+PRECISIONS = ("fast", "exact")
 
 
 # ------------------------------------------------------------------------------------------ variables
 class VariableStore:
-    def __init__(self):
+    """Variables (reference names -> fp32 host tensors) + their kernel-ready packed copies for ONE model replica.
+    `precision`: "fast" = fp16 operands / stored activations (RN_FMT_F16); "exact" = fp16 hi/lo pairs with three
+    tensor-core products per tap (RN_FMT_F16X2), matching the reference's fp32 convolutions to ~1e-6."""
+
+    def __init__(self, precision: str = "fast", device: str = "cuda", seed: int = 0):
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}, got {precision!r}")
         self.vars: Dict[str, torch.Tensor] = {}
         self.packed: Dict[str, object] = {}
         self.scope: List[str] = []
-        self.rng = np.random.default_rng(0)
-        self.device = "cuda"
+        self.rng = np.random.default_rng(seed)
+        self.device = device
+        self.precision = precision
+        self.strict = False            # True: get_variable raises for a name that is not among the loaded weights
+        self.loaded: set = set()       # names installed by load_weight_dict
+        self.consumed: set = set()     # loaded names a model function has asked for
+
+    @property
+    def fmt(self) -> int:
+        return 2 if self.precision == "exact" else 0
 
     def reset(self, seed: int = 0):
         self.vars.clear()
         self.packed.clear()
         self.scope = []
         self.rng = np.random.default_rng(seed)
+        self.strict = False
+        self.loaded = set()
+        self.consumed = set()
 
     def full_name(self, name: str) -> str:
         return "/".join(self.scope + [name])
 
+    def unused(self) -> List[str]:
+        """Loaded weights that no model function has consumed (a wrong prefix / spelling shows up here)."""
+        return sorted(self.loaded - self.consumed)
 
-_STORE = VariableStore()
+
+_DEFAULT_STORE = VariableStore()
+_STORE = _DEFAULT_STORE              # the CURRENT store (module functions below act on it)
 
 
 def get_store() -> VariableStore:
     return _STORE
+
+
+@contextlib.contextmanager
+def use_store(store: VariableStore):
+    """Make `store` the current variable store for the duration of the block (every engine owns one, so engines with
+    different weights / precisions can coexist in a process)."""
+    global _STORE
+    prev = _STORE
+    _STORE = store
+    try:
+        yield store
+    finally:
+        _STORE = prev
+
+
+def compute_fmt() -> int:
+    """RN_FMT_* of the current store's 16-bit tensors (0 fp16, 2 fp16 hi/lo pairs)."""
+    return _STORE.fmt
+
+
+def set_precision(precision: str):
+    """Precision of the current store; packed weights are re-derived on the next use."""
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}, got {precision!r}")
+    if precision != _STORE.precision:
+        _STORE.precision = precision
+        _STORE.packed.clear()
 
 
 def reset_default_graph(seed: int = 0):
@@ -67,21 +118,32 @@ def _npz_key(name: str) -> str:
     return n.replace("/", "_")
 
 
-def load_weight_dict(weights: Dict[str, np.ndarray]):
+def load_weight_dict(weights: Dict[str, np.ndarray], strict: bool = True):
     """Install pretrained/seeded weights.  Keys may be TF variable names
-    ('encoder/e_conv1/e_conv1/weights[:0]') or the npz-dir spelling ('e_conv1_e_conv1_weights')."""
+    ('encoder/e_conv1/e_conv1/weights[:0]') or the npz-dir spelling ('e_conv1_e_conv1_weights').
+    strict (default): a model function that asks for a variable which is NOT among the loaded ones raises KeyError
+    instead of silently falling back to a random initialiser, and `get_store().unused()` lists loaded entries nothing
+    consumed."""
     _STORE.packed.clear()
     for k, v in weights.items():
         k = k[:-2] if k.endswith(":0") else k
         _STORE.vars[k] = torch.as_tensor(np.asarray(v), dtype=torch.float32)
+        _STORE.loaded.add(k)
+    _STORE.strict = bool(strict)
 
 
 def _lookup(full: str) -> Optional[torch.Tensor]:
     v = _STORE.vars.get(full)
-    if v is None:
-        v = _STORE.vars.get(_npz_key(full))
-        if v is not None:
-            _STORE.vars[full] = v
+    if v is not None:
+        if full in _STORE.loaded:
+            _STORE.consumed.add(full)
+        return v
+    alt = _npz_key(full)
+    v = _STORE.vars.get(alt)
+    if v is not None:
+        _STORE.vars[full] = v
+        if alt in _STORE.loaded:
+            _STORE.consumed.add(alt)
     return v
 
 
@@ -124,6 +186,9 @@ def get_variable(name, shape=None, dtype=None, initializer=None, trainable=True,
     full = _STORE.full_name(name)
     v = _lookup(full)
     if v is None:
+        if _STORE.strict and not isinstance(initializer, (np.ndarray, torch.Tensor, list, tuple)):
+            raise KeyError(f"variable {full!r} (npz spelling {_npz_key(full)!r}) is not among the loaded weights; "
+                           f"refusing to fall back to a random initialiser (load_weight_dict(..., strict=False) allows it)")
         if callable(initializer):
             shp = tuple(int(s) for s in (shape if isinstance(shape, (list, tuple)) else [shape]))
             v = torch.from_numpy(initializer(shp))
@@ -179,6 +244,15 @@ def realize(x):
     return x.realize() if hasattr(x, "realize") else x
 
 
+Split16 = ops.Split16      # "exact" precision activation: fp16 hi/lo planes [2, *shape]
+
+
+def to_float(x) -> torch.Tensor:
+    """fp32 copy of any activation (16-bit tensor, fp16 hi/lo pair, deferred tensor) -- for tests / stage dumps."""
+    x = realize(x)
+    return x.float() if isinstance(x, (Split16, torch.Tensor)) else torch.as_tensor(x).float()
+
+
 def shape(x):
     return list(x.shape)
 
@@ -188,9 +262,7 @@ def cast(x, dtype):
     tensors pass through untouched because the add happens in fp32 inside the epilogue anyway."""
     if isinstance(x, Deferred):
         return x
-    if dtype in (torch.float32, "float32") and x.dtype in (torch.float16, torch.bfloat16):
-        return x            # kept in 16-bit storage; arithmetic on it is fp32 in-kernel
-    return x
+    return x                # 16-bit (or hi/lo pair) storage is kept; arithmetic on it is fp32 in-kernel
 
 
 def add(a, b):

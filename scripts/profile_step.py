@@ -18,9 +18,10 @@ from rendernet_b200.engine import RenderEngine  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=24)
 ap.add_argument("--steps", type=int, default=1)
+ap.add_argument("--precision", default="exact", choices=["exact", "fast"])
 args = ap.parse_args()
 B = args.batch
-eng = RenderEngine(None, B, use_graph=False, seed=0)
+eng = RenderEngine(None, B, use_graph=False, seed=0, precision=args.precision)
 rng0, rng1 = np.random.default_rng(0), np.random.default_rng(1)
 vox = (rng0.random((B, 64, 64, 64, 1)) < 0.10).astype(np.float32)
 poses = np.stack([rng1.uniform(0, 2 * np.pi, B), (90 - rng1.uniform(10, 170, B)) * np.pi / 180,

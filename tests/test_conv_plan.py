@@ -69,16 +69,10 @@ def test_plan_banded_res1_and_thin_layers():
 
 
 def test_plan_tuning_switches_and_validation():
-    prev = lib.rn_set_epilogue_groups(1)
-    try:
-        assert plan(Cin=1024, Cout=1024, k=1)["epilogue_groups"] == 1
-    finally:
-        lib.rn_set_epilogue_groups(prev)
-    prev = lib.rn_set_default_cta_group(1)
-    try:
-        assert plan(Cin=1024, Cout=1024, k=3, ny=3)["cta_group"] == 1
-    finally:
-        lib.rn_set_default_cta_group(prev)
+    # per-call overrides travel in the descriptor (the library has no mutable global state)
+    assert plan(Cin=1024, Cout=1024, k=1, epi_groups=1)["epilogue_groups"] == 1
+    assert plan(Cin=1024, Cout=1024, k=3, ny=3, cta_group=1)["cta_group"] == 1
+    assert plan(Cin=1024, Cout=1024, k=3, ny=3, tma_store=-1)["epilogue_mode"] == 0
     assert plan(Cin=1024, Cout=1024, k=3, ny=3, out32=True)["epilogue_mode"] == 0      # fp32 output: direct stores
     plan(Cin=1000, expect=-4)                        # Cin % 16
     plan(Cout=1030, cout_pad=1024, expect=-4)        # Cout > cout_pad
@@ -88,3 +82,25 @@ def test_plan_tuning_switches_and_validation():
     plan(k=3, ny=3, taps=[(0, 0, 0)] * 9, expect=-14)      # taps not ordered for halo sharing
     plan(msub=3, expect=-16)
     assert lib.rn_conv_plan(None, (C.c_int * 16)(), 16) == -1
+
+
+def test_plan_exact_mode_split_operands():
+    """RN_FMT_F16X2: every tap becomes 3 pseudo-taps (x_hi.w_hi, x_lo.w_hi, x_hi.w_lo); split kernels exist for CTA pairs or
+    single CTAs with two epilogue groups, direct-store epilogue; the LO-plane offsets are mandatory."""
+    planes = dict(fmt=2, x_plane=24 * 64 * 64 * 1024, w_plane=9 * 1024 * 1024, o_plane=24 * 64 * 64 * 1024)
+    p = plan(Cin=1024, Cout=1024, k=3, ny=3, **planes)
+    assert (p["bn"], p["cluster"], p["cta_group"], p["epilogue_groups"], p["ny"], p["epilogue_mode"]) == (256, 2, 2, 2, 3, 0)
+    assert p["stages"] >= 3 and p["smem_bytes"] <= 232448
+    q = plan(Cin=1024, Cout=1024, k=1, **planes)
+    assert (q["bn"], q["cta_group"], q["epilogue_groups"]) == (256, 2, 2)
+    b = plan(Cin=192, Cout=1024, k=3, ny=3, force_bn=128, x_channels=1024, w_banded=1, **planes)
+    assert (b["bn"], b["cta_group"], b["msub"], b["epilogue_groups"], b["ny"]) == (128, 2, 2, 2, 3)
+    odd = plan(B=1, H=24, W=8, Cin=64, Cout=256, k=3, fmt=2, x_plane=8 * 24 * 64, w_plane=9 * 256 * 64, o_plane=8 * 24 * 256)
+    assert (odd["cluster"], odd["cta_group"], odd["epilogue_groups"]) in ((1, 1, 2), (2, 2, 2))
+    k4 = plan(Cin=64, Cout=64, k=4, taps=[(kx - 1, ky - 1, 0) for ky in range(4) for kx in range(4)], fmt=2,
+              x_plane=24 * 64 * 64 * 64, w_plane=16 * 64 * 64, o_plane=24 * 64 * 64 * 64)       # 16 taps x 3 = 48 pseudo-taps
+    assert k4["stages"] >= 2
+    plan(Cin=64, Cout=64, k=3, fmt=2, expect=-18)                                   # LO-plane offsets missing
+    plan(ndim=3, D=8, Cin=32, Cout=32, k=3, taps=[(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)],
+         fmt=2, x_plane=8, w_plane=8, o_plane=8, expect=-3)                         # 27 taps x 3 > 48
+    plan(fmt=3, expect=-17)
