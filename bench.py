@@ -112,10 +112,22 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def _use_all_host_threads():
-    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must still use every host core."""
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must still use every PHYSICAL host core (one thread per
+    hyper-thread is 10x slower for oneDNN convolutions: 0.026 vs 0.30 renders/s measured on the 64-core / 128-thread box)."""
     import torch
-    n = os.cpu_count() or 1
-    torch.set_num_threads(n)
+    n = None
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+    except Exception:
+        pass
+    if not n:
+        n = max(1, (os.cpu_count() or 2) // 2)
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    torch.set_num_threads(int(n))
     return torch.get_num_threads()
 
 
@@ -160,7 +172,7 @@ def run_reference(args, rank, world):
         t8, _ = cpu_forward_timer(args.config, 1, warm=0, batch=8)
         b8 = {"value": 8.0 / float(t8[0]), "unit": unit, "sample": "one B=8 forward after the timed steps"}
     sample = (f"{args.steps} timed B=1 forwards (one 64^3 voxel -> 512^2 image each) of the same synthetic workload on "
-              f"{cores} host threads (torch.set_num_threads(os.cpu_count()), so torchrun's OMP_NUM_THREADS=1 does not apply); "
+              f"{cores} host threads (torch.set_num_threads(physical cores), so torchrun's OMP_NUM_THREADS=1 does not apply); "
               f"oracle/rendernet_oracle.py = CPU restatement of the TF-1 graph (TensorFlow-1 itself is not installable)")
     line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -54,6 +54,13 @@ long long rn_launch_count(void);
 int rn_resample_f32(const float* vox, const float* minv, float* out, int B, int C, int size, int new_size,
                     int transform, void* stream);
 
+/* tf_interpolate (tools/resampling_voxel_grid.py:381-486) at caller-supplied coordinates: x, y, z [B*n_per_item] fp32
+ * (sampler x addresses the LAST spatial axis of vox, z the first: flat = b*S^3 + z*S^2 + y*S + x, :427-449),
+ * out [B*n_per_item, C] fp32.  Bit-faithful to the reference arithmetic everywhere, including the clamped-corner weight
+ * cancellation outside the cube (which rn_resample_f32 replaces by exact zeros). */
+int rn_interpolate_f32(const float* vox, const float* x, const float* y, const float* z, float* out, int B, int C, int size,
+                       long long n_per_item, void* stream);
+
 /* ---- weight packing -------------------------------------------------------------------------------
  * TF filter (fp32) -> [n_sel][cout_pad][Cin] 16-bit, K-major rows for the tensor-core kernel.
  *   transposed=0: w is [ntaps_total][Cin][Cout]   (tf.nn.conv2d / conv3d filters, layer_util.py:162,243)
@@ -117,6 +124,13 @@ typedef struct rn_conv_desc {
   int epi_groups, res_prefetch, tma_store;
 } rn_conv_desc;
 int rn_conv_igemm(const rn_conv_desc* d, void* stream);
+/* Per-call overrides of the launch heuristics for the reference-shaped wrappers below (their last argument before
+ * `stream`; NULL = library defaults).  0 = default for every field; cluster 1/2/4; cta_group 1/2; kps = k-groups per
+ * pipeline stage; msub 1/2 M sub-tiles; epilogue_groups 1/2; res_prefetch / tma_store / yhalo: 1 = on, -1 = off.
+ * Every combination computes bit-identical results (tests/test_gpu_kernels.py::*_bit_identical). */
+typedef struct rn_tuning {
+  int cluster, cta_group, kps, msub, epilogue_groups, res_prefetch, tma_store, yhalo;
+} rn_tuning;
 /* The launch plan rn_conv_igemm would use for `d`, without touching the device (works on a host without a GPU; the SM
  * count then defaults to 148).  Pointers in `d` are only tested for null / 16-byte alignment.  out[0..n_out) receives
  * {N tile, cluster size, cta_group, M sub-tiles, epilogue warp groups, ny (halo sharing), tile W, tile H, tile D,
@@ -129,10 +143,10 @@ int rn_conv_plan(const rn_conv_desc* d, int* out, int n_out);
  * layer_util.conv3d (:228), projection_unit's 1x1 conv (:8-22). */
 int rn_conv2d_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
                    const void* residual, int residual_is_f32, void* out16, float* out32, int B, int H, int W,
-                   int Cin, int Cout, int cout_pad, int kh, int kw, int fmt, void* stream);
+                   int Cin, int Cout, int cout_pad, int kh, int kw, int fmt, const rn_tuning* tune, void* stream);
 int rn_conv3d_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
                    const void* residual, int residual_is_f32, void* out16, float* out32, int B, int H, int W,
-                   int D, int Cin, int Cout, int cout_pad, int k, int fmt, void* stream);
+                   int D, int Cin, int Cout, int cout_pad, int k, int fmt, const rn_tuning* tune, void* stream);
 /* layer_util.conv3d 3^3 SAME stride 1 (res_block_3d, tools/layer_util.py:60-88; RenderNet_Shader.py:45-64) as a
  * depth-folded 2-D convolution: the D axis is part of the GEMM's N (128 = (128/Cout) output depths x Cout) and K
  * ((128/Cout + 2) input depths x Cin, padded to 64-element blocks), so TMA moves full 128-byte rows and each
@@ -146,7 +160,7 @@ int rn_pack_conv3d_banded(const float* w, void* packed, int Cin, int Cout, int s
 int rn_expand_channels(const float* v, float* v_full, int C, int D, void* stream);
 int rn_conv3d_banded_same(const void* x, const void* w_banded, const float* bias_full, const float* alpha_full,
                           int act, const void* residual, int residual_is_f32, void* out16, float* out32, int B,
-                          int H, int W, int D, int Cin, int Cout, int sz, int fmt, void* stream);
+                          int H, int W, int D, int Cin, int Cout, int sz, int fmt, const rn_tuning* tune, void* stream);
 
 /* slim.conv2d_transpose / layer_util.conv2d_transpose (layer_util.py:186; RenderNet_Shader.py:106-129),
  * SAME, out = in*stride.  w_packed holds the stride^2 phase filters back to back, as produced by
@@ -155,7 +169,7 @@ int rn_pack_conv2d_transpose_weights(const float* w, void* packed, int kh, int k
                                      int cout_pad, int stride, int fmt, void* stream);
 int rn_conv2d_transpose_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
                              void* out16, float* out32, int B, int H, int W, int Cin, int Cout, int cout_pad,
-                             int kh, int kw, int stride, int fmt, void* stream);
+                             int kh, int kw, int stride, int fmt, const rn_tuning* tune, void* stream);
 
 /* Stride-2, k = 4 SAME transposed conv (e_conv7/8/9, RenderNet_Shader.py:106-119) as ONE launch: rows = input pixels,
  * N = (ay, ax, co) = 4*Cout, 9 taps (dy,dx in {-1,0,1}) with the unused phase/tap combinations zero in the packed
@@ -164,7 +178,7 @@ int rn_conv2d_transpose_same(const void* x, const void* w_packed, const float* b
 int rn_pack_conv2d_transpose_s2_merged(const float* w, void* packed, int Cin, int Cout, int fmt, void* stream);
 int rn_conv2d_transpose_s2_merged(const void* x, const void* w_merged, const float* bias4, const float* alpha4, int act,
                                   void* out16, float* out32, int B, int H, int W, int Cin, int Cout, int fmt,
-                                  void* stream);
+                                  const rn_tuning* tune, void* stream);
 
 /* Thin-channel stride-1 transposed conv (e_conv10 32->16, e_conv11 16->3 at 512^2; RenderNet_Shader.py:122-129) with
  * F = 64/Cin adjacent x-pixels folded into the channel axis: rows of the implicit GEMM are pixel groups, K = F*Cin
@@ -175,7 +189,7 @@ int rn_pack_conv2d_transpose_xfold(const float* w, void* packed, int kh, int kw,
                                    int fmt, void* stream);
 int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, const float* bias_x, const float* alpha_x, int act,
                                  void* out16, float* out32, int B, int H, int W, int Cin, int Cout, int kh, int kw, int F,
-                                 int cout_pad, int fmt, void* stream);
+                                 int cout_pad, int fmt, const rn_tuning* tune, void* stream);
 
 /* ---- thin 3-D convolutions on CUDA cores (too few channels for the tensor pipe) ---------------------
  * tf.nn.conv3d SAME + bias + PReLU (layer_util.py:228-265, RenderNet_Shader.py:36-43): e_conv1 (Cin=1,

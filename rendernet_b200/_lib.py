@@ -31,7 +31,12 @@ class rn_conv_desc(C.Structure):
     ]
 
 
+class rn_tuning(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("cluster", "cta_group", "kps", "msub", "epilogue_groups", "res_prefetch", "tma_store", "yhalo")]
+
+
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_tp = C.POINTER(rn_tuning)
 PLAN_FIELDS = ("bn", "cluster", "cta_group", "msub", "epilogue_groups", "ny", "tile_w", "tile_h", "tile_d", "kps", "stages",
                "smem_bytes", "grid", "tiles", "epilogue_mode", "row_bytes")
 
@@ -41,25 +46,26 @@ SIGNATURES = {
     "rn_error_string": (C.c_char_p, [_i]),
     "rn_launch_count": (_ll, []),
     "rn_resample_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rn_interpolate_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _vp]),
     "rn_pack_conv_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "rn_cast_f32_to_16": (_i, [_vp, _vp, _ll, _ll, _i, _vp]),
     "rn_cast_16_to_f32": (_i, [_vp, _vp, _ll, _i, _vp]),
     "rn_bias_act_16": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "rn_conv_igemm": (_i, [C.POINTER(rn_conv_desc), _vp]),
     "rn_conv_plan": (_i, [C.POINTER(rn_conv_desc), C.POINTER(C.c_int), _i]),
-    "rn_conv2d_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "rn_conv3d_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rn_conv2d_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _tp, _vp]),
+    "rn_conv3d_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _tp, _vp]),
     "rn_conv3d_banded_bytes": (_ll, [_i, _i, _i]),
     "rn_pack_conv3d_banded": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rn_expand_channels": (_i, [_vp, _vp, _i, _i, _vp]),
-    "rn_conv3d_banded_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rn_conv3d_banded_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _tp, _vp]),
     "rn_pack_conv2d_transpose_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "rn_conv2d_transpose_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rn_conv2d_transpose_same": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _tp, _vp]),
     "rn_pack_conv2d_transpose_s2_merged": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "rn_conv2d_transpose_s2_merged": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "rn_conv2d_transpose_s2_merged": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _tp, _vp]),
     "rn_xfold_factor": (_i, [_i, _i]),
     "rn_pack_conv2d_transpose_xfold": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "rn_conv2d_transpose_s1_xfold": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rn_conv2d_transpose_s1_xfold": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _tp, _vp]),
     "rn_conv3d_direct": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rn_resample_conv1_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rn_binvox_decode": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -200,18 +200,22 @@ static int plan_conv(const rn_conv_desc* d, IgemmParams& p, ConvPlan& pl) {
       p.tap_b[t] = static_cast<uint8_t>(t);
     }
   } else {
-    // Split ("exact") mode: tap t = ky*nx0 + kx0 becomes the three pseudo-taps ky*(3*nx0) + 3*kx0 + {0,1,2} =
-    // (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo) with the same input offset; the ky-major order that y-halo sharing needs
-    // is preserved, so the three terms of a filter column still share one activation load each.
+    // Split ("exact") mode: tap t = ky*nx0 + kx0 becomes three pseudo-taps with the same input offset:
+    // (x_lo, w_hi), (x_hi, w_lo), (x_hi, w_hi).  Order along the k loop: ALL correction terms of the tile first, the hi.hi
+    // terms last.  The tensor core's fp32 accumulation truncates (round toward zero, one truncation per MMA step), so the
+    // error of a step scales with the magnitude the accumulator has at that moment: while only 2^-11-sized corrections
+    // have been summed it is negligible, and only the hi.hi third of the steps runs against the full-size accumulator
+    // (measured on the 3x3 1024->1024 trunk: profiles/r02_exact_accumulation_order.log).  Within each of the three
+    // passes the ky-major order that y-halo sharing needs is preserved: pseudo kx' = j*nx0 + kx0, tap = ky*(3*nx0) + kx'.
     const int nx0 = d->ntaps / p.ny;
     for (int t = 0; t < d->ntaps; ++t) {
       const int ky = t / nx0, kx0 = t % nx0;
-      for (int j = 0; j < 3; ++j) {
-        const int q = ky * (3 * nx0) + 3 * kx0 + j;
+      for (int j = 0; j < 3; ++j) {          // j = 0: x_lo.w_hi, 1: x_hi.w_lo, 2: x_hi.w_hi
+        const int q = ky * (3 * nx0) + j * nx0 + kx0;
         p.tap[q][0] = d->taps[3 * t + 0];
         p.tap[q][1] = d->taps[3 * t + 1];
         p.tap[q][2] = d->taps[3 * t + 2];
-        p.tap[q][3] = static_cast<int8_t>(j == 1 ? 1 : (j == 2 ? 2 : 0));
+        p.tap[q][3] = static_cast<int8_t>(j == 0 ? 1 : (j == 1 ? 2 : 0));
         p.tap_b[q] = static_cast<uint8_t>(t);
       }
     }

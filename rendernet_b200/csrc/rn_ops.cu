@@ -61,6 +61,14 @@ __device__ __forceinline__ float load16(const uint16_t* __restrict__ p, long lon
 }
 
 // ------------------------------------------------------------------------------------------ resampler
+// One row of p_src = Minv . (gx, gy, gz, 1) (tools/resampling_voxel_grid.py:605) in the arithmetic of a float32 matmul that
+// accumulates over k = 0..3 with fused multiply-adds -- what NumPy/OpenBLAS (and therefore the oracle) computes: verified
+// bit for bit against np.matmul on all 128^3 grid points for five poses.  The order matters: axis-aligned poses put sample
+// points exactly ON the clamp discontinuity at 0 / size-1, where one ulp decides between a voxel value and zero.
+__device__ __forceinline__ float sample_coord(float m0, float m1, float m2, float m3, float gx, float gy, float gz) {
+  return __fadd_rn(__fmaf_rn(m2, gz, __fmaf_rn(m1, gy, __fmul_rn(m0, gx))), m3);
+}
+
 // One warp per output row (innermost output axis); each lane owns 4 consecutive points per iteration so
 // C=1 rows are written with one 16-byte store per lane (512 B per warp instruction).
 template <int C>
@@ -81,9 +89,6 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
   // grid point (gx, gy, gz) = (k, j, i) (:500-512); with the axis transform N[b,p,q,r] = T[b,q,nsz-1-p,r]
   const float gy = transform ? static_cast<float>(nsz - 1 - o1) : static_cast<float>(o2);
   const float gz = transform ? static_cast<float>(o2) : static_cast<float>(o1);
-  const float bx = fmaf(m01, gy, fmaf(m02, gz, m03));
-  const float by = fmaf(m11, gy, fmaf(m12, gz, m13));
-  const float bz = fmaf(m21, gy, fmaf(m22, gz, m23));
   const float lim = static_cast<float>(size - 1);
   const float* vb = vox + static_cast<size_t>(b) * size * size * size * C;
   float* orow = out + static_cast<size_t>(warp_global) * nsz * C;
@@ -93,7 +98,9 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float gx = static_cast<float>(r0 + u);
-      const float x = fmaf(m00, gx, bx), y = fmaf(m10, gx, by), z = fmaf(m20, gx, bz);
+      const float x = sample_coord(m00, m01, m02, m03, gx, gy, gz);
+      const float y = sample_coord(m10, m11, m12, m13, gx, gy, gz);
+      const float z = sample_coord(m20, m21, m22, m23, gx, gy, gz);
 #pragma unroll
       for (int c = 0; c < C; ++c) res[u][c] = 0.f;
       // clamp-then-weight rule (:410-485): both clamped corners coincide outside [0,size-1) -> weights cancel
@@ -145,6 +152,50 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
         }
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ tf_interpolate
+// tools/resampling_voxel_grid.py:381-486 at caller-supplied sample coordinates, operation for operation: BOTH corners of
+// every axis are clamped to [0, size-1] (:410-422) and the weights come from the CLAMPED corners (:465-482), so a point
+// outside the cube gets two coincident corners whose weights cancel up to fp32 rounding (the reference's <= 2e-4 |v|
+// "noise", reproduced here bit for bit -- unlike resample_kernel, which writes exact zeros there).  One thread per point.
+__global__ void __launch_bounds__(256) interpolate_kernel(const float* __restrict__ vox, const float* __restrict__ xs,
+                                                          const float* __restrict__ ys, const float* __restrict__ zs,
+                                                          float* __restrict__ out, long long n_total, long long n_per_item,
+                                                          int C, int size) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n_total) return;
+  const long long b = i / n_per_item;
+  const float x = xs[i], y = ys[i], z = zs[i];
+  const int mx = size - 1;
+  int x0 = static_cast<int>(floorf(x)), y0 = static_cast<int>(floorf(y)), z0 = static_cast<int>(floorf(z));
+  int x1 = x0 + 1, y1 = y0 + 1, z1 = z0 + 1;
+  x0 = min(max(x0, 0), mx); x1 = min(max(x1, 0), mx);
+  y0 = min(max(y0, 0), mx); y1 = min(max(y1, 0), mx);
+  z0 = min(max(z0, 0), mx); z1 = min(max(z1, 0), mx);
+  const float x0f = static_cast<float>(x0), x1f = static_cast<float>(x1), y0f = static_cast<float>(y0);
+  const float y1f = static_cast<float>(y1), z0f = static_cast<float>(z0), z1f = static_cast<float>(z1);
+  const float ax = __fsub_rn(x1f, x), bx = __fsub_rn(x, x0f), ay = __fsub_rn(y1f, y), by = __fsub_rn(y, y0f);
+  const float az = __fsub_rn(z1f, z), bz = __fsub_rn(z, z0f);
+  const float wa = __fmul_rn(__fmul_rn(ax, ay), az), wb = __fmul_rn(__fmul_rn(ax, by), az);
+  const float wc = __fmul_rn(__fmul_rn(bx, ay), az), wd = __fmul_rn(__fmul_rn(bx, by), az);
+  const float we = __fmul_rn(__fmul_rn(ax, ay), bz), wf = __fmul_rn(__fmul_rn(ax, by), bz);
+  const float wg = __fmul_rn(__fmul_rn(bx, ay), bz), wh = __fmul_rn(__fmul_rn(bx, by), bz);
+  const float* vb = vox + static_cast<size_t>(b) * size * size * size * C;
+  auto at = [&](int zz, int yy, int xx) { return vb + ((static_cast<size_t>(zz) * size + yy) * size + xx) * C; };
+  const float *pa = at(z0, y0, x0), *pb = at(z0, y1, x0), *pc = at(z0, y0, x1), *pd = at(z0, y1, x1);
+  const float *pe = at(z1, y0, x0), *pf = at(z1, y1, x0), *pg = at(z1, y0, x1), *ph = at(z1, y1, x1);
+  for (int c = 0; c < C; ++c) {
+    float s = __fmul_rn(wa, __ldg(pa + c));                    // add_n order a..h (:485)
+    s = __fadd_rn(s, __fmul_rn(wb, __ldg(pb + c)));
+    s = __fadd_rn(s, __fmul_rn(wc, __ldg(pc + c)));
+    s = __fadd_rn(s, __fmul_rn(wd, __ldg(pd + c)));
+    s = __fadd_rn(s, __fmul_rn(we, __ldg(pe + c)));
+    s = __fadd_rn(s, __fmul_rn(wf, __ldg(pf + c)));
+    s = __fadd_rn(s, __fmul_rn(wg, __ldg(pg + c)));
+    s = __fadd_rn(s, __fmul_rn(wh, __ldg(ph + c)));
+    out[i * C + c] = s;
   }
 }
 
@@ -400,10 +451,9 @@ __global__ void __launch_bounds__(256) resample_conv1_kernel(const float* __rest
       if (p >= 0 && p < nsz && q >= 0 && q < nsz && r >= 0 && r < nsz) {
         // N[b,p,q,r] = T[b,q,nsz-1-p,r]; grid point (gx,gy,gz) = (r, nsz-1-p, q)
         const float gx = static_cast<float>(r), gy = static_cast<float>(nsz - 1 - p), gz = static_cast<float>(q);
-        const float bx = fmaf(m01, gy, fmaf(m02, gz, m03));
-        const float by = fmaf(m11, gy, fmaf(m12, gz, m13));
-        const float bz = fmaf(m21, gy, fmaf(m22, gz, m23));
-        const float x = fmaf(m00, gx, bx), y = fmaf(m10, gx, by), z = fmaf(m20, gx, bz);
+        const float x = sample_coord(m00, m01, m02, m03, gx, gy, gz);
+        const float y = sample_coord(m10, m11, m12, m13, gx, gy, gz);
+        const float z = sample_coord(m20, m21, m22, m23, gx, gy, gz);
         if (x >= 0.f && x < lim && y >= 0.f && y < lim && z >= 0.f && z < lim) {
           const float x0f = floorf(x), y0f = floorf(y), z0f = floorf(z);
           const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f), z0 = static_cast<int>(z0f);
@@ -779,6 +829,18 @@ static int pack_conv_weights_impl(const float* w, void* packed, int ntaps_total,
   return static_cast<int>(cudaGetLastError());
 }
 
+extern "C" int rn_interpolate_f32(const float* vox, const float* x, const float* y, const float* z, float* out, int B, int C,
+                                  int size, long long n_per_item, void* stream) {
+  if (!vox || !x || !y || !z || !out || B < 1 || C < 1 || size < 2 || n_per_item < 1) return -1;
+  const long long n = static_cast<long long>(B) * n_per_item;
+  const long long blocks = (n + 255) / 256;
+  if (blocks > 0x7fffffffLL) return -2;
+  interpolate_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(vox, x, y, z, out, n, n_per_item, C,
+                                                                                         size);
+  RN_COUNT_LAUNCH();
+  return static_cast<int>(cudaGetLastError());
+}
+
 extern "C" int rn_pack_conv_weights(const float* w, void* packed, int ntaps_total, int Cin, int Cout, int cout_pad,
                                     int transposed, const int* tap_sel, int n_sel, int fmt, void* stream) {
   return pack_conv_weights_impl(w, packed, ntaps_total, Cin, Cout, cout_pad, transposed, tap_sel, n_sel, fmt, 0, stream);
@@ -815,9 +877,18 @@ extern "C" int rn_bias_act_16(const void* x, const float* bias, const float* alp
 }
 
 // ---------------------------------------------------------------------------------- igemm wrappers
+static void apply_tuning(rn_conv_desc& d, const rn_tuning* t) {
+  if (t == nullptr) return;
+  d.cluster = t->cluster; d.cta_group = t->cta_group; d.force_kps = t->kps; d.msub = t->msub;
+  d.epi_groups = t->epilogue_groups; d.res_prefetch = t->res_prefetch; d.tma_store = t->tma_store;
+}
+static bool want_yhalo(const rn_tuning* t) { return (t != nullptr && t->yhalo != 0) ? t->yhalo > 0 : tuning().yhalo != 0; }
+static int want_epi_groups(const rn_tuning* t) { return (t != nullptr && t->epilogue_groups != 0) ? t->epilogue_groups : tuning().epi_groups; }
+
 extern "C" int rn_conv2d_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
                               const void* residual, int residual_is_f32, void* out16, float* out32, int B, int H,
-                              int W, int Cin, int Cout, int cout_pad, int kh, int kw, int fmt, void* stream) {
+                              int W, int Cin, int Cout, int cout_pad, int kh, int kw, int fmt, const rn_tuning* tune,
+                              void* stream) {
   if (kh * kw > kMaxTaps || kh < 1 || kw < 1) return -20;
   int8_t taps[kMaxTaps * 3];
   const int pby = (kh - 1) / 2, pbx = (kw - 1) / 2;  // SAME, stride 1: before = (k-1)//2
@@ -838,13 +909,15 @@ extern "C" int rn_conv2d_same(const void* x, const void* w_packed, const float* 
     d.w_plane = static_cast<long long>(kh) * kw * cout_pad * Cin;
     d.o_plane = static_cast<long long>(B) * H * W * Cout;
   }
-  if (kh == 3 && Cin % 64 == 0 && tuning().yhalo) d.ny = 3;   // taps are already ordered ky*kw + kx with dy = ky - 1
+  apply_tuning(d, tune);
+  if (kh == 3 && Cin % 64 == 0 && want_yhalo(tune)) d.ny = 3;   // taps are already ordered ky*kw + kx with dy = ky - 1
   return rn_conv_igemm(&d, stream);
 }
 
 extern "C" int rn_conv3d_same(const void* x, const void* w_packed, const float* bias, const float* alpha, int act,
                               const void* residual, int residual_is_f32, void* out16, float* out32, int B, int H,
-                              int W, int D, int Cin, int Cout, int cout_pad, int k, int fmt, void* stream) {
+                              int W, int D, int Cin, int Cout, int cout_pad, int k, int fmt, const rn_tuning* tune,
+                              void* stream) {
   if (k * k * k > kMaxTaps || k < 1) return -20;
   int8_t taps[kMaxTaps * 3];
   const int pb = (k - 1) / 2;
@@ -866,6 +939,7 @@ extern "C" int rn_conv3d_same(const void* x, const void* w_packed, const float* 
     d.w_plane = static_cast<long long>(k) * k * k * cout_pad * Cin;
     d.o_plane = static_cast<long long>(B) * H * W * D * Cout;
   }
+  apply_tuning(d, tune);
   return rn_conv_igemm(&d, stream);
 }
 
@@ -913,7 +987,8 @@ extern "C" int rn_pack_conv2d_transpose_weights(const float* w, void* packed, in
 
 extern "C" int rn_conv2d_transpose_same(const void* x, const void* w_packed, const float* bias, const float* alpha,
                                         int act, void* out16, float* out32, int B, int H, int W, int Cin, int Cout,
-                                        int cout_pad, int kh, int kw, int stride, int fmt, void* stream) {
+                                        int cout_pad, int kh, int kw, int stride, int fmt, const rn_tuning* tune,
+                                        void* stream) {
   if (kh * kw > kMaxTaps || stride < 1) return -20;
   const int Ho = H * stride, Wo = W * stride;
   size_t off = 0;
@@ -938,6 +1013,7 @@ extern "C" int rn_conv2d_transpose_same(const void* x, const void* w_packed, con
         d.w_plane = static_cast<long long>(kh) * kw * cout_pad * Cin;   // LO plane follows ALL phases of the HI plane
         d.o_plane = static_cast<long long>(B) * Ho * Wo * Cout;
       }
+      apply_tuning(d, tune);
       int r = rn_conv_igemm(&d, stream);
       if (r != 0) return r;
       off += static_cast<size_t>(pt.n) * cout_pad * Cin;
@@ -977,7 +1053,7 @@ extern "C" int rn_expand_channels(const float* v, float* v_full, int C, int D, v
 extern "C" int rn_conv3d_banded_same(const void* x, const void* w_banded, const float* bias_full,
                                      const float* alpha_full, int act, const void* residual, int residual_is_f32,
                                      void* out16, float* out32, int B, int H, int W, int D, int Cin, int Cout,
-                                     int sz, int fmt, void* stream) {
+                                     int sz, int fmt, const rn_tuning* tune, void* stream) {
   if (rn_conv3d_banded_bytes(Cin, Cout, sz) < 0) return -30;
   int Do, pz;
   same_pad(D, 3, sz, &Do, &pz);                     // TF SAME along z: out = ceil(D/sz), pad-before pz
@@ -1007,14 +1083,15 @@ extern "C" int rn_conv3d_banded_same(const void* x, const void* w_banded, const 
     d.w_plane = rn_conv3d_banded_bytes(Cin, Cout, sz) / 2;
     d.o_plane = static_cast<long long>(B) * H * W * Fo;
   }
-  if (tuning().yhalo) d.ny = 3;
+  apply_tuning(d, tune);
+  if (want_yhalo(tune)) d.ny = 3;
   // With a residual the epilogue is the critical path of these short-K tiles, and the paired (cta_group::2) form couples
   // the two CTAs' epilogues through the shared accumulator hand-over: multicast clusters of independent CTAs are 17 %
   // faster there (0.296 vs 0.355 ms), while the PReLU-only convs prefer the pair (0.238 vs 0.270 ms);
   // profiles/r01_probe_res1_cg.log.  Results are bit-identical either way.
   // (With two epilogue warp groups the pair form drains fast enough again, so the override only applies to the
   // single-group configuration.)
-  if (residual != nullptr && tuning().epi_groups == 1) d.cta_group = 1;
+  if (residual != nullptr && want_epi_groups(tune) == 1 && d.cta_group == 0) d.cta_group = 1;
   return rn_conv_igemm(&d, stream);
 }
 
@@ -1101,7 +1178,8 @@ extern "C" int rn_pack_conv2d_transpose_xfold(const float* w, void* packed, int 
 // per-Cout vectors tiled F times and zero padded to cout_pad (rn_expand_channels + padding by the caller).
 extern "C" int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, const float* bias_x, const float* alpha_x,
                                             int act, void* out16, float* out32, int B, int H, int W, int Cin, int Cout,
-                                            int kh, int kw, int F, int cout_pad, int fmt, void* stream) {
+                                            int kh, int kw, int F, int cout_pad, int fmt, const rn_tuning* tune,
+                                            void* stream) {
   if (F < 2 || W % F != 0 || kh * 3 > kMaxTaps) return -20;
   int8_t taps[kMaxTaps * 3];
   const int pby = (kh - 1) / 2;                     // SAME stride-1 transposed: dy = pb - ky
@@ -1122,7 +1200,8 @@ extern "C" int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, 
     d.w_plane = static_cast<long long>(kh) * 3 * cout_pad * F * Cin;
     d.o_plane = static_cast<long long>(B) * H * W * Cout;
   }
-  if (tuning().yhalo && (F * Cin) % 64 == 0) d.ny = kh;    // tap = kyr*3 + j, dy consecutive in kyr: the kh taps share one halo load
+  apply_tuning(d, tune);
+  if (want_yhalo(tune) && (F * Cin) % 64 == 0) d.ny = kh;    // tap = kyr*3 + j, dy consecutive in kyr: the kh taps share one halo load
   return rn_conv_igemm(&d, stream);
 }
 
@@ -1139,7 +1218,7 @@ extern "C" int rn_pack_conv2d_transpose_s2_merged(const float* w, void* packed, 
 
 extern "C" int rn_conv2d_transpose_s2_merged(const void* x, const void* w_merged, const float* bias4,
                                              const float* alpha4, int act, void* out16, float* out32, int B, int H,
-                                             int W, int Cin, int Cout, int fmt, void* stream) {
+                                             int W, int Cin, int Cout, int fmt, const rn_tuning* tune, void* stream) {
   if (Cout % 16 != 0) return -20;
   int8_t taps[27];
   for (int ky = 0; ky < 3; ++ky)
@@ -1161,7 +1240,8 @@ extern "C" int rn_conv2d_transpose_s2_merged(const void* x, const void* w_merged
     d.w_plane = 9LL * 4 * Cout * Cin;
     d.o_plane = static_cast<long long>(B) * Ho * Wo * Cout;
   }
-  if (Cin % 64 == 0 && tuning().yhalo) d.ny = 3;
+  apply_tuning(d, tune);
+  if (Cin % 64 == 0 && want_yhalo(tune)) d.ny = 3;
   return rn_conv_igemm(&d, stream);
 }
 

@@ -10,7 +10,7 @@ from typing import Optional, Sequence
 
 import torch
 
-from ._lib import check, lib, rn_conv_desc
+from ._lib import check, lib, rn_conv_desc, rn_tuning
 
 ACT_NONE, ACT_PRELU, ACT_SIGMOID = 0, 1, 2
 _ACT = {None: ACT_NONE, "none": ACT_NONE, "prelu": ACT_PRELU, "sigmoid": ACT_SIGMOID}
@@ -119,6 +119,18 @@ def _unwrap(t):
     return t.planes if isinstance(t, Split16) else t
 
 
+def _tune(tune):
+    """dict of rn_tuning fields (tests / A-B runs) -> ctypes pointer, None -> NULL (library defaults)."""
+    if not tune:
+        return None
+    t = rn_tuning()
+    for k, v in tune.items():
+        if not hasattr(t, k):
+            raise KeyError(f"unknown tuning field {k!r}")
+        setattr(t, k, int(v))
+    return C.byref(t)
+
+
 def round_up(v: int, m: int) -> int:
     return (v + m - 1) // m * m
 
@@ -132,6 +144,20 @@ def resample(vox: torch.Tensor, minv: torch.Tensor, new_size: int, transform: bo
     out = torch.empty((B, new_size, new_size, new_size, Cc), device=vox.device, dtype=torch.float32)
     check(lib.rn_resample_f32(vox.data_ptr(), minv.data_ptr(), out.data_ptr(), B, Cc, S, new_size,
                               1 if transform else 0, _stream()), "rn_resample_f32")
+    return out
+
+
+def interpolate(vox: torch.Tensor, x: torch.Tensor, y: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    """tf_interpolate at explicit coordinates: vox [B,S,S,S,C] fp32, x/y/z [B*n] fp32 -> [B*n, C] fp32 (rn_interpolate_f32)."""
+    vox = _cuda(vox, torch.float32)
+    x, y, z = (_cuda(t.reshape(-1).to(device=vox.device, dtype=torch.float32)) for t in (x, y, z))
+    B, S, _, _, Cc = vox.shape
+    n = x.numel()
+    if y.numel() != n or z.numel() != n or n % B != 0:
+        raise ValueError("interpolate: x, y, z must hold the same number of points, a multiple of the batch size")
+    out = torch.empty((n, Cc), device=vox.device, dtype=torch.float32)
+    check(lib.rn_interpolate_f32(vox.data_ptr(), x.data_ptr(), y.data_ptr(), z.data_ptr(), out.data_ptr(), B, Cc, S, n // B,
+                                 _stream()), "rn_interpolate_f32")
     return out
 
 
@@ -226,7 +252,7 @@ def _ret(out16, out32, want16, want32, fmt):
 
 
 def conv2d(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, residual: Optional[torch.Tensor] = None,
-           want16: bool = True, want32: bool = False, out16=None, out32=None, alpha=None):
+           want16: bool = True, want32: bool = False, out16=None, out32=None, alpha=None, tune=None):
     """SAME stride-1 conv2d + bias (+PReLU/sigmoid) (+residual).  x [B,H,W,Cin] 16-bit."""
     x = _act_in(x, L.fmt, L.dtype)
     B, H, W, Cin = x.shape
@@ -239,12 +265,12 @@ def conv2d(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, residual: 
     check(lib.rn_conv2d_same(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(),
                              _ptr(alpha if alpha is not None else L.alpha) if a == ACT_PRELU else None, a, _ptr(residual), res_f32,
                              _ptr(out16), _ptr(out32), B, H, W, Cin, L.cout, L.cout_pad, L.ksize[0], L.ksize[1],
-                             L.fmt, _stream()), "rn_conv2d_same")
+                             L.fmt, _tune(tune), _stream()), "rn_conv2d_same")
     return _ret(out16, out32, want16, want32, L.fmt)
 
 
 def conv3d(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, residual: Optional[torch.Tensor] = None,
-           want16: bool = True, want32: bool = False, out16=None, out32=None, alpha=None):
+           want16: bool = True, want32: bool = False, out16=None, out32=None, alpha=None, tune=None):
     """SAME stride-1 k^3 conv3d on the tensor pipe.  x [B,H,W,D,Cin] 16-bit."""
     x = _act_in(x, L.fmt, L.dtype)
     B, H, W, D, Cin = x.shape
@@ -255,7 +281,7 @@ def conv3d(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, residual: 
     check(lib.rn_conv3d_same(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(),
                              _ptr(alpha if alpha is not None else L.alpha) if a == ACT_PRELU else None, a, _ptr(residual), res_f32,
                              _ptr(out16), _ptr(out32), B, H, W, D, Cin, L.cout, L.cout_pad, L.ksize[0],
-                             L.fmt, _stream()), "rn_conv3d_same")
+                             L.fmt, _tune(tune), _stream()), "rn_conv3d_same")
     return _ret(out16, out32, want16, want32, L.fmt)
 
 
@@ -297,7 +323,7 @@ class BandedConv3d:
 
 def conv3d_banded(x: torch.Tensor, L: BandedConv3d, act: Optional[str] = None,
                   residual: Optional[torch.Tensor] = None, alpha: Optional[torch.Tensor] = None, alpha_tag=None,
-                  want16: bool = True, want32: bool = False, out16=None, out32=None):
+                  want16: bool = True, want32: bool = False, out16=None, out32=None, tune=None):
     """x [B,H,W,D,Cin] 16-bit -> [B,H,W,D,Cout]; alpha is the per-Cout PReLU slope (length Cout)."""
     x = _act_in(x, L.fmt, L.dtype)
     B, H, W, D, Cin = x.shape
@@ -317,12 +343,12 @@ def conv3d_banded(x: torch.Tensor, L: BandedConv3d, act: Optional[str] = None,
             check(lib.rn_expand_channels(v.data_ptr(), alpha_full.data_ptr(), L.cout, Do, _stream()), "rn_expand_channels")
     check(lib.rn_conv3d_banded_same(x.data_ptr(), L.w.data_ptr(), bias_full.data_ptr(), _ptr(alpha_full), a,
                                     _ptr(residual), res_f32, _ptr(out16), _ptr(out32), B, H, W, D, Cin, L.cout, L.sz,
-                                    L.fmt, _stream()), "rn_conv3d_banded_same")
+                                    L.fmt, _tune(tune), _stream()), "rn_conv3d_banded_same")
     return _ret(out16, out32, want16, want32, L.fmt)
 
 
 def conv2d_transpose(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, want16: bool = True,
-                     want32: bool = False, out16=None, out32=None, alpha=None):
+                     want32: bool = False, out16=None, out32=None, alpha=None, tune=None):
     """SAME transposed conv, out = in*stride.  x [B,H,W,Cin] 16-bit."""
     x = _act_in(x, L.fmt, L.dtype)
     B, H, W, Cin = x.shape
@@ -333,7 +359,7 @@ def conv2d_transpose(x: torch.Tensor, L: PackedConv, act: Optional[str] = None, 
     check(lib.rn_conv2d_transpose_same(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(),
                                        _ptr(alpha if alpha is not None else L.alpha) if a == ACT_PRELU else None, a, _ptr(out16), _ptr(out32),
                                        B, H, W, Cin, L.cout, L.cout_pad, L.ksize[0], L.ksize[1], s,
-                                       L.fmt, _stream()), "rn_conv2d_transpose_same")
+                                       L.fmt, _tune(tune), _stream()), "rn_conv2d_transpose_same")
     return _ret(out16, out32, want16, want32, L.fmt)
 
 
@@ -360,7 +386,7 @@ class MergedConvT2:
 
 def conv2d_transpose_s2_merged(x: torch.Tensor, L: MergedConvT2, act: Optional[str] = None,
                                alpha: Optional[torch.Tensor] = None, alpha_tag=None, want16: bool = True,
-                               want32: bool = False, out16=None, out32=None):
+                               want32: bool = False, out16=None, out32=None, tune=None):
     x = _act_in(x, L.fmt, L.dtype)
     B, H, W, Cin = x.shape
     assert Cin == L.cin
@@ -374,7 +400,7 @@ def conv2d_transpose_s2_merged(x: torch.Tensor, L: MergedConvT2, act: Optional[s
             if alpha_tag is not None:
                 L._alpha[alpha_tag] = alpha4
     check(lib.rn_conv2d_transpose_s2_merged(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(), _ptr(alpha4), a, _ptr(out16),
-                                            _ptr(out32), B, H, W, Cin, L.cout, L.fmt, _stream()),
+                                            _ptr(out32), B, H, W, Cin, L.cout, L.fmt, _tune(tune), _stream()),
           "rn_conv2d_transpose_s2_merged")
     return _ret(out16, out32, want16, want32, L.fmt)
 
@@ -407,7 +433,7 @@ class XFoldConvT:
 
 
 def conv2d_transpose_xfold(x: torch.Tensor, L: XFoldConvT, act: Optional[str] = None, alpha: Optional[torch.Tensor] = None,
-                           alpha_tag=None, want16: bool = True, want32: bool = False, out16=None, out32=None):
+                           alpha_tag=None, want16: bool = True, want32: bool = False, out16=None, out32=None, tune=None):
     x = _act_in(x, L.fmt, L.dtype)
     B, H, W, Cin = x.shape
     assert Cin == L.cin and W % L.F == 0
@@ -422,7 +448,7 @@ def conv2d_transpose_xfold(x: torch.Tensor, L: XFoldConvT, act: Optional[str] = 
                 L._alpha[alpha_tag] = alpha_x
     check(lib.rn_conv2d_transpose_s1_xfold(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(), _ptr(alpha_x), a, _ptr(out16),
                                            _ptr(out32), B, H, W, Cin, L.cout, L.kh, L.kw, L.F, L.cout_pad, L.fmt,
-                                           _stream()), "rn_conv2d_transpose_s1_xfold")
+                                           _tune(tune), _stream()), "rn_conv2d_transpose_s1_xfold")
     return _ret(out16, out32, want16, want32, L.fmt)
 
 

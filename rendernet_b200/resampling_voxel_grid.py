@@ -110,6 +110,18 @@ def tf_resampling(voxel_array, transformation_matrix, params=None, Scale_matrix=
     return ResampledGrid(_to_cuda_f32(voxel_array), torch.from_numpy(minv).cuda(), new_size)
 
 
+def tf_interpolate(voxel, x, y, z, out_size):
+    """:381-486 as a standalone call: trilinear interpolation of `voxel` [B,S,S,S,C] at the flat coordinate lists x, y, z
+    (each B*n points, batch-major) -> [B*n, C] float32; `out_size` = [B, h, w, d, C] is only used, like upstream, for the
+    point count per item.  Clamp-then-weight rule reproduced bit for bit (rn_interpolate_f32)."""
+    vox = _to_cuda_f32(voxel)
+    n = int(out_size[1]) * int(out_size[2]) * int(out_size[3])
+    xs, ys, zs = (torch.as_tensor(np.asarray(t, np.float32) if not isinstance(t, torch.Tensor) else t).reshape(-1) for t in (x, y, z))
+    if xs.numel() != vox.shape[0] * n:
+        raise ValueError(f"tf_interpolate: {xs.numel()} points for out_size {list(out_size)} and batch {vox.shape[0]}")
+    return ops.interpolate(vox, xs, ys, zs)
+
+
 def tf_rotation_resampling(voxel_array, view_params, size=64, new_size=128):
     """:616-632."""
     vp = _np32(view_params)

@@ -273,7 +273,6 @@ def test_tma_store_epilogue_bit_identical(B, H, W, Cin, Cout, k):
     """The TMA-store epilogue (swizzled smem panels + cp.async.bulk.tensor store, edges clipped by the hardware) writes
     exactly what the direct-store epilogue writes -- incl. ragged tiles, residual adds and untouched neighbours."""
     ops = _ops()
-    from rendernet_b200._lib import lib
     rng = np.random.default_rng(B * H + Cout)
     x = torch.from_numpy(q16(rng.standard_normal((B, H, W, Cin)))).to(dev).half()
     w = torch.from_numpy(q16(rng.standard_normal((k, k, Cin, Cout)) / np.sqrt(k * k * Cin)))
@@ -281,14 +280,10 @@ def test_tma_store_epilogue_bit_identical(B, H, W, Cin, Cout, k):
                       torch.from_numpy(rng.uniform(0, 0.3, Cout).astype(np.float32)))
     res = torch.from_numpy(q16(rng.standard_normal((B, H, W, Cout)))).to(dev).half()
     outs = []
-    for on in (0, 1):
-        prev = lib.rn_set_tma_store(on)
-        try:
-            y1 = ops.conv2d(x, L, act="prelu")
-            y2 = ops.conv2d(x, L, act=None, residual=res)
-            torch.cuda.synchronize()
-        finally:
-            lib.rn_set_tma_store(prev)
+    for on in (-1, 1):              # rn_tuning.tma_store: -1 = direct-store epilogue, 1 = TMA-store epilogue
+        y1 = ops.conv2d(x, L, act="prelu", tune=dict(tma_store=on))
+        y2 = ops.conv2d(x, L, act=None, residual=res, tune=dict(tma_store=on))
+        torch.cuda.synchronize()
         outs.append((y1.clone(), y2.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     close(outs[1][0], orc.prelu(orc.conv2d(x.float().cpu().numpy(), w.numpy(), L.bias[:Cout].cpu().numpy()),
@@ -359,7 +354,6 @@ def test_conv_m_subtiles_bit_identical(case):
     (TMA zero fill / store clipping on the second sub-tile), the banded 3^3 conv with residual + PReLU, the merged
     stride-2 transposed conv (TMA scatter store) and the x-folded thin transposed conv."""
     ops = _ops()
-    from rendernet_b200._lib import lib
     torch.manual_seed(4)
 
     def both(fn):
@@ -367,12 +361,7 @@ def test_conv_m_subtiles_bit_identical(case):
         outs = []
         for m in (1, 2):
             for g in (1, 2):
-                prev, prev_g = lib.rn_set_default_msub(m), lib.rn_set_epilogue_groups(g)
-                try:
-                    outs.append(fn().clone())
-                finally:
-                    lib.rn_set_default_msub(prev)
-                    lib.rn_set_epilogue_groups(prev_g)
+                outs.append(fn(dict(msub=m, epilogue_groups=g)).clone())
         assert all(torch.equal(outs[0], o) for o in outs[1:])
         return outs[0]
 
@@ -382,7 +371,7 @@ def test_conv_m_subtiles_bit_identical(case):
         w = torch.randn(3, 3, Cin, Cout, device=dev) / (9 * Cin) ** 0.5
         L = ops.pack_conv("conv2d", w, torch.randn(Cout) * 0.1, torch.rand(Cout) * 0.3)
         res = torch.randn(B, H, W, Cout, device=dev).half()
-        y = both(lambda: ops.conv2d(x, L, act="prelu", residual=res))
+        y = both(lambda t: ops.conv2d(x, L, act="prelu", residual=res, tune=t))
         want = orc.prelu(orc.conv2d(x.float().cpu().numpy(), w.half().float().cpu().numpy(), L.bias[:Cout].cpu().numpy()),
                          L.alpha[:Cout].cpu().numpy()) + res.float().cpu().numpy()
         close(y, want, rel=1.5e-3)
@@ -391,7 +380,7 @@ def test_conv_m_subtiles_bit_identical(case):
         x = torch.randn(B, H, W, Cin, device=dev).half()
         w = torch.randn(1, 1, Cin, Cout, device=dev) / Cin ** 0.5
         L = ops.pack_conv("conv2d", w, torch.randn(Cout) * 0.1, None)
-        y = both(lambda: ops.conv2d(x, L))
+        y = both(lambda t: ops.conv2d(x, L, tune=t))
         close(y, orc.conv2d(x.float().cpu().numpy(), w.half().float().cpu().numpy(), L.bias[:Cout].cpu().numpy()), rel=1.5e-3)
     elif case == "banded_res":
         x = torch.randn(2, 32, 32, 32, 32, device=dev).half()
@@ -399,7 +388,7 @@ def test_conv_m_subtiles_bit_identical(case):
         w = torch.randn(3, 3, 3, 32, 32, device=dev) / (27 * 32) ** 0.5
         Lb = ops.BandedConv3d(w, torch.randn(32) * 0.1)
         al = torch.rand(32, device=dev) * 0.3
-        y = both(lambda: ops.conv3d_banded(x, Lb, act="prelu", alpha=al, residual=res))
+        y = both(lambda t: ops.conv3d_banded(x, Lb, act="prelu", alpha=al, residual=res, tune=t))
         want = orc.prelu(orc.conv3d(x.float().cpu().numpy(), w.half().float().cpu().numpy(), Lb.bias.cpu().numpy(), (1, 1, 1)),
                          al.cpu().numpy()) + res.float().cpu().numpy()
         close(y, want, rel=1.5e-3)
@@ -408,7 +397,7 @@ def test_conv_m_subtiles_bit_identical(case):
         w = torch.randn(4, 4, 32, 64, device=dev) / (16 * 64) ** 0.5
         L = ops.MergedConvT2(w, torch.randn(32) * 0.1)
         al = torch.rand(32, device=dev) * 0.3
-        y = both(lambda: ops.conv2d_transpose_s2_merged(x, L, act="prelu", alpha=al))
+        y = both(lambda t: ops.conv2d_transpose_s2_merged(x, L, act="prelu", alpha=al, tune=t))
         want = orc.prelu(orc.conv2d_transpose(x.float().cpu().numpy(), w.half().float().cpu().numpy(),
                                               L.bias[:32].cpu().numpy(), (2, 2)), al.cpu().numpy())
         close(y, want, rel=1.5e-3)
@@ -418,7 +407,7 @@ def test_conv_m_subtiles_bit_identical(case):
         b = torch.randn(16) * 0.1
         L = ops.XFoldConvT(w, b, ops.XFoldConvT.factor(32, 64))
         al = torch.rand(16, device=dev) * 0.3
-        y = both(lambda: ops.conv2d_transpose_xfold(x, L, act="prelu", alpha=al))
+        y = both(lambda t: ops.conv2d_transpose_xfold(x, L, act="prelu", alpha=al, tune=t))
         want = orc.prelu(orc.conv2d_transpose(x.float().cpu().numpy(), w.half().float().cpu().numpy(), b.numpy(), (1, 1)),
                          al.cpu().numpy())
         close(y, want, rel=1.5e-3)
@@ -428,7 +417,6 @@ def test_conv_two_epilogue_groups_bit_identical():
     """The second group of four epilogue warps (EG = 2: projection unit 1x1, 4x4 convs with short K, residual adds) must
     reproduce the single-group kernel bit for bit, including ragged image edges and the residual / sigmoid epilogues."""
     ops = _ops()
-    from rendernet_b200._lib import lib
     torch.manual_seed(9)
     for (B, H, W, Cin, Cout, k, act, use_res) in ((4, 32, 32, 256, 256, 1, "prelu", False), (3, 24, 40, 128, 512, 1, None, True),
                                                   (2, 32, 32, 64, 256, 4, "sigmoid", False), (2, 16, 48, 128, 128, 3, "prelu", True)):
@@ -438,11 +426,7 @@ def test_conv_two_epilogue_groups_bit_identical():
         res = torch.randn(B, H, W, Cout, device=dev).half() if use_res else None
         outs = []
         for g in (1, 2):
-            prev = lib.rn_set_epilogue_groups(g)
-            try:
-                outs.append(ops.conv2d(x, L, act=act, residual=res).clone())
-            finally:
-                lib.rn_set_epilogue_groups(prev)
+            outs.append(ops.conv2d(x, L, act=act, residual=res, tune=dict(epilogue_groups=g)).clone())
         assert torch.equal(outs[0], outs[1]), (B, H, W, Cin, Cout, k, act, use_res)
         want = orc.conv2d(x.float().cpu().numpy(), w.half().float().cpu().numpy(), L.bias[:Cout].cpu().numpy())
         if act == "prelu":
