@@ -1,0 +1,26 @@
+#!/bin/bash
+# round-2 multi-GPU ablation on ONE 8-GPU box: output gather nccl / peer / none, both precisions, per-rank step times
+mkdir -p gpurun_out
+N=${1:-8}
+run() {  # tag, extra args
+  tag=$1; shift
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
+     bench.py --gpus $N --steps 10 --warmup 3 --no-other-precision --no-cpu-baseline "$@" > gpurun_out/r02_scale${N}_$tag.json 2> gpurun_out/r02_scale${N}_$tag.err
+  echo "$tag rc=$?"; python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/r02_scale${N}_$tag.json"))
+    print("  value", round(d["value"],1), "ms/step", round(d["ms_per_step"],2), "per-rank", [round(x,2) for x in d["per_rank_ms"]], "e2e", round(d["e2e"]["value"],1), d["config"]["parallelism"][:60], d["clocks"])
+except Exception as e: print("  ERR", e)
+PY
+}
+run fast_nccl --precision fast --gather nccl
+run fast_none --precision fast --gather none
+run fast_peer --precision fast --gather peer
+run exact_nccl --precision exact --gather nccl
+run exact_none --precision exact --gather none
+timeout 600 python bench.py --steps 10 --no-cpu-baseline > gpurun_out/r02_scale${N}_n1_samebox.json 2> gpurun_out/r02_scale${N}_n1_samebox.err; echo "n1 rc=$?"
+python - <<PY
+import json
+d=json.load(open("gpurun_out/r02_scale${N}_n1_samebox.json")); print("N=1 same box exact", round(d["value"],1), "fast", round(d["other_precision"]["value"],1))
+PY
