@@ -467,9 +467,10 @@ def main():
                     help="BASELINE.json config: 2 = B=24 Shader (3 = the same at --gpus 8), 4 = Texture+Normal B=24, 5 = 360-frame turntable")
     ap.add_argument("--precision", type=str, default="exact", choices=["exact", "fast"],
                     help="headline precision mode (the other one is timed too and reported under other_precision)")
-    ap.add_argument("--gather", type=str, default="nccl", choices=["nccl", "peer", "none"],
-                    help="N>1 output all-gather: NCCL (default, what the north_star names), copy-engine P2P writes over CUDA IPC "
-                         "(rendernet_b200.parallel.PeerImageGather; falls back to NCCL if IPC is unavailable), or none (ablation)")
+    ap.add_argument("--gather", type=str, default="nccl_sync", choices=["nccl_sync", "nccl", "peer", "none"],
+                    help="N>1 output all-gather: ncclAllGather between steps on the compute stream (default), ncclAllGather overlapped "
+                         "on a side stream, copy-engine P2P writes over CUDA IPC (rendernet_b200.parallel.PeerImageGather; falls back "
+                         "to NCCL if IPC is unavailable), or none (ablation); see ShardedRenderEngine for the measurements")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-precision", action="store_true")

@@ -106,6 +106,11 @@ typedef struct rn_conv_desc {
    * tap starting at channel a_c_base + n_tile*a_c_ntile (may run out of range: zero filled), and w_packed is one
    * banded filter [ntaps*Cin/KB][force_bn][KB] shared by all N tiles.  All zero for ordinary convolutions. */
   int x_channels, a_c_base, a_c_ntile, w_banded;
+  /* geometry of the depth-folded conv3d behind a banded filter (channels per depth of x / of the output, z stride; 0 = not
+   * given): lets the launcher issue the edge K blocks of the band, which touch only half of the N tile's output depths,
+   * as N = 64 MMAs instead of multiplying structural zeros.  w_packed must then come from rn_pack_conv3d_banded (K blocks in
+   * processing order, a "single-CTA" and a "CTA-pair" arrangement of the half tiles back to back). */
+  int band_cin, band_cout, band_sz;
   int cluster;              /* thread-block-cluster size for the weight-tile TMA multicast: 0 auto, 1, 2 or 4 */
   int cta_group;            /* 0 auto, 1 = single-CTA MMA, 2 = paired tcgen05.mma.cta_group::2 (M = 256) */
   /* y-halo sharing (2-D only): taps ordered tap = ky*nx + kx with dy(ky) = dy(0) + ky; the ny taps of a filter column
@@ -151,7 +156,8 @@ int rn_conv3d_same(const void* x, const void* w_packed, const float* bias, const
  * depth-folded 2-D convolution: the D axis is part of the GEMM's N (128 = (128/Cout) output depths x Cout) and K
  * ((128/Cout + 2) input depths x Cin, padded to 64-element blocks), so TMA moves full 128-byte rows and each
  * activation byte is fetched from L2 9x instead of 27x.  w_banded from rn_pack_conv3d_banded
- * ([9][kblocks][128][64] 16-bit, bytes = rn_conv3d_banded_bytes); bias/alpha are per Cout (length Cout) and are
+ * (2 arrangements x [9][kblocks][128][64] 16-bit -- one for single-CTA, one for CTA-pair launches --, bytes =
+ * rn_conv3d_banded_bytes per plane; RN_FMT_F16X2: twice that, LO plane after the HI plane); bias/alpha are per Cout (length Cout) and are
  * expanded over depth internally via bias_full/alpha_full scratch [D*Cout] fp32 supplied by the caller
  * (fill them with rn_expand_channels).  x: [B,H,W,D,Cin]; residual, out: [B,H,W,ceil(D/sz),Cout], 16-bit.
  * sz = stride along D (1: res blocks / e_conv3; 2: e_conv2's stride (1,1,2), RenderNet_Shader.py:41), TF SAME pads. */

@@ -24,6 +24,7 @@ class rn_conv_desc(C.Structure):
         ("o_z", C.c_longlong), ("fmt", C.c_int), ("force_bn", C.c_int), ("force_kps", C.c_int),
         ("max_ctas", C.c_int),
         ("x_channels", C.c_int), ("a_c_base", C.c_int), ("a_c_ntile", C.c_int), ("w_banded", C.c_int),
+        ("band_cin", C.c_int), ("band_cout", C.c_int), ("band_sz", C.c_int),
         ("cluster", C.c_int), ("cta_group", C.c_int), ("ny", C.c_int), ("tile_w", C.c_int), ("msub", C.c_int),
         ("o_nsplit", C.c_int), ("o_nhi", C.c_longlong),
         ("x_plane", C.c_longlong), ("w_plane", C.c_longlong), ("o_plane", C.c_longlong),

@@ -223,6 +223,15 @@ static int plan_conv(const rn_conv_desc* d, IgemmParams& p, ConvPlan& pl) {
     p.split = 1;
   }
   p.ab_fmt = d->fmt == 1 ? 1 : 0;
+  if (d->w_banded && d->band_cin > 0) {     // depth-folded conv3d: K-block order / half-tile blocks (rn_igemm.cuh band_layout)
+    if (d->force_bn != 128 || d->band_cout < 8 || 128 % d->band_cout != 0 || d->band_cin < 8 || 64 % d->band_cin != 0 ||
+        d->band_sz < 1 || d->band_sz > 2)
+      return -19;
+    const BandLayout L = band_layout(d->band_cin, d->band_cout, d->band_sz);
+    if (L.kblocks != p.kblocks || L.kblocks > 8) return -19;
+    p.band_half = 1;                        // the packed filter is in processing order even when no block is a half block
+    for (int i = 0; i < L.kblocks; ++i) { p.kb_order[i] = L.order[i]; p.kb_half[i] = L.half[i]; }
+  }
   p.rank = d->ndim == 3 ? 5 : 4;
   p.W = d->W; p.H = d->H; p.D = D; p.B = d->B;
   // TMA-store epilogue: dense 16-bit NHWC output only (no fp32 copy, no ragged / split columns)
@@ -387,11 +396,17 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
               swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) return 1000 + static_cast<int>(r);
+  const uint16_t* w_hi = static_cast<const uint16_t*>(d->w_packed);
+  if (p.band_half && CG == 2) {   // CTA-pair arrangement of the half tiles follows the single-CTA one
+    const long long arr = 9LL * p.kblocks * 128 * 64;
+    w_hi += arr;
+    if (split) w_lo += arr;
+  }
   if (d->w_banded) {  // [ntaps*kblocks][BN][KB], identical for every N tile
     const cuuint64_t dims[3] = {(cuuint64_t)KB, (cuuint64_t)BN, (cuuint64_t)d->ntaps * p.kblocks};
     const cuuint64_t strides[2] = {(cuuint64_t)KB * 2, (cuuint64_t)KB * 2 * BN};
     const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)(BN / CL), 1};  // CL == 2 also for the paired MMA
-    r = enc(&p.tmB, dt, 3, const_cast<void*>(d->w_packed), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    r = enc(&p.tmB, dt, 3, const_cast<uint16_t*>(w_hi), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS && split)
       r = enc(&p.tmB2, dt, 3, const_cast<uint16_t*>(w_lo), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -400,7 +415,7 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
     const cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->cout_pad, (cuuint64_t)d->ntaps};
     const cuuint64_t strides[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * d->cout_pad};
     const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)(BN / CL), 1};  // CL == 2 also for the paired MMA
-    r = enc(&p.tmB, dt, 3, const_cast<void*>(d->w_packed), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    r = enc(&p.tmB, dt, 3, const_cast<uint16_t*>(w_hi), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_of(p.row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS && split)
       r = enc(&p.tmB2, dt, 3, const_cast<uint16_t*>(w_lo), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -43,7 +43,14 @@ struct alignas(64) IgemmParams {
   // x_hi.w_hi + x_lo.w_hi + x_hi.w_lo (the lo.lo term is below fp32 resolution); the epilogue reads a hi+lo residual and
   // writes hi and lo planes.  The reference computes these convolutions in fp32 (tools/layer_util.py:171,212,253).
   int split;
-  long long o_plane;              // element offset of the LO plane of out16 / of a 16-bit residual
+  long long o_plane;
+  // Depth-folded conv3d only: the K blocks of a tap are processed in the order kb_order[0..kblocks) (a block that feeds the
+  // whole N tile first, so that it initialises every accumulator column); kb_half[i] says which half of the N tile block i
+  // feeds: 0 = all of it, 1 = columns [0, BN/2), 2 = columns [BN/2, BN).  The edge blocks of the band touch only half of
+  // the tile's output depths, and their MMAs are issued with N = BN/2 instead of multiplying structural zeros.
+  int band_half;                  // 1: kb_order / kb_half are in use
+  uint8_t kb_order[8];
+  uint8_t kb_half[8];              // element offset of the LO plane of out16 / of a 16-bit residual
   // fused epilogue: v = acc + bias; v = act(v); v += residual; store
   void* out16;                    // 16-bit output or nullptr
   float* out32;                   // fp32 output or nullptr
@@ -61,6 +68,41 @@ struct alignas(64) IgemmParams {
   int o_nsplit;                   // > 0: column n lands at (n / o_nsplit) * o_nhi + (n % o_nsplit) instead of n (merged
   long long o_nhi;                //      phases of a stride-2 transposed conv: n = (ay, ax, co))
 };
+
+// Band structure of the depth-folded 3^3 conv3d (rn_conv3d_banded_same): N tile = 128/Cout output depths x Cout, K per tap =
+// the input depths those need, in blocks of 64 elements = 64/Cin depths.  Shared by the filter packer and the launcher.
+struct BandLayout {
+  int kblocks;
+  bool any_half;
+  uint8_t order[8];   // processing order of the K blocks (a full block first)
+  uint8_t half[8];    // per PROCESSED block: 0 full, 1 lower half of the N tile, 2 upper half
+};
+inline BandLayout band_layout(int Cin, int Cout, int sz) {
+  BandLayout L{};
+  const int zo_n = 128 / Cout, dpb = 64 / Cin, nzi = (zo_n - 1) * sz + 3;
+  L.kblocks = (nzi * Cin + 63) / 64;
+  uint8_t h[8] = {0};
+  int first_full = -1;
+  for (int kb = 0; kb < L.kblocks && kb < 8; ++kb) {
+    const int zi_lo = kb * dpb, zi_hi = (kb + 1) * dpb - 1 < nzi - 1 ? (kb + 1) * dpb - 1 : nzi - 1;
+    int zo_min = (zi_lo - 2 + sz - 1) / sz;                 // smallest zo with sz*zo + 2 >= zi_lo
+    if (zi_lo - 2 < 0) zo_min = 0;
+    int zo_max = zi_hi / sz;                                // largest zo with sz*zo <= zi_hi
+    if (zo_max > zo_n - 1) zo_max = zo_n - 1;
+    const int c0 = zo_min * Cout, c1 = (zo_max + 1) * Cout; // columns [c0, c1) of the 128-column tile
+    h[kb] = c1 <= 64 ? 1 : (c0 >= 64 ? 2 : 0);
+    if (h[kb] == 0 && first_full < 0) first_full = kb;
+  }
+  int n = 0;
+  if (first_full >= 0 && L.kblocks <= 8) {
+    L.order[n] = static_cast<uint8_t>(first_full); L.half[n++] = 0;
+    for (int kb = 0; kb < L.kblocks; ++kb)
+      if (kb != first_full) { L.order[n] = static_cast<uint8_t>(kb); L.half[n] = h[kb]; L.any_half |= h[kb] != 0; ++n; }
+  } else {
+    for (int kb = 0; kb < L.kblocks && kb < 8; ++kb) { L.order[kb] = static_cast<uint8_t>(kb); L.half[kb] = 0; }
+  }
+  return L;
+}
 
 // launch-heuristic defaults (immutable after first use; RN_TUNE environment override -- rn_igemm.cu)
 struct Tuning {

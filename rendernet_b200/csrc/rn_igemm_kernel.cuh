@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
       constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
       constexpr int kBRows = BN / CL;               // rows of the B tile this CTA fetches (and multicasts)
       const int kps = p.kps, kblocks = p.kblocks, stages = p.stages;
-      const bool rank5 = (p.rank == 5), banded = (p.b_banded != 0);
+      const bool rank5 = (p.rank == 5), banded = (p.b_banded != 0), band_half = (p.band_half != 0);
       const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(full_bar);
       const uint32_t a_sub = static_cast<uint32_t>(p.a_sub_bytes), sub_u = static_cast<uint32_t>(sub_bytes);
       const uint32_t b_sub = static_cast<uint32_t>(p.b_sub_bytes);
@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
           const uint64_t mapA = (split && (p.tap[kx][3] & 1)) ? mapA_lo : mapA_hi;
           int ac = a_c0, bk = 0;
           for (int kb = 0; kb < kblocks; ++kb) {
+            if (band_half) ac = a_c0 + static_cast<int>(p.kb_order[kb]) * kb_elems;   // blocks run in kb_order (B is packed so)
             if (j == 0) {
               n_here = min(kps, left);
               mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -338,6 +339,9 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
     // ------------------------------------------------------------ MMA issuer (one thread; leader CTA only for CG=2)
     if ((CG == 1 || cta_rank == 0) && elect_one()) {
       const uint32_t idesc = make_idesc_f16(CG * kTileM, BN, p.ab_fmt);
+      const uint32_t idesc_half = make_idesc_f16(CG * kTileM, BN / 2, p.ab_fmt);   // edge K blocks of a banded filter
+      const bool band_half = p.band_half != 0;
+      const int kblocks = p.kblocks;
       const int mma_per_kit = p.row_bytes >> 5;  // 32 B (= 16 elements, UMMA_K) per instruction
       const int kps = p.kps, stages = p.stages;
       // descriptor = constant high part | (smem address >> 4); all operand buffers are 1024-byte aligned
@@ -356,6 +360,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * ms * BN);
         uint32_t accum = 0;
+        int kbi = 0;                                // K block (in processing order) of the current group
         for (int left = total_k; left > 0;) {
           const int n_here = min(kps, left);
           mbar_wait(&full_bar[stage], phase);
@@ -363,13 +368,19 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
           uint64_t da = desc_hi | static_cast<uint64_t>(base16 + static_cast<uint32_t>(stage) * stage16);
           for (int j = 0; j < n_here; ++j) {
             uint64_t dak = da, dbk = da + a16;
+            // banded filter: an edge K block feeds only half of the N tile -> N = BN/2 MMAs on that half of the accumulator
+            // (its packed tile holds the needed rows first; the very first block of a tile is always a full one)
+            const uint32_t half = band_half ? p.kb_half[kbi] : 0u;
+            const uint32_t id_j = half ? idesc_half : idesc;
+            const uint32_t d_j = d_tmem + (half == 2u ? static_cast<uint32_t>(BN / 2) : 0u);
+            if (++kbi == kblocks) kbi = 0;
             for (int ky = 0; ky < ny; ++ky) {       // operand ky = the halo shifted down by ky image rows
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (k < mma_per_kit) {
-                  umma_f16<CG>(d_tmem, dak + 2 * k, dbk + 2 * k, idesc, accum);
+                  umma_f16<CG>(d_j, dak + 2 * k, dbk + 2 * k, id_j, accum);
                   if constexpr (MS == 2)   // second accumulator, same weight operand
-                    umma_f16<CG>(d_tmem + BN, dak + ams16 + 2 * k, dbk + 2 * k, idesc, accum);
+                    umma_f16<CG>(d_j + BN, dak + ams16 + 2 * k, dbk + 2 * k, id_j, accum);
                   accum = 1;
                 }
               }

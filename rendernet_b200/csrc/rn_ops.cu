@@ -238,23 +238,40 @@ __global__ void cast_16_to_f32_kernel(const uint16_t* __restrict__ s, float* __r
 
 
 // ------------------------------------------------------------------------------------------ banded conv3d filter
-// Wb[tap=(ky,kx)][kb][n = zo_l*Cout + co][k = zi_l*Cin + ci] with, relative to the N tile's first output depth z0,
-// zi = sz*z0 - pz + kb*(64/Cin) + zi_l and zo = z0 + zo_l  ->  kz = zi - (sz*zo - pz) = kb*(64/Cin) + zi_l - sz*zo_l;
-// entry = w[ky][kx][kz][ci][co] when 0 <= kz < 3, else 0.   (BN = 128, KB = 64; sz = z stride)
+// Wb[arr][tap=(ky,kx)][i][n'][k = zi_l*Cin + ci]: K block i of the processing order is block kb = order[i] of the band.
+// Relative to the N tile's first output depth z0: zi = sz*z0 - pz + kb*(64/Cin) + zi_l, zo = z0 + zo_l
+//   ->  kz = zi - (sz*zo - pz) = kb*(64/Cin) + zi_l - sz*zo_l;  entry = w[ky][kx][kz][ci][co] when 0 <= kz < 3, else 0.
+// Row n' of a tile holds filter row n = zo_l*Cout + co.  Full blocks: n = n'.  Half blocks (they feed only columns
+// [base, base+64) of the tile, base = 0 or 64; rn_igemm.cuh band_layout) keep the needed rows FIRST so that an N = 64 MMA finds
+// them at the start of the operand: arrangement 0 (single CTA holds all 128 rows): n = base + n' for n' < 64;
+// arrangement 1 (cta_group::2, CTA r holds rows [64r, 64r+64) and supplies columns [32r, 32r+32) of the N = 64 MMA):
+// n = base + 32r + i for n' = 64r + i, i < 32.  Unused rows are zero.   (BN = 128, KB = 64; sz = z stride)
 __global__ void pack_banded_kernel(const float* __restrict__ w, uint16_t* __restrict__ packed, int Cin, int Cout,
-                                   int kblocks, int sz, int fmt) {
-  const long long total = 9LL * kblocks * 128 * 64;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+                                   BandLayout L, int sz, int fmt, long long plane) {
+  const int kblocks = L.kblocks;
+  const long long per_arr = 9LL * kblocks * 128 * 64;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < 2 * per_arr;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(i % 64);
-    const int n = static_cast<int>((i / 64) % 128);
-    const int kb = static_cast<int>((i / (64 * 128)) % kblocks);
-    const int tap = static_cast<int>(i / (64LL * 128 * kblocks));
-    const int zi_l = k / Cin, ci = k % Cin, zo_l = n / Cout, co = n % Cout;
-    const int kz = kb * (64 / Cin) + zi_l - sz * zo_l;
+    const int arr = static_cast<int>(i / per_arr);
+    const long long r = i - arr * per_arr;
+    const int k = static_cast<int>(r % 64);
+    const int np = static_cast<int>((r / 64) % 128);
+    const int bi = static_cast<int>((r / (64 * 128)) % kblocks);
+    const int tap = static_cast<int>(r / (64LL * 128 * kblocks));
+    const int kb = L.order[bi], half = L.half[bi];
+    int n = np;
+    if (half != 0) {
+      const int base = half == 2 ? 64 : 0;
+      if (arr == 0) n = np < 64 ? base + np : -1;
+      else n = (np % 64) < 32 ? base + 32 * (np / 64) + (np % 64) : -1;
+    }
     float v = 0.f;
-    if (kz >= 0 && kz <= 2) v = w[((static_cast<long long>(tap) * 3 + kz) * Cin + ci) * Cout + co];
-    store16(packed, i, v, fmt, total);
+    if (n >= 0) {
+      const int zi_l = k / Cin, ci = k % Cin, zo_l = n / Cout, co = n % Cout;
+      const int kz = kb * (64 / Cin) + zi_l - sz * zo_l;
+      if (kz >= 0 && kz <= 2) v = w[((static_cast<long long>(tap) * 3 + kz) * Cin + ci) * Cout + co];
+    }
+    store16(packed, i, v, fmt, plane);
   }
 }
 
@@ -1023,21 +1040,23 @@ extern "C" int rn_conv2d_transpose_same(const void* x, const void* w_packed, con
 
 
 // ---------------------------------------------------------------------------------- depth-folded conv3d
-static int banded_kblocks(int Cin, int Cout, int sz) {
-  const int span = ((128 / Cout - 1) * sz + 3) * Cin;  // input depths needed by one N tile, in elements
-  return (span + 63) / 64;
+static bool banded_ok(int Cin, int Cout, int sz) {
+  return !(Cin < 8 || Cout < 8 || 64 % Cin != 0 || 128 % Cout != 0 || sz < 1 || sz > 2);
 }
 
 extern "C" long long rn_conv3d_banded_bytes(int Cin, int Cout, int sz) {
-  if (Cin < 8 || Cout < 8 || 64 % Cin != 0 || 128 % Cout != 0 || sz < 1 || sz > 2) return -1;
-  return 9LL * banded_kblocks(Cin, Cout, sz) * 128 * 64 * 2;
+  if (!banded_ok(Cin, Cout, sz)) return -1;
+  const BandLayout L = band_layout(Cin, Cout, sz);
+  if (L.kblocks > 8) return -1;
+  return 2LL * 9LL * L.kblocks * 128 * 64 * 2;       // two arrangements (single CTA / CTA pair), 16-bit
 }
 
 extern "C" int rn_pack_conv3d_banded(const float* w, void* packed, int Cin, int Cout, int sz, int fmt, void* stream) {
-  if (!w || !packed || rn_conv3d_banded_bytes(Cin, Cout, sz) < 0) return -1;
-  const int kb = banded_kblocks(Cin, Cout, sz);
-  pack_banded_kernel<<<grid_for(9LL * kb * 128 * 64, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, static_cast<uint16_t*>(packed), Cin, Cout, kb, sz, fmt);
+  if (!w || !packed || rn_conv3d_banded_bytes(Cin, Cout, sz) < 0 || fmt < 0 || fmt > 2) return -1;
+  const BandLayout L = band_layout(Cin, Cout, sz);
+  const long long total = 2LL * 9LL * L.kblocks * 128 * 64;
+  pack_banded_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<uint16_t*>(packed), Cin, Cout, L, sz, fmt, total);
   RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }
@@ -1068,7 +1087,8 @@ extern "C" int rn_conv3d_banded_same(const void* x, const void* w_banded, const 
   rn_conv_desc d;
   memset(&d, 0, sizeof(d));
   d.ndim = 2; d.B = B; d.H = H; d.W = W; d.D = 1;
-  d.Cin = banded_kblocks(Cin, Cout, sz) * 64;      // K elements per (ky,kx) tap
+  d.Cin = band_layout(Cin, Cout, sz).kblocks * 64;  // K elements per (ky,kx) tap
+  d.band_cin = Cin; d.band_cout = Cout; d.band_sz = sz;
   d.Cout = static_cast<int>(Fo); d.cout_pad = static_cast<int>(Fo);
   d.ntaps = 9; d.taps = taps; d.x = x; d.w_packed = w_banded; d.bias = bias_full; d.alpha = alpha_full; d.act = act;
   d.residual = residual; d.residual_is_f32 = residual_is_f32; d.out16 = out16; d.out32 = out32;

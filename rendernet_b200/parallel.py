@@ -156,9 +156,16 @@ class ShardedRenderEngine:
 
     With world == 1 (or no process group) it degenerates to the engine itself."""
 
-    def __init__(self, engine, gather: str = "nccl", group=None):
-        if gather not in ("nccl", "peer", "none"):
-            raise ValueError("gather must be nccl | peer | none")
+    def __init__(self, engine, gather: str = "nccl_sync", group=None):
+        """gather: "nccl_sync" (default) = ncclAllGather on the COMPUTE stream right after the step, straight from the engine's
+        output buffer; "nccl" = the same collective on a side stream, overlapped with the next step; "peer" = copy-engine P2P
+        writes (PeerImageGather); "none".  Measured on 8 x B200 (profiles/r02_scale8_*.json, fast precision, 24 renders per GPU
+        and step): no gather 37.5 ms/step, overlapped NCCL 40.6, peer 44.9.  The overlapped collective is NOT free: the
+        persistent convolution kernels occupy every SM (1 CTA/SM, ~210 KB of shared memory each), so NCCL's CTAs only get SMs at
+        kernel boundaries and the next convolution then starts short of SMs -- 3.2 ms per step for a transfer that needs < 1 ms
+        of NVLink time.  Running it between two steps costs just that transfer time."""
+        if gather not in ("nccl", "nccl_sync", "peer", "none"):
+            raise ValueError("gather must be nccl_sync | nccl | peer | none")
         self.engine, self.group = engine, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -167,7 +174,9 @@ class ShardedRenderEngine:
         outs = list(engine.outputs) if not isinstance(engine.out, torch.Tensor) else [engine.out]   # Texture engine: 2 images
         self._multi = not isinstance(engine.out, torch.Tensor)
         self.peer = None
-        self.kind_note = {"nccl": "NCCL all-gather", "none": "no gather (per-rank outputs only)"}.get(self.kind, "")
+        self.kind_note = {"nccl": "NCCL all-gather on a side stream, overlapped with the next step",
+                          "nccl_sync": "NCCL all-gather on the compute stream between steps",
+                          "none": "no gather (per-rank outputs only)"}.get(self.kind, "")
         if self.kind == "peer" and len(outs) != 1:
             self.kind, self.kind_note = "nccl", "NCCL all-gather (peer gather handles one output tensor)"
         if self.kind == "peer":
@@ -185,11 +194,11 @@ class ShardedRenderEngine:
                 self.peer, self.kind, self.kind_note = None, "nccl", "NCCL all-gather (peer gather unavailable)"
             else:
                 self.kind_note = "copy-engine P2P writes over NVLink (CUDA IPC)"
-        if self.kind == "nccl":
+        if self.kind in ("nccl", "nccl_sync"):
             self.comm = torch.cuda.Stream(device=self.dev)
             self.gathered = [torch.empty((self.world * o.shape[0],) + tuple(o.shape[1:]), device=self.dev, dtype=o.dtype)
                              for o in outs]
-        if self.kind != "none":
+        if self.kind in ("nccl", "peer"):
             self.src = [torch.empty_like(o) for o in outs]       # the graph overwrites the engine's outputs every step
             self.ev_ready, self.ev_done = torch.cuda.Event(), torch.cuda.Event()
             self.ev_done.record(torch.cuda.current_stream(self.dev))
@@ -213,6 +222,10 @@ class ShardedRenderEngine:
 
     def _gather(self):
         if self.kind == "none":
+            return
+        if self.kind == "nccl_sync":                 # stream-ordered between this step and the next: no copy, no overlap
+            for g, o in zip(self.gathered, self._engine_outs()):
+                dist.all_gather_into_tensor(g, o, group=self.group)
             return
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(self.ev_done)                 # the previous gather has consumed self.src
@@ -244,6 +257,8 @@ class ShardedRenderEngine:
         Texture engine; this rank's own images when there is no gather)."""
         if self.kind == "none":
             return self.engine.out
+        if self.kind == "nccl_sync":
+            return tuple(self.gathered) if self._multi else self.gathered[0]
         torch.cuda.current_stream(self.dev).wait_event(self.ev_done)
         if self.peer is not None:
             return self.peer.last
