@@ -243,6 +243,28 @@ int rn_phong_composite(const float* img, const float* light_dir, const float* li
                        float k_diffuse, int background_white, int with_mask, float* out_f32, uint8_t* out_u8,
                        int B, int H, int W, void* stream);
 
+/* ---- backward pass: input gradients of the forward path --------------------------------------------
+ * What inverse rendering differentiates through the frozen network (Reconstruct_RenderNet_Face.py:383-412).  The data
+ * gradient of every stride-1 convolution / transposed convolution is itself a convolution and runs through rn_conv_igemm
+ * (mirrored taps, filters packed with the channel roles swapped: rendernet_b200/backward.py); these are the remaining pieces. */
+/* dL/d(pre) = g * (y > 0 ? 1 : alpha[c]) for y = prelu(pre) stored post-activation (alpha >= 0); 16-bit in/out, n elements,
+ * C = innermost (channel) extent.  tools/layer_util.py:27-45. */
+int rn_prelu_backward_16(const void* g, const void* y, const float* alpha, void* out, long long n, int C, int fmt, void* stream);
+/* Network output img = sigmoid(logits) (RenderNet_Shader.py:127-130): out16[p, c] = scale * g[p,c] * img[p,c] * (1 - img[p,c])
+ * for c < C, 0 for C <= c < Cpad (the last up-conv's data-gradient GEMM needs K % 16 == 0).  g, img fp32 [npix, C]. */
+int rn_sigmoid_backward(const float* g, const float* img, void* out16, long long npix, int C, int Cpad, float scale, int fmt,
+                        void* stream);
+/* Data gradient of the thin strided tf.nn.conv3d SAME layers (e_conv1 5^3 s2 1|5->8, e_conv2 3^3 s(1,1,2) 8->16;
+ * RenderNet_Shader.py:36-43): g16 [B,Ho,Wo,Do,Cout] 16-bit, w fp32 TF layout [k,k,k,Cin,Cout] -> dx16 (16-bit) and/or
+ * dx32 (fp32, multiplied by out_scale) [B,H,W,D,Cin]. */
+int rn_conv3d_backward_data_direct(const void* g16, const float* w, void* dx16, float* dx32, int B, int H, int W, int D, int Cin,
+                                   int Cout, int k, int sy, int sx, int sz, float out_scale, int fmt, void* stream);
+/* Backward of rn_resample_f32: gout = dL/dout [B,new,new,new,C] fp32 -> dvox [B,size^3,C] += (scatter-add of the 8 corner
+ * weights; may be NULL) and dminv [B,3,4] += dL/d(inverse sampling matrix) (may be NULL).  Both are ACCUMULATED into: zero
+ * them first.  Points outside the cube contribute nothing (the forward writes exact zeros there).  C = 1 or 4. */
+int rn_resample_backward_f32(const float* vox, const float* minv, const float* gout, float* dvox, float* dminv, int B, int C,
+                             int size, int new_size, int transform, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

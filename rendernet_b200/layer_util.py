@@ -83,6 +83,13 @@ def _alpha_arg(alpha, cout_pad):
     return _dev_vec(alpha, cout_pad)
 
 
+def _record(**rec):
+    """Append a layer record to the store's tape (backward.py differentiates the recorded forward pass)."""
+    tape = _store().tape
+    if tape is not None:
+        tape.append(rec)
+
+
 # ------------------------------------------------------------------------------------------ reference API
 def projection_unit(input, n_features=18, scope='projection_unit'):
     """layer_util.py:8-22.  [B,H,W,D,C] -> reshape [B,H,W,D*C] (free in channel-last) -> 1x1 conv -> PReLU.
@@ -354,6 +361,11 @@ def _deferred_conv(kind, x, w, b, stride):
 
     def run(act, alpha, residual, want32):
         xt = _as16(xin)
+        y = _run(xt, act, alpha, residual, want32)
+        _record(op="conv", kind=kind, stride=stride, x=xt, w=w, b=b, act=act, alpha=alpha, residual=residual, y=y)
+        return y
+
+    def _run(xt, act, alpha, residual, want32):
         banded = (kind == "conv3d" and USE_BANDED_CONV3D and tuple(w.shape[:3]) == (3, 3, 3)
                   and ops.BandedConv3d.eligible(int(w.shape[3]), int(w.shape[4]), int(xt.shape[3]), stride))
         if kind == "conv3d" and stride != 1 and not banded:
@@ -464,11 +476,16 @@ def _deferred_direct3d(x, w, b, stride):
             # resample + axis transform + e_conv1 + bias + PReLU in one kernel; the 128^3 grid is never written
             bd = _dev_vec(b) if b is not None else torch.zeros(cout, device=wd.device, dtype=torch.float32)
             ad = _alpha_arg(alpha, cout) if act == "prelu" else None
-            return ops.resample_conv1(xin.voxel, xin.minv, xin.new_size, wd, bd, ad, tf.COMPUTE_DTYPE, fmt=_store().fmt)
+            y = ops.resample_conv1(xin.voxel, xin.minv, xin.new_size, wd, bd, ad, tf.COMPUTE_DTYPE, fmt=_store().fmt)
+            _record(op="resample_conv1", grid=xin, w=w, b=b, act=act, alpha=alpha, stride=list(stride), y=y)
+            return y
         xt = realize(xin)
         if not xt.is_cuda:
             xt = xt.to(_store().device)
         bd = _dev_vec(b) if b is not None else torch.zeros(cout, device=xt.device, dtype=torch.float32)
+        if _store().tape is not None:
+            raise NotImplementedError("backward tape: the thin direct conv3d is only differentiated in its fused "
+                                      "resample + e_conv1 form (Shader path)")
         if act == "prelu":
             ad = _alpha_arg(alpha, cout)
             y = ops.conv3d_direct(xt if isinstance(xt, ops.Split16) else xt.contiguous(), wd, bd, ad, stride, tf.COMPUTE_DTYPE, fmt=_store().fmt)

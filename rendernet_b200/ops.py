@@ -668,3 +668,76 @@ def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     check(lib.rn_concat_channels_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel() // Ca, Ca, Cb, _stream()),
           "rn_concat_channels_f32")
     return out
+
+
+# --------------------------------------------------------------------------------------- backward (input gradients)
+def conv2d_taps(x, w_packed, bias, taps, cout: int, cout_pad: int, fmt: int, residual=None, ny: int = 0, want32: bool = False,
+                dtype: torch.dtype = torch.float16):
+    """Stride-1 2-D convolution with an explicit tap list (dx, dy) over the packed filter [ntaps][cout_pad][Cin]
+    (rn_conv_igemm): what the data gradients of the k = 4 convolutions need (their mirrored taps are not a TF SAME set).
+    x: 16-bit [B,H,W,Cin] (Split16 for fmt 2); returns 16-bit [B,H,W,cout] (or fp32 with want32)."""
+    x = _act_in(x, fmt, dtype)
+    B, H, W, Cin = x.shape
+    out16 = None if want32 else _alloc16((B, H, W, cout), fmt, dtype, x.device)
+    out32 = torch.empty((B, H, W, cout), device=x.device, dtype=torch.float32) if want32 else None
+    residual, _ = _residual(residual, fmt)
+    conv_igemm_raw(x, w_packed, bias, [(int(t[0]), int(t[1]), 0) for t in taps], 2, B, H, W, 1, Cin, cout, cout_pad,
+                   out16=out16, out32=out32, residual=residual, fmt=fmt, ny=ny)
+    return out32 if want32 else _wrap16(out16, fmt)
+
+
+def prelu_backward(g, y, alpha: torch.Tensor):
+    """dL/d(pre) = g * (y > 0 ? 1 : alpha[c]) (rn_prelu_backward_16); g, y 16-bit tensors of one format, alpha fp32 [C]."""
+    g, y = _cuda(g), _cuda(y)
+    fmt = 2 if isinstance(g, Split16) else fmt_of(g.dtype)
+    if isinstance(y, Split16) != (fmt == 2) or tuple(g.shape) != tuple(y.shape):
+        raise TypeError("prelu_backward: g and y must have the same shape and 16-bit format")
+    C_ = g.shape[-1]
+    alpha = _cuda(alpha.to(device=g.device, dtype=torch.float32))
+    assert alpha.numel() >= C_
+    out = _alloc16(g.shape, fmt, torch.float16 if fmt != 1 else torch.bfloat16, g.device)
+    check(lib.rn_prelu_backward_16(g.data_ptr(), y.data_ptr(), alpha.data_ptr(), out.data_ptr(), g.numel(), C_, fmt, _stream()),
+          "rn_prelu_backward_16")
+    return _wrap16(out, fmt)
+
+
+def sigmoid_backward(g: torch.Tensor, img: torch.Tensor, c_pad: int, scale: float, fmt: int):
+    """scale * g * img * (1 - img), zero padded to c_pad channels, as a 16-bit tensor [..., c_pad] (rn_sigmoid_backward)."""
+    g, img = _cuda(g, torch.float32), _cuda(img, torch.float32)
+    assert g.shape == img.shape
+    Cc = img.shape[-1]
+    shape = tuple(img.shape[:-1]) + (c_pad,)
+    out = _alloc16(shape, fmt, torch.float16, img.device)
+    check(lib.rn_sigmoid_backward(g.data_ptr(), img.data_ptr(), out.data_ptr(), img.numel() // Cc, Cc, c_pad, float(scale), fmt,
+                                  _stream()), "rn_sigmoid_backward")
+    return _wrap16(out, fmt)
+
+
+def conv3d_backward_data_direct(g, w_tf: torch.Tensor, in_shape, stride: Sequence[int], want32: bool = False,
+                                out_scale: float = 1.0):
+    """Data gradient of a thin strided SAME conv3d: g 16-bit [B,Ho,Wo,Do,Cout], w_tf fp32 [k,k,k,Cin,Cout], in_shape =
+    (B,H,W,D,Cin) of the forward input -> 16-bit (or fp32 x out_scale) gradient of that shape."""
+    g = _cuda(g)
+    fmt = 2 if isinstance(g, Split16) else fmt_of(g.dtype)
+    w_tf = _cuda(w_tf, torch.float32)
+    B, H, W, D, Cin = (int(v) for v in in_shape)
+    k, Cout = int(w_tf.shape[0]), int(w_tf.shape[4])
+    out16 = None if want32 else _alloc16((B, H, W, D, Cin), fmt, torch.float16, g.device)
+    out32 = torch.empty((B, H, W, D, Cin), device=g.device, dtype=torch.float32) if want32 else None
+    check(lib.rn_conv3d_backward_data_direct(g.data_ptr(), w_tf.data_ptr(), _ptr(out16), _ptr(out32), B, H, W, D, Cin, Cout, k,
+                                             int(stride[0]), int(stride[1]), int(stride[2]), float(out_scale), fmt, _stream()),
+          "rn_conv3d_backward_data_direct")
+    return out32 if want32 else _wrap16(out16, fmt)
+
+
+def resample_backward(vox: torch.Tensor, minv: torch.Tensor, gout: torch.Tensor, transform: bool, want_dvox: bool = True,
+                      want_dminv: bool = True):
+    """Backward of `resample`: gout fp32 [B,N,N,N,C] -> (dvox [B,S,S,S,C] or None, dminv [B,3,4] or None), fp32."""
+    vox, minv, gout = _cuda(vox, torch.float32), _cuda(minv, torch.float32), _cuda(gout, torch.float32)
+    B, S, _, _, Cc = vox.shape
+    N = gout.shape[1]
+    dvox = torch.zeros_like(vox) if want_dvox else None
+    dminv = torch.zeros_like(minv) if want_dminv else None
+    check(lib.rn_resample_backward_f32(vox.data_ptr(), minv.data_ptr(), gout.data_ptr(), _ptr(dvox), _ptr(dminv), B, Cc, S, N,
+                                       1 if transform else 0, _stream()), "rn_resample_backward_f32")
+    return dvox, dminv

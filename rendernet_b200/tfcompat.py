@@ -50,6 +50,7 @@ class VariableStore:
         self.strict = False            # True: get_variable raises for a name that is not among the loaded weights
         self.loaded: set = set()       # names installed by load_weight_dict
         self.consumed: set = set()     # loaded names a model function has asked for
+        self.tape = None               # list -> every realised layer appends a record (rendernet_b200/backward.py)
 
     @property
     def fmt(self) -> int:

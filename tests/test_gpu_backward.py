@@ -1,0 +1,199 @@
+"""GPU tests of the backward (input-gradient) pass, SURVEY §8 f-4 first stage: every gradient is compared with
+torch.autograd on the CPU oracle (the PyTorch restatement of the reference graph), so the reference for d/d(input) is
+exactly what `tf.gradients` would produce for that graph (Reconstruct_RenderNet_Face.py:383-412).
+
+Tolerances: relative to the largest reference gradient entry; exact precision 2e-3 (fp32-level operands, the remaining error
+is the fp16 hi/lo storage of gradients and accumulation order), fast precision 3e-2 (fp16 operands in ~60 chained layers).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import rendernet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def _rel_err(got, want):
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+# ----------------------------------------------------------------------------------------- differentiable oracle pieces
+def _torch_resample(vox, minv, new_size, size):
+    """Differentiable (w.r.t. vox and minv) restatement of tf_resampling + tf_interpolate + the axis transform, float64, with the
+    reference's clamp rule (zero outside [0, size-1)); flat index order of tools/resampling_voxel_grid.py:427-449."""
+    B, C = vox.shape[0], vox.shape[-1]
+    N = new_size
+    p, q, r = torch.meshgrid(torch.arange(N, dtype=torch.float64), torch.arange(N, dtype=torch.float64),
+                             torch.arange(N, dtype=torch.float64), indexing="ij")
+    g = torch.stack([r, (N - 1) - p, q, torch.ones_like(p)], 0).reshape(4, -1)            # N[b,p,q,r] = sample(Minv . (r, N-1-p, q, 1))
+    pts = minv @ g                                                                        # [B,3,N^3]
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    lim = size - 1
+    inside = (x >= 0) & (x < lim) & (y >= 0) & (y < lim) & (z >= 0) & (z < lim)
+    x0, y0, z0 = (torch.floor(t).clamp(0, lim - 1) for t in (x, y, z))
+    ax, bx, ay, by, az, bz = (x0 + 1) - x, x - x0, (y0 + 1) - y, y - y0, (z0 + 1) - z, z - z0
+    xi, yi, zi = x0.long(), y0.long(), z0.long()
+    flat = vox.reshape(B, -1, C)
+    out = 0
+    for dz, wz in ((0, az), (1, bz)):
+        for dy, wy in ((0, ay), (1, by)):
+            for dx, wx in ((0, ax), (1, bx)):
+                idx = ((zi + dz) * size + (yi + dy)) * size + (xi + dx)
+                out = out + (wx * wy * wz).unsqueeze(-1) * torch.gather(flat, 1, idx.unsqueeze(-1).expand(-1, -1, C))
+    out = out * inside.unsqueeze(-1)
+    return out.reshape(B, N, N, N, C)
+
+
+# ----------------------------------------------------------------------------------------- single operations
+def test_resample_backward_matches_autograd():
+    """dL/dvox and dL/dMinv of the resampler (C = 1 and C = 4) vs autograd through a float64 restatement."""
+    from rendernet_b200 import ops
+    rng = np.random.default_rng(0)
+    for C in (1, 4):
+        B, S, N = 2, 16, 32
+        vox = rng.random((B, S, S, S, C)).astype(np.float32)
+        poses = np.stack([rng.uniform(0, 6.28, B), rng.uniform(-1.0, 1.0, B), rng.uniform(0.8, 1.3, B)], 1).astype(np.float32)
+        R, Sm = orc.rotation_around_grid_centroid(poses)
+        minv = orc.inverse_total_matrix(R, Sm, S, N)
+        G = rng.standard_normal((B, N, N, N, C)).astype(np.float32)
+        vt = torch.tensor(vox.astype(np.float64), requires_grad=True)
+        mt = torch.tensor(minv.astype(np.float64), requires_grad=True)
+        out = _torch_resample(vt, mt, N, S)
+        fwd = ops.resample(torch.from_numpy(vox).to(dev), torch.from_numpy(minv).to(dev), N, True)
+        assert _rel_err(fwd.cpu().numpy(), out.detach().numpy()) < 1e-5                  # the restatement IS the forward op
+        (out * torch.from_numpy(G).double()).sum().backward()
+        dvox, dminv = ops.resample_backward(torch.from_numpy(vox).to(dev), torch.from_numpy(minv).to(dev),
+                                            torch.from_numpy(G).to(dev), True)
+        e1, e2 = _rel_err(dvox.cpu().numpy(), vt.grad.numpy()), _rel_err(dminv.cpu().numpy(), mt.grad.numpy())
+        print(f"resampler backward C={C}: dvox rel err {e1:.2e}, dMinv rel err {e2:.2e}")
+        assert e1 < 1e-4 and e2 < 1e-3
+
+
+def test_pose_matrix_vjp_matches_finite_differences():
+    from rendernet_b200.backward import pose_matrix_jacobian_vjp
+    from rendernet_b200.engine import pose_to_matrix
+    rng = np.random.default_rng(1)
+    vp = np.stack([rng.uniform(0, 6.28, 3), rng.uniform(-1.0, 1.0, 3), rng.uniform(0.8, 1.3, 3)], 1)
+    dm = rng.standard_normal((3, 3, 4))
+    got = pose_matrix_jacobian_vjp(vp, dm)
+    eps = 1e-3
+    for j in range(3):
+        d = np.zeros_like(vp); d[:, j] = eps
+        fd = ((pose_to_matrix(vp + d).astype(np.float64) - pose_to_matrix(vp - d).astype(np.float64)) / (2 * eps) * dm).sum((1, 2))
+        assert np.allclose(got[:, j], fd, rtol=2e-2, atol=2e-2 * np.abs(fd).max()), (j, got[:, j], fd)
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_layer_data_gradients_match_autograd(precision):
+    """One recorded layer of each kind: forward through layer_util with a tape, backward through ShaderInputGradients' rules,
+    vs autograd of the oracle op.  (The whole-network test below exercises the same code end to end.)"""
+    from rendernet_b200 import layer_util as lu, ops, tfcompat as tf
+    from rendernet_b200.backward import ShaderInputGradients
+    rng = np.random.default_rng(3)
+    fmt = 2 if precision == "exact" else 0
+    tol = 2e-3 if precision == "exact" else 2e-2
+    cases = [("conv2d", 3, 64, 128, 1, (2, 16, 16)), ("conv2d", 4, 64, 32, 1, (1, 16, 24)), ("conv2d", 1, 128, 64, 1, (1, 8, 16)),
+             ("conv2d_transpose", 4, 32, 64, 1, (1, 16, 16)), ("conv2d_transpose", 4, 16, 3, 1, (1, 16, 32)),
+             ("conv2d_transpose", 4, 64, 32, 2, (2, 8, 8)), ("conv3d", 3, 32, 32, 1, (1, 8, 8, 32)), ("conv3d", 3, 16, 32, 1, (1, 8, 8, 32)),
+             ("conv3d", 3, 8, 16, 2, (1, 8, 8, 64))]
+    for kind, k, cin, cout, stride, sp in cases:
+        ig = ShaderInputGradients(None, 1, precision=precision)
+        x = rng.standard_normal(sp + (cin,)).astype(np.float32)
+        if kind == "conv2d":
+            w = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+            ref_fn = lambda xt: orc.conv2d(xt, w, None)                                         # noqa: E731
+        elif kind == "conv2d_transpose":
+            w = (rng.standard_normal((k, k, cout, cin)) / np.sqrt(k * k * cin)).astype(np.float32)
+            ref_fn = lambda xt: orc.conv2d_transpose(xt, w, None, (stride, stride))            # noqa: E731
+        else:
+            w = (rng.standard_normal((k, k, k, cin, cout)) / np.sqrt(k ** 3 * cin)).astype(np.float32)
+            ref_fn = lambda xt: orc.conv3d(xt, w, None, (1, 1, stride))                         # noqa: E731
+        alpha = rng.uniform(0.05, 0.3, cout).astype(np.float32)
+        xt = torch.tensor(x, requires_grad=True)
+        yref = orc.prelu(ref_fn(xt), alpha)
+        G = rng.standard_normal(tuple(yref.shape)).astype(np.float32)
+        (yref * torch.from_numpy(G)).sum().backward()
+        # forward on the device with a tape, through the same deferred-layer machinery the model functions use
+        tape = []
+        ig.store.tape = tape
+        with tf.use_store(ig.store):
+            xs = ops.cast_to_16(torch.from_numpy(x).to(dev), fmt=fmt)
+            with tf.variable_scope("t"):
+                wv = tf.get_variable("weights", initializer=w)
+                av = tf.get_variable("alpha", initializer=alpha)
+            d = lu._deferred_conv(kind, xs, wv, None, stride)
+            d.act, d.alpha = "prelu", av
+            y = d.realize()
+        ig.store.tape = None
+        e_f = _rel_err(tf.to_float(y).cpu().numpy(), yref.detach().numpy())
+        # backward: seed the gradient of y (scaled like the real pass) and apply one tape step
+        rec = tape[-1]
+        g = ops.cast_to_16(torch.from_numpy(G).to(dev) * 64.0, fmt=fmt)
+        with tf.use_store(ig.store):
+            g = ops.prelu_backward(g, rec["y"], ig._alpha(rec["alpha"], cout))
+            if kind == "conv3d" and stride == 2:
+                gx = ops.conv3d_backward_data_direct(g, rec["w"].to(dev).float().contiguous(), tuple(xs.shape), (1, 1, 2))
+            else:
+                L = ig._dgrad_layer(rec)
+                if kind == "conv3d":
+                    gx = ops.conv3d_banded(g, L)
+                elif kind == "conv2d" and k % 2 == 0:
+                    gx = ops.conv2d_taps(g, L.w, L.bias, L.taps, L.cout, L.cout_pad, fmt, ny=k if L.cin % 64 == 0 else 0)
+                elif kind == "conv2d_transpose" and stride == 2:
+                    gx = ops.conv2d(ig._space_to_depth(g), L)
+                elif kind == "conv2d_transpose" and cout % 16 != 0:
+                    gp = torch.zeros(tuple(g.shape[:-1]) + (16,), device=dev)
+                    gp[..., :cout] = tf.to_float(g)
+                    gx = ops.conv2d(ops.cast_to_16(gp, fmt=fmt), L)
+                else:
+                    gx = ops.conv2d(g, L)
+        e_b = _rel_err(tf.to_float(gx).cpu().numpy() / 64.0, xt.grad.numpy())
+        print(f"[{precision}] {kind} k{k} {cin}->{cout} s{stride}: forward err {e_f:.2e}, data-gradient err {e_b:.2e}")
+        assert e_b < tol, (kind, k, cin, cout, stride, e_b)
+
+
+# ----------------------------------------------------------------------------------------- whole network
+def _oracle_gradients(vox, poses, W, G):
+    """autograd through the whole oracle graph: float64 resampler restatement -> fp32 rendernet_shader."""
+    B = vox.shape[0]
+    R, Sm = orc.rotation_around_grid_centroid(poses)
+    minv = orc.inverse_total_matrix(R, Sm, 64, 128)
+    vt = torch.tensor(vox.astype(np.float64), requires_grad=True)
+    mt = torch.tensor(minv.astype(np.float64), requires_grad=True)
+    grid = _torch_resample(vt, mt, 128, 64)
+    img = orc.rendernet_shader(grid.float(), W)
+    (img * torch.from_numpy(G)).sum().backward()
+    return img.detach().numpy(), vt.grad.numpy(), mt.grad.numpy()
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_full_size_input_gradients_match_oracle_autograd(golden_dir, precision):
+    """Full-size Shader network (chair, demo pose, 64^3 -> 512^2): dL/dvoxels and dL/d(azimuth, elevation, scale) of a random
+    linear image loss vs torch.autograd through the CPU oracle -- the gradients inverse rendering needs
+    (Reconstruct_RenderNet_Face.py:383-412)."""
+    from rendernet_b200.backward import ShaderInputGradients, pose_matrix_jacobian_vjp
+    bv = np.load(os.path.join(golden_dir, "binvox.npz"))
+    vox = np.unpackbits(bv["chair_bits"]).reshape(1, 64, 64, 64, 1).astype(np.float32)
+    vox = vox * 0.75 + 0.125 * (np.random.default_rng(2).random(vox.shape) < 0.02)     # continuous occupancies, as inverse rendering feeds
+    poses = orc.compute_pose_param(250.0, 60.0, 3.3).astype(np.float32)
+    W = orc.init_shader_weights(seed=1, alpha_range=(0.05, 0.3), bias_jitter=0.02)
+    G = np.random.default_rng(5).standard_normal((1, 512, 512, 3)).astype(np.float32)
+    img_ref, dvox_ref, dminv_ref = _oracle_gradients(vox, poses, W, G)
+    dpose_ref = pose_matrix_jacobian_vjp(poses, dminv_ref)
+    ig = ShaderInputGradients(W, 1, precision=precision)
+    img = ig.forward(vox, poses)
+    assert float(np.abs(img.cpu().numpy() - img_ref).max()) < 1e-3
+    dvox, dpose = ig.backward(G)
+    e_v, e_p = _rel_err(dvox, dvox_ref), _rel_err(dpose, dpose_ref)
+    cos = float((dvox.ravel() * dvox_ref.ravel()).sum() / (np.linalg.norm(dvox) * np.linalg.norm(dvox_ref)))
+    print(f"[{precision}] dL/dvox rel-max err {e_v:.2e} (cosine {cos:.6f}), dL/dpose {dpose} vs {dpose_ref} rel err {e_p:.2e}")
+    tol = 5e-3 if precision == "exact" else 5e-2
+    assert e_v < tol and e_p < tol and cos > (0.9999 if precision == "exact" else 0.999)
