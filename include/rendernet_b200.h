@@ -215,6 +215,14 @@ int rn_conv3d_direct(const void* x, int x_is_f32, const float* w, const float* b
 int rn_resample_conv1_fused(const float* vox, const float* minv, const float* w, const float* bias,
                             const float* alpha, void* out16, int B, int size, int new_size, int fmt, void* stream);
 
+/* The same fusion for the Texture/Normal network's input (BASELINE config 4; RenderNet_Texture_Face_Normal.py:155-179):
+ * tf_rotation_resampling of the geometry grid (vox fp32 [B,size^3], C = 1) AND of the decoded texture volume (tex fp32
+ * [B,size^3,4], 16-byte aligned) with the same pose + axis transform + tf.concat(axis=4) (:178) + e_conv1 5^3 stride 2,
+ * 5 -> 8 (w fp32 [5,5,5,5,8]) + bias + PReLU, one kernel; bit-identical to rn_resample_f32 x2 -> rn_concat_channels_f32 ->
+ * rn_conv3d_direct. */
+int rn_resample5_conv1_fused(const float* vox, const float* tex, const float* minv, const float* w, const float* bias,
+                             const float* alpha, void* out16, int B, int size, int new_size, int fmt, void* stream);
+
 /* ---- binvox run-length decode on the device (tools/binvox_rw.py:84-93) ----------------------
  * pairs: the raw (value, count) byte pairs of n_items files back to back; run_start[r] = number of voxels before run r
  * WITHIN its item (exclusive prefix sum of the counts, host-computed); item_first_run[i] = index of item i's first

@@ -11,7 +11,7 @@ from . import tfcompat as tf
 from .layer_util import (conv2d, conv2d_transpose, conv3d, conv3d_transpose, fully_connected, keep_prob, prelu,
                          projection_unit, res_block_2d, res_block_3d)
 from .model_util import tf_transform_voxel_to_match_image
-from .resampling_voxel_grid import tf_rotation_resampling
+from .resampling_voxel_grid import concat_resampled, tf_rotation_resampling
 from .tfcompat import realize
 
 
@@ -120,5 +120,5 @@ def render_graph(model_in, texture_in, param_in, prob=0.75, new_res=128, is_trai
     texture_decoded = decoder_texture(z_in=texture_in)
     texture_rotated = tf_transform_voxel_to_match_image(
         tf_rotation_resampling(texture_decoded, param_in, new_size=new_res))
-    model_texture_concat = ops.concat_channels(rotated_models, texture_rotated)        # tf.concat(..., 4) (:178)
+    model_texture_concat = concat_resampled(rotated_models, texture_rotated)          # tf.concat(..., 4) (:178), kept deferred
     return RenderNet(model_texture_concat, prob=prob, is_training=is_training)

@@ -557,6 +557,173 @@ __global__ void __launch_bounds__(256) resample_conv1_kernel(const float* __rest
 }
 
 
+// ------------------------------------------------------------------------------------------ resampler x2 (+) concat (+) e_conv1, Texture net
+// BASELINE config 4 (RenderNet_Texture_Face_Normal.py:155-179): the geometry grid (C = 1) and the decoded texture volume
+// (C = 4) are resampled with the SAME pose, concatenated on the channel axis and fed to e_conv1 (5^3, stride 2, 5 -> 8).
+// Unfused that is two gathers, a concat and a CUDA-core conv over a 128^3 x 5 fp32 grid (42 MB per render written and read
+// back).  Fused exactly like resample_conv1_kernel: one CTA = 8^3 outputs, the 19^3 x 5 input points it needs are sampled
+// into shared memory (one set of trilinear weights per point, five gathers per corner), tiles outside the rotated cube skip
+// both the gather and the convolution, tiles that sampled only zeros skip the convolution.  Accumulation order per output =
+// conv3d_direct_kernel<5,8,5>'s (ky, kx, kz, ci), so the result is bit-identical to the unfused chain.
+constexpr int RC5_C = 5;
+constexpr int RC5_TILE = RC_IN * RC_IN * RC_ZP;          // floats per channel plane of the input tile
+
+__global__ void __launch_bounds__(256) resample5_conv1_kernel(const float* __restrict__ vox, const float* __restrict__ tex,
+                                                              const float* __restrict__ minv, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, const float* __restrict__ alpha,
+                                                              uint16_t* __restrict__ out, int B, int size, int nsz, int fmt) {
+  extern __shared__ __align__(16) float smem5[];
+  float* tile = smem5;                                   // [5][19*19*20]
+  float* ws = smem5 + RC5_C * RC5_TILE;                  // [125][5][8]
+  const int tid = threadIdx.x;
+  const int No = nsz >> 1;
+  const int tpe = No / RC_T;
+  int bid = blockIdx.x;
+  const int tz = bid % tpe; bid /= tpe;
+  const int tx = bid % tpe; bid /= tpe;
+  const int ty = bid % tpe;
+  const int b = bid / tpe;
+  for (int i = tid; i < 125 * RC5_C * 8; i += 256) ws[i] = __ldg(w + i);
+
+  const float* M = minv + b * 12;
+  const float m00 = __ldg(M + 0), m01 = __ldg(M + 1), m02 = __ldg(M + 2), m03 = __ldg(M + 3);
+  const float m10 = __ldg(M + 4), m11 = __ldg(M + 5), m12 = __ldg(M + 6), m13 = __ldg(M + 7);
+  const float m20 = __ldg(M + 8), m21 = __ldg(M + 9), m22 = __ldg(M + 10), m23 = __ldg(M + 11);
+  const float lim = static_cast<float>(size - 1);
+  const size_t vol = static_cast<size_t>(size) * size * size;
+  const float* vb = vox + static_cast<size_t>(b) * vol;
+  const float* tb = tex + static_cast<size_t>(b) * vol * 4;
+  const size_t sy = static_cast<size_t>(size), sz = static_cast<size_t>(size) * size;
+  const int p0 = 2 * ty * RC_T - 1, q0 = 2 * tx * RC_T - 1, r0 = 2 * tz * RC_T - 1;
+
+  int nonzero = 0;
+  bool maybe_inside = true;
+  {
+    const float pl = static_cast<float>(max(p0, 0)), ph = static_cast<float>(min(p0 + RC_IN - 1, nsz - 1));
+    const float ql = static_cast<float>(max(q0, 0)), qh = static_cast<float>(min(q0 + RC_IN - 1, nsz - 1));
+    const float rl = static_cast<float>(max(r0, 0)), rh = static_cast<float>(min(r0 + RC_IN - 1, nsz - 1));
+    const float gyl = static_cast<float>(nsz - 1) - ph, gyh = static_cast<float>(nsz - 1) - pl;
+    const float mrow[3][4] = {{m00, m01, m02, m03}, {m10, m11, m12, m13}, {m20, m21, m22, m23}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float lo = fminf(mrow[a][0] * rl, mrow[a][0] * rh) + fminf(mrow[a][1] * gyl, mrow[a][1] * gyh) +
+                       fminf(mrow[a][2] * ql, mrow[a][2] * qh) + mrow[a][3];
+      const float hi = fmaxf(mrow[a][0] * rl, mrow[a][0] * rh) + fmaxf(mrow[a][1] * gyl, mrow[a][1] * gyh) +
+                       fmaxf(mrow[a][2] * ql, mrow[a][2] * qh) + mrow[a][3];
+      if (hi < -0.01f || lo > lim + 0.01f) maybe_inside = false;
+    }
+  }
+  if (maybe_inside) {
+    int iz = tid % RC_IN, row = tid / RC_IN;
+    for (int i = tid; i < RC_IN * RC_IN * RC_IN; i += 256) {
+      const int iy = row / RC_IN, ix = row - iy * RC_IN;
+      const int p = p0 + iy, q = q0 + ix, r = r0 + iz;
+      float v[RC5_C] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (p >= 0 && p < nsz && q >= 0 && q < nsz && r >= 0 && r < nsz) {
+        const float gx = static_cast<float>(r), gy = static_cast<float>(nsz - 1 - p), gz = static_cast<float>(q);
+        const float x = sample_coord(m00, m01, m02, m03, gx, gy, gz);
+        const float y = sample_coord(m10, m11, m12, m13, gx, gy, gz);
+        const float z = sample_coord(m20, m21, m22, m23, gx, gy, gz);
+        if (x >= 0.f && x < lim && y >= 0.f && y < lim && z >= 0.f && z < lim) {
+          const float x0f = floorf(x), y0f = floorf(y), z0f = floorf(z);
+          const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f), z0 = static_cast<int>(z0f);
+          const float x1f = x0f + 1.f, y1f = y0f + 1.f, z1f = z0f + 1.f;
+          const float ax = __fsub_rn(x1f, x), bxw = __fsub_rn(x, x0f);
+          const float ay = __fsub_rn(y1f, y), byw = __fsub_rn(y, y0f);
+          const float az = __fsub_rn(z1f, z), bzw = __fsub_rn(z, z0f);
+          const float wgt[8] = {__fmul_rn(__fmul_rn(ax, ay), az), __fmul_rn(__fmul_rn(ax, byw), az),
+                                __fmul_rn(__fmul_rn(bxw, ay), az), __fmul_rn(__fmul_rn(bxw, byw), az),
+                                __fmul_rn(__fmul_rn(ax, ay), bzw), __fmul_rn(__fmul_rn(ax, byw), bzw),
+                                __fmul_rn(__fmul_rn(bxw, ay), bzw), __fmul_rn(__fmul_rn(bxw, byw), bzw)};
+          const size_t c000 = (static_cast<size_t>(z0) * size + y0) * size + x0;
+          const size_t off[8] = {c000, c000 + sy, c000 + 1, c000 + sy + 1, c000 + sz, c000 + sz + sy, c000 + sz + 1,
+                                 c000 + sz + sy + 1};                                   // corners a..h (:440-449)
+          float s = __fmul_rn(wgt[0], __ldg(vb + off[0]));                              // add_n order a..h (:485)
+#pragma unroll
+          for (int k = 1; k < 8; ++k) s = __fadd_rn(s, __fmul_rn(wgt[k], __ldg(vb + off[k])));
+          v[0] = s;
+          float4 t4 = __ldg(reinterpret_cast<const float4*>(tb) + off[0]);
+          float t0 = __fmul_rn(wgt[0], t4.x), t1 = __fmul_rn(wgt[0], t4.y), t2 = __fmul_rn(wgt[0], t4.z), t3 = __fmul_rn(wgt[0], t4.w);
+#pragma unroll
+          for (int k = 1; k < 8; ++k) {
+            t4 = __ldg(reinterpret_cast<const float4*>(tb) + off[k]);
+            t0 = __fadd_rn(t0, __fmul_rn(wgt[k], t4.x)); t1 = __fadd_rn(t1, __fmul_rn(wgt[k], t4.y));
+            t2 = __fadd_rn(t2, __fmul_rn(wgt[k], t4.z)); t3 = __fadd_rn(t3, __fmul_rn(wgt[k], t4.w));
+          }
+          v[1] = t0; v[2] = t1; v[3] = t2; v[4] = t3;
+        }
+      }
+      const int ti = row * RC_ZP + (iz & 1) * 10 + (iz >> 1);
+#pragma unroll
+      for (int c = 0; c < RC5_C; ++c) {
+        nonzero |= (v[c] != 0.f);
+        tile[c * RC5_TILE + ti] = v[c];
+      }
+      iz += 256 % RC_IN;
+      row += 256 / RC_IN;
+      if (iz >= RC_IN) { iz -= RC_IN; ++row; }
+    }
+  }
+  const int any = __syncthreads_or(nonzero);
+
+  const int oz = tid & 7, ox = (tid >> 3) & 7, oy = tid >> 6;   // second output: oy + 4
+  float acc0[8], acc1[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc0[c] = acc1[c] = 0.f;
+  if (any) {
+    for (int ky = 0; ky < 5; ++ky) {
+      for (int kx = 0; kx < 5; ++kx) {
+        const float* t0 = tile + ((2 * oy + ky) * RC_IN + (2 * ox + kx)) * RC_ZP + oz;
+        const float* t1 = t0 + 8 * RC_IN * RC_ZP;
+        const float* wk = ws + (ky * 5 + kx) * 5 * RC5_C * 8;
+#pragma unroll
+        for (int kz = 0; kz < 5; ++kz) {
+          const int zi = (kz & 1) * 10 + (kz >> 1);
+#pragma unroll
+          for (int c = 0; c < RC5_C; ++c) {
+            const float a0 = t0[c * RC5_TILE + zi], a1 = t1[c * RC5_TILE + zi];
+            const float4 wlo = *reinterpret_cast<const float4*>(wk + (kz * RC5_C + c) * 8);
+            const float4 whi = *reinterpret_cast<const float4*>(wk + (kz * RC5_C + c) * 8 + 4);
+            acc0[0] = fmaf(a0, wlo.x, acc0[0]); acc0[1] = fmaf(a0, wlo.y, acc0[1]);
+            acc0[2] = fmaf(a0, wlo.z, acc0[2]); acc0[3] = fmaf(a0, wlo.w, acc0[3]);
+            acc0[4] = fmaf(a0, whi.x, acc0[4]); acc0[5] = fmaf(a0, whi.y, acc0[5]);
+            acc0[6] = fmaf(a0, whi.z, acc0[6]); acc0[7] = fmaf(a0, whi.w, acc0[7]);
+            acc1[0] = fmaf(a1, wlo.x, acc1[0]); acc1[1] = fmaf(a1, wlo.y, acc1[1]);
+            acc1[2] = fmaf(a1, wlo.z, acc1[2]); acc1[3] = fmaf(a1, wlo.w, acc1[3]);
+            acc1[4] = fmaf(a1, whi.x, acc1[4]); acc1[5] = fmaf(a1, whi.y, acc1[5]);
+            acc1[6] = fmaf(a1, whi.z, acc1[6]); acc1[7] = fmaf(a1, whi.w, acc1[7]);
+          }
+        }
+      }
+    }
+  }
+  uint32_t pk0[4], pk1[4], pl0[4], pl1[4];
+#pragma unroll
+  for (int c = 0; c < 8; c += 2) {
+    const float b0 = __ldg(bias + c), b1 = __ldg(bias + c + 1);
+    float u0 = acc0[c] + b0, u1 = acc0[c + 1] + b1, v0 = acc1[c] + b0, v1 = acc1[c + 1] + b1;
+    if (alpha != nullptr) {
+      const float al0 = __ldg(alpha + c), al1 = __ldg(alpha + c + 1);
+      u0 = fmaxf(u0, 0.f) + al0 * fminf(u0, 0.f);
+      u1 = fmaxf(u1, 0.f) + al1 * fminf(u1, 0.f);
+      v0 = fmaxf(v0, 0.f) + al0 * fminf(v0, 0.f);
+      v1 = fmaxf(v1, 0.f) + al1 * fminf(v1, 0.f);
+    }
+    pack16x2(u0, u1, fmt, &pk0[c / 2], &pl0[c / 2]);
+    pack16x2(v0, v1, fmt, &pk1[c / 2], &pl1[c / 2]);
+  }
+  const size_t o0 = (((static_cast<size_t>(b) * No + (ty * RC_T + oy)) * No + (tx * RC_T + ox)) * No + (tz * RC_T + oz)) * 8;
+  const size_t o1 = o0 + static_cast<size_t>(4) * No * No * 8;
+  *reinterpret_cast<uint4*>(out + o0) = make_uint4(pk0[0], pk0[1], pk0[2], pk0[3]);
+  *reinterpret_cast<uint4*>(out + o1) = make_uint4(pk1[0], pk1[1], pk1[2], pk1[3]);
+  if (fmt == 2) {
+    const size_t plane = static_cast<size_t>(B) * No * No * No * 8;
+    *reinterpret_cast<uint4*>(out + plane + o0) = make_uint4(pl0[0], pl0[1], pl0[2], pl0[3]);
+    *reinterpret_cast<uint4*>(out + plane + o1) = make_uint4(pl1[0], pl1[1], pl1[2], pl1[3]);
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------ texture decoder (config 4)
 // fully_connected (tools/layer_util.py:311-343): y[b][n] = act(sum_k x[b][k] w[k][n] + bias[n]); w is TF [in,out].
 // One thread per output column, weights streamed once (coalesced across n), x staged in shared memory.
@@ -1303,6 +1470,31 @@ extern "C" int rn_resample_conv1_fused(const float* vox, const float* minv, cons
   if (blocks > 0x7fffffffLL) return -3;
   resample_conv1_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       vox, minv, w, bias, alpha, static_cast<uint16_t*>(out16), B, size, new_size, fmt);
+  RN_COUNT_LAUNCH();
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rn_resample5_conv1_fused(const float* vox, const float* tex, const float* minv, const float* w,
+                                        const float* bias, const float* alpha, void* out16, int B, int size, int new_size,
+                                        int fmt, void* stream) {
+  if (!vox || !tex || !minv || !w || !bias || !out16 || B < 1 || size < 2 || fmt < 0 || fmt > 2) return -1;
+  if (new_size < 16 || new_size % 16 != 0) return -2;
+  if ((reinterpret_cast<uintptr_t>(tex) & 15) != 0) return -4;      // float4 gathers of the 4-channel texture volume
+  const int tpe = new_size / 2 / RC_T;
+  const long long blocks = static_cast<long long>(B) * tpe * tpe * tpe;
+  if (blocks > 0x7fffffffLL) return -3;
+  const size_t smem = (static_cast<size_t>(RC5_C) * RC5_TILE + 125 * RC5_C * 8) * sizeof(float);
+  static std::atomic<bool> attr_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return static_cast<int>(cudaErrorInvalidDevice);
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(resample5_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set[dev].store(true, std::memory_order_release);
+  }
+  resample5_conv1_kernel<<<static_cast<int>(blocks), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      vox, tex, minv, w, bias, alpha, static_cast<uint16_t*>(out16), B, size, new_size, fmt);
   RN_COUNT_LAUNCH();
   return static_cast<int>(cudaGetLastError());
 }

@@ -22,7 +22,8 @@ import torch
 from . import ops
 from . import tfcompat as tf
 from .RenderNet_Shader import RenderNet
-from .resampling_voxel_grid import ResampledGrid, inverse_sampling_matrix, tf_rotation_around_grid_centroid
+from .resampling_voxel_grid import (ConcatResampledGrid, ResampledGrid, inverse_sampling_matrix,
+                                     tf_rotation_around_grid_centroid)
 
 
 def pose_to_matrix(view_params, size=64, new_size=128) -> np.ndarray:
@@ -274,9 +275,11 @@ class TextureRenderEngine(_EngineBase):
     RenderNet_Texture_Face_Normal.py:155-179)."""
 
     def __init__(self, weights: Optional[Dict[str, np.ndarray]], batch: int, size: int = 64, new_size: int = 128,
-                 use_graph: bool = True, seed: int = 0, device: str = "cuda", precision: str = "fast", strict: bool = True):
+                 use_graph: bool = True, seed: int = 0, device: str = "cuda", precision: str = "fast", strict: bool = True,
+                 fuse_input: bool = True):
         super().__init__(weights, precision, seed, device, use_graph, strict)
         self.B, self.size, self.new_size = batch, size, new_size
+        self.fuse_input = fuse_input      # False: two stand-alone resamplings + concat + CUDA-core e_conv1 (the r01 path; A/B, tests)
         dev = self.device
         self.vox = torch.zeros((batch, size, size, size, 1), device=dev, dtype=torch.float32)
         self.tex = torch.zeros((batch, 199), device=dev, dtype=torch.float32)
@@ -289,10 +292,14 @@ class TextureRenderEngine(_EngineBase):
 
     def _forward(self):
         from .RenderNet_Texture_Face_Normal import RenderNet as RenderNetTexture, decoder_texture
-        grid = ops.resample(self.vox, self.minv, self.new_size, True)
+        # both resamplings stay deferred: resample x2 + axis transform + concat + e_conv1 run as one kernel
         tex3d = tf.realize(decoder_texture(self.tex))
-        tex_rot = ops.resample(tex3d, self.minv, self.new_size, True)
-        x5 = ops.concat_channels(grid, tex_rot)
+        if not self.fuse_input:
+            x5 = ops.concat_channels(ops.resample(self.vox, self.minv, self.new_size, True),
+                                     ops.resample(tex3d, self.minv, self.new_size, True))
+        else:
+            x5 = ConcatResampledGrid(ResampledGrid(self.vox, self.minv, self.new_size, transform=True),
+                                     ResampledGrid(tex3d, self.minv, self.new_size, transform=True))
         self.out = RenderNetTexture(x5, is_training=False)
         return list(self.out)
 

@@ -16,7 +16,7 @@ import torch
 
 from . import ops
 from . import tfcompat as tf
-from .resampling_voxel_grid import ResampledGrid
+from .resampling_voxel_grid import ConcatResampledGrid, ResampledGrid
 from .tfcompat import Deferred, realize
 
 USE_MERGED_TCONV = True    # one launch (N = 4*Cout, 9 taps) instead of 4 phase launches for k=4 stride-2 transposed convs
@@ -479,6 +479,14 @@ def _deferred_direct3d(x, w, b, stride):
             y = ops.resample_conv1(xin.voxel, xin.minv, xin.new_size, wd, bd, ad, tf.COMPUTE_DTYPE, fmt=_store().fmt)
             _record(op="resample_conv1", grid=xin, w=w, b=b, act=act, alpha=alpha, stride=list(stride), y=y)
             return y
+        if (USE_FUSED_RESAMPLE_CONV1 and isinstance(xin, ConcatResampledGrid) and xin.transform and xin._value is None
+                and key == (5, 8, 5) and list(stride) == [2, 2, 2] and xin.new_size % 16 == 0
+                and act in (None, "prelu") and residual is None and not want32):
+            # Texture net: resample (C=1) + resample (C=4) + concat + e_conv1 + bias + PReLU in one kernel
+            bd = _dev_vec(b) if b is not None else torch.zeros(cout, device=wd.device, dtype=torch.float32)
+            ad = _alpha_arg(alpha, cout) if act == "prelu" else None
+            return ops.resample5_conv1(xin.geom.voxel, xin.tex.voxel, xin.minv, xin.new_size, wd, bd, ad, tf.COMPUTE_DTYPE,
+                                       fmt=_store().fmt)
         xt = realize(xin)
         if not xt.is_cuda:
             xt = xt.to(_store().device)

@@ -530,6 +530,26 @@ def resample_conv1(vox: torch.Tensor, minv: torch.Tensor, new_size: int, w_tf: t
     return _wrap16(out, fmt)
 
 
+def resample5_conv1(vox: torch.Tensor, tex: torch.Tensor, minv: torch.Tensor, new_size: int, w_tf: torch.Tensor,
+                    bias: torch.Tensor, alpha: Optional[torch.Tensor], dtype: torch.dtype = torch.float16,
+                    fmt: Optional[int] = None):
+    """Texture net input chain in one kernel (rn_resample5_conv1_fused): resample geometry (C = 1) and texture volume (C = 4)
+    with one pose + axis transform + concat + e_conv1 (5^3 s2, 5 -> 8) + bias + PReLU.
+    vox fp32 [B,S,S,S,1], tex fp32 [B,S,S,S,4], minv fp32 [B,3,4], w_tf fp32 [5,5,5,5,8] -> 16-bit [B,new/2,new/2,new/2,8]."""
+    vox, tex, minv = _cuda(vox, torch.float32), _cuda(tex, torch.float32), _cuda(minv, torch.float32)
+    w_tf, bias = _cuda(w_tf, torch.float32), _cuda(bias, torch.float32)
+    B, S = vox.shape[0], vox.shape[1]
+    if (tuple(vox.shape) != (B, S, S, S, 1) or tuple(tex.shape) != (B, S, S, S, 4) or tuple(w_tf.shape) != (5, 5, 5, 5, 8)
+            or tuple(minv.shape) != (B, 3, 4)):
+        raise ValueError(f"resample5_conv1: unsupported shapes {tuple(vox.shape)}, {tuple(tex.shape)}, {tuple(w_tf.shape)}")
+    No = new_size // 2
+    fmt = fmt_of(dtype) if fmt is None else int(fmt)
+    out = _alloc16((B, No, No, No, 8), fmt, dtype, vox.device)
+    check(lib.rn_resample5_conv1_fused(vox.data_ptr(), tex.data_ptr(), minv.data_ptr(), w_tf.data_ptr(), bias.data_ptr(),
+                                       _ptr(alpha), out.data_ptr(), B, S, new_size, fmt, _stream()), "rn_resample5_conv1_fused")
+    return _wrap16(out, fmt)
+
+
 def binvox_decode(pairs_list, dims, fix_coords: bool = True, device="cuda") -> torch.Tensor:
     """Run-length (value, count) byte pairs of n binvox payloads -> float32 [n, d0, d2, d1, 1] on the device."""
     import numpy as np

@@ -95,6 +95,42 @@ class ResampledGrid:
         return list(self.shape)
 
 
+class ConcatResampledGrid:
+    """tf.concat([rotated geometry (C = 1), rotated texture volume (C = 4)], axis=4) of two deferred, axis-transformed
+    resamplings that share pose and size (RenderNet_Texture_Face_Normal.py:155-179), still deferred: when the consumer is the
+    Texture net's e_conv1 the whole chain runs as ONE kernel (rn_resample5_conv1_fused) and the 128^3 x 5 grid is never written."""
+
+    def __init__(self, geom: ResampledGrid, tex: ResampledGrid):
+        if (geom.new_size != tex.new_size or geom.transform != tex.transform or geom.minv.data_ptr() != tex.minv.data_ptr()
+                and not torch.equal(geom.minv, tex.minv)):
+            raise ValueError("ConcatResampledGrid: the two grids must share pose, size and axis transform")
+        if geom.voxel.shape[-1] != 1 or tex.voxel.shape[-1] != 4:
+            raise ValueError("ConcatResampledGrid: expects a 1-channel geometry grid and a 4-channel texture volume")
+        self.geom, self.tex = geom, tex
+        self.minv, self.new_size, self.transform = geom.minv, geom.new_size, geom.transform
+        self.shape = tuple(geom.shape[:-1]) + (5,)
+        self.dtype = torch.float32
+        self._value = None
+
+    def realize(self) -> torch.Tensor:
+        if self._value is None:
+            self._value = ops.concat_channels(self.geom.realize(), self.tex.realize())
+        return self._value
+
+    def get_shape(self):
+        return list(self.shape)
+
+
+def concat_resampled(a, b):
+    """tf.concat([a, b], 4): stays deferred for (geometry, texture) pairs of resampled grids, plain concat otherwise."""
+    if isinstance(a, ResampledGrid) and isinstance(b, ResampledGrid) and a._value is None and b._value is None:
+        try:
+            return ConcatResampledGrid(a, b)
+        except ValueError:
+            pass
+    return ops.concat_channels(a.realize() if hasattr(a, "realize") else a, b.realize() if hasattr(b, "realize") else b)
+
+
 def _to_cuda_f32(x) -> torch.Tensor:
     if hasattr(x, "realize"):          # deferred conv output (texture decoder)
         x = x.realize()
