@@ -273,6 +273,17 @@ int rn_conv3d_backward_data_direct(const void* g16, const float* w, void* dx16, 
 int rn_resample_backward_f32(const float* vox, const float* minv, const float* gout, float* dvox, float* dminv, int B, int C,
                              int size, int new_size, int transform, void* stream);
 
+/* ---- backward pass, stage 2: weight gradients (training step, RenderNet_Shader.py:159-167) -------------------------------
+ * dW of a stride-1 SAME conv2d (slim.conv2d / layer_util.conv2d, tools/layer_util.py:147-184) on the tensor cores:
+ *   dw[ky][kx][ci][co] = sum_{b,y,x} x[b, y+ky-pb, x+kx-pb, ci] * g[b, y, x, co]        (TF filter layout, fp32)
+ * x 16-bit [B,H,W,Cin] (the layer's input), g 16-bit [B,H,W,Cout] (dL/d conv output); both are read as MN-major tcgen05
+ * operands directly from their channel-last layout (K = pixels).  Cin % 128 == 0, Cout % 128 == 0, kh*kw <= 16,
+ * fmt RN_FMT_F16 or RN_FMT_F16X2.  dw is overwritten. */
+int rn_conv2d_weight_grad(const void* x, const void* g, float* dw, int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                          int fmt, void* stream);
+/* db[c] = sum over the npix pixels of g[p][c] (bias gradient of any conv); g 16-bit [npix, C], db fp32 [C], overwritten. */
+int rn_bias_grad_16(const void* g, float* db, long long npix, int C, int fmt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,11 +57,7 @@ static cudaError_t launch_variant(int BN, int CL, int CG, int MS, int EG, int SP
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_fn() {
+PFN_encodeTiled get_encode_fn() {
   static PFN_encodeTiled fn = nullptr;
   if (fn == nullptr) {
     void* p = nullptr;
@@ -102,6 +98,7 @@ static Tuning parse_tuning() {
   get("res_prefetch", &t.res_prefetch, 0, 1);
   get("tma_store", &t.tma_store, 0, 1);
   get("yhalo", &t.yhalo, 0, 1);
+  get("tiled_tex_conv", &t.tiled_tex_conv, 0, 1);
   return t;
 }
 const Tuning& tuning() {
@@ -110,7 +107,7 @@ const Tuning& tuning() {
 }
 
 // SM count of the CURRENT device (cached per device ordinal); 148 when no device is visible (rn_conv_plan on a CPU host)
-static int num_sms() {
+int num_sms() {
   static std::atomic<int> cache[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {

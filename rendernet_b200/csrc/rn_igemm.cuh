@@ -114,7 +114,15 @@ struct Tuning {
   int res_prefetch = 1;   // fetch 16-bit residual rows one panel ahead in the epilogue
   int tma_store = 1;      // TMA-store epilogue where the output is a dense 16-bit NHWC tensor
   int yhalo = 1;          // y-halo sharing of the activation operand (3x3, banded 3^3, merged / x-folded transposed)
+  int tiled_tex_conv = 1; // shared-memory tiled kernel for the texture decoder's 4^3 8->4 conv (0: generic kernel; A/B, tests)
 };
 const Tuning& tuning();
+
+// cuTensorMapEncodeTiled resolved through the runtime (no libcuda link), and the SM count of the current device (rn_igemm.cu)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_fn();
+int num_sms();
 
 }  // namespace rn

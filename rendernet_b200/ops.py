@@ -761,3 +761,29 @@ def resample_backward(vox: torch.Tensor, minv: torch.Tensor, gout: torch.Tensor,
     check(lib.rn_resample_backward_f32(vox.data_ptr(), minv.data_ptr(), gout.data_ptr(), _ptr(dvox), _ptr(dminv), B, Cc, S, N,
                                        1 if transform else 0, _stream()), "rn_resample_backward_f32")
     return dvox, dminv
+
+
+def conv2d_weight_grad(x, g, kh: int, kw: int) -> torch.Tensor:
+    """dW of a stride-1 SAME conv2d on the tensor cores (rn_conv2d_weight_grad): x 16-bit [B,H,W,Cin] (layer input), g 16-bit
+    [B,H,W,Cout] (gradient of the conv output), same 16-bit format -> fp32 [kh,kw,Cin,Cout] (TF filter layout)."""
+    x, g = _cuda(x), _cuda(g)
+    fmt = 2 if isinstance(x, Split16) else fmt_of(x.dtype)
+    if isinstance(g, Split16) != (fmt == 2):
+        raise TypeError("conv2d_weight_grad: x and g must share the 16-bit format")
+    B, H, W, Cin = x.shape
+    Cout = g.shape[-1]
+    assert tuple(g.shape[:3]) == (B, H, W)
+    dw = torch.empty((kh, kw, Cin, Cout), device=x.device, dtype=torch.float32)
+    check(lib.rn_conv2d_weight_grad(x.data_ptr(), g.data_ptr(), dw.data_ptr(), B, H, W, Cin, Cout, kh, kw, fmt, _stream()),
+          "rn_conv2d_weight_grad")
+    return dw
+
+
+def bias_grad(g) -> torch.Tensor:
+    """db[c] = sum over pixels of a 16-bit channel-last gradient tensor (rn_bias_grad_16) -> fp32 [C]."""
+    g = _cuda(g)
+    fmt = 2 if isinstance(g, Split16) else fmt_of(g.dtype)
+    Cc = g.shape[-1]
+    db = torch.empty(Cc, device=g.device, dtype=torch.float32)
+    check(lib.rn_bias_grad_16(g.data_ptr(), db.data_ptr(), g.numel() // Cc, Cc, fmt, _stream()), "rn_bias_grad_16")
+    return db
