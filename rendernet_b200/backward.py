@@ -192,8 +192,11 @@ class ShaderInputGradients:
         return a
 
     # ------------------------------------------------------------------------------------------- backward
-    def backward(self, dimg, want_dvox: bool = True, want_dpose: bool = True):
-        """dimg: dL/dimg [B,512,512,3|1] (NumPy or tensor).  Returns (dL/dvoxels [B,S,S,S,1] or None, dL/dview_params [B,3] or None)."""
+    def backward(self, dimg, want_dvox: bool = True, want_dpose: bool = True, want_weight_grads: bool = False):
+        """dimg: dL/dimg [B,512,512,3|1] (NumPy or tensor).  Returns (dL/dvoxels [B,S,S,S,1] or None, dL/dview_params [B,3] or None).
+        want_weight_grads (stage 2, partial): also fills `self.weight_grads` {variable name: fp32 device tensor} with dL/dW and
+        dL/dbias of every stride-1 conv2d layer (projection unit, res2 / res3 trunks, e_conv5 / e_conv6: 97 % of the parameters)
+        through the tcgen05 weight-gradient kernel (rn_conv2d_weight_grad)."""
         if self.tape is None:
             raise RuntimeError("call forward() first")
         dev = self.store.device
@@ -203,6 +206,7 @@ class ShaderInputGradients:
             raise ValueError(f"dimg shape {tuple(dimg.shape)} != image shape {tuple(self.img.shape)}")
         grads = {_key(self.img): dimg.contiguous()}
         dgrid = None
+        self.weight_grads = {}
         with torch.cuda.device(self.device), tf.use_store(self.store):
             for rec in reversed(self.tape):
                 y = rec["y"]
@@ -228,6 +232,11 @@ class ShaderInputGradients:
                     k = _key(res)
                     grads[k] = ops.bias_act(g, None, None, None, residual=grads[k]) if k in grads else g
                 x, kind, stride = rec["x"], rec["kind"], rec["stride"]
+                if want_weight_grads and kind == "conv2d" and int(x.shape[-1]) % 128 == 0 and int(y.shape[-1]) % 128 == 0:
+                    k = int(rec["w"].shape[0])
+                    self.weight_grads[rec["w"]._rn_name] = ops.conv2d_weight_grad(x, g, k, k) * (1.0 / self.loss_scale)
+                    if rec["b"] is not None:
+                        self.weight_grads[rec["b"]._rn_name] = ops.bias_grad(g) * (1.0 / self.loss_scale)
                 acc = grads.pop(_key(x), None)                 # gradient already collected for x (fan-out): fused as `residual`
                 if kind == "conv3d" and stride == 2:           # e_conv2: thin, z-strided -> CUDA cores
                     w32 = rec["w"].to(dev).float().contiguous()

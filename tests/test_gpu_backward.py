@@ -172,17 +172,25 @@ def test_layer_data_gradients_match_autograd(precision):
 
 
 # ----------------------------------------------------------------------------------------- whole network
+WGRAD_PROBES = ("encoder/res2_skip/con1_3X3/weights", "encoder/res2_skip/con1_3X3/biases", "encoder/res3_2/conv2_3x3/weights",
+                "encoder/e_conv5/e_conv5/weights", "encoder/projection_unit/Conv/weights")
+
+
 def _oracle_gradients(vox, poses, W, G):
-    """autograd through the whole oracle graph: float64 resampler restatement -> fp32 rendernet_shader."""
+    """autograd through the whole oracle graph: float64 resampler restatement -> fp32 rendernet_shader; also the gradients of
+    a few full-size filters (WGRAD_PROBES)."""
     B = vox.shape[0]
     R, Sm = orc.rotation_around_grid_centroid(poses)
     minv = orc.inverse_total_matrix(R, Sm, 64, 128)
     vt = torch.tensor(vox.astype(np.float64), requires_grad=True)
     mt = torch.tensor(minv.astype(np.float64), requires_grad=True)
+    Wt = dict(W)
+    for n in WGRAD_PROBES:
+        Wt[n] = torch.tensor(W[n], requires_grad=True)
     grid = _torch_resample(vt, mt, 128, 64)
-    img = orc.rendernet_shader(grid.float(), W)
+    img = orc.rendernet_shader(grid.float(), Wt)
     (img * torch.from_numpy(G)).sum().backward()
-    return img.detach().numpy(), vt.grad.numpy(), mt.grad.numpy()
+    return img.detach().numpy(), vt.grad.numpy(), mt.grad.numpy(), {n: Wt[n].grad.numpy() for n in WGRAD_PROBES}
 
 
 @pytest.mark.parametrize("precision", ["exact", "fast"])
@@ -197,15 +205,22 @@ def test_full_size_input_gradients_match_oracle_autograd(golden_dir, precision):
     poses = orc.compute_pose_param(250.0, 60.0, 3.3).astype(np.float32)
     W = orc.init_shader_weights(seed=1, alpha_range=(0.05, 0.3), bias_jitter=0.02)
     G = np.random.default_rng(5).standard_normal((1, 512, 512, 3)).astype(np.float32)
-    img_ref, dvox_ref, dminv_ref = _oracle_gradients(vox, poses, W, G)
+    img_ref, dvox_ref, dminv_ref, dw_ref = _oracle_gradients(vox, poses, W, G)
     dpose_ref = pose_matrix_jacobian_vjp(poses, dminv_ref)
     ig = ShaderInputGradients(W, 1, precision=precision)
     img = ig.forward(vox, poses)
     assert float(np.abs(img.cpu().numpy() - img_ref).max()) < 1e-3
-    dvox, dpose = ig.backward(G)
+    dvox, dpose = ig.backward(G, want_weight_grads=True)
     e_v, e_r, e_p = _rel_err(dvox, dvox_ref), _rms_err(dvox, dvox_ref), _rel_err(dpose, dpose_ref)
     cos = float((dvox.ravel() * dvox_ref.ravel()).sum() / (np.linalg.norm(dvox) * np.linalg.norm(dvox_ref)))
     print(f"[{precision}] dL/dvox err max {e_v:.2e} rms {e_r:.2e} (cosine {cos:.6f}), dL/dpose {dpose} vs {dpose_ref} rel err {e_p:.2e}")
+    # full-size weight gradients (tcgen05 wgrad kernel, K = 4096 pixels) of a few layers vs autograd
+    for n in WGRAD_PROBES:
+        got, want = ig.weight_grads[n].cpu().numpy(), dw_ref[n]
+        c = float((got.ravel() * want.ravel()).sum() / (np.linalg.norm(got) * np.linalg.norm(want)))
+        print(f"[{precision}] dL/d({n}) {tuple(got.shape)}: rms err {_rms_err(got, want):.2e}, cosine {c:.6f}")
+        assert got.shape == want.shape and c > (0.9995 if precision == "exact" else 0.99)
+    assert len(ig.weight_grads) == 2 * 35          # filters and biases of projection, res2 x21, e_conv5, res3 x11, e_conv6
     # Why percent-level and not 1e-6 like the single layers: the two forward passes differ by ~1.6e-4 (exact) / 2e-3 (fast)
     # relative at the deep layers, so a fraction f ~ 0.8 x that of all units sits on opposite sides of the PReLU kink in the two
     # implementations; each such unit contributes a full-size, independent error to the gradient, i.e. a relative rms error of
