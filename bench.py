@@ -342,7 +342,21 @@ def run_ours(args, rank, world, local_rank):
                 eng.result(eng.submitted - 1)
         torch.cuda.synchronize()
         ms_total, per = timed(args.steps, False)
-        r = {"ms_step": ms_total / args.steps, "per_rank_ms": [p / args.steps for p in per],
+        phases = None
+        if args.phases and sh is not None:            # where does a step's time go: graph replay vs the gather on the compute stream
+            sh.timing = []
+            timed(args.steps, False)
+            comp, gath, period = sh.phase_times()
+            sh.timing = None
+            t = torch.tensor([comp, gath, period], device=dev)
+            if world > 1:
+                allp = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(allp, t)
+                phases = {"compute_ms_per_rank": [round(float(v[0]), 3) for v in allp], "gather_ms_per_rank": [round(float(v[1]), 3) for v in allp],
+                          "period_ms_per_rank": [round(float(v[2]), 3) for v in allp]}
+            else:
+                phases = {"compute_ms_per_rank": [comp], "gather_ms_per_rank": [gath], "period_ms_per_rank": [period]}
+        r = {"ms_step": ms_total / args.steps, "per_rank_ms": [p / args.steps for p in per], "phases": phases,
              "value": units_per_step_global * args.steps / (ms_total / 1e3),
              "launches": eng.launches_per_step * (nchunk if cfg == 5 else 1),
              "gather": sh.kind_note if sh is not None else ("NCCL all-gather of the frames" if world > 1 else "single GPU"),
@@ -434,6 +448,7 @@ def run_ours(args, rank, world, local_rank):
                        "cuda_graph": M["cuda_graph"],
                        "l2": "no explicit flush: every layer streams 200-1600 MB of activations (> 126 MB L2) per step"},
             "per_rank_ms": M["per_rank_ms"],
+            "phases": M["phases"],
             "clocks": clocks,
             "e2e": {"value": M["e2e_value"], "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "per_rank_ms": M["e2e_per_rank_ms"], "note": e2e_note},
@@ -471,6 +486,7 @@ def main():
                     help="N>1 output all-gather: ncclAllGather between steps on the compute stream (default), ncclAllGather overlapped "
                          "on a side stream, copy-engine P2P writes over CUDA IPC (rendernet_b200.parallel.PeerImageGather; falls back "
                          "to NCCL if IPC is unavailable), or none (ablation); see ShardedRenderEngine for the measurements")
+    ap.add_argument("--phases", action="store_true", help="N>1: also record per-step device timestamps (compute vs gather) per rank")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-precision", action="store_true")

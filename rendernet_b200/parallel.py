@@ -171,6 +171,7 @@ class ShardedRenderEngine:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.kind = gather if self.world > 1 else "none"
         self.dev = engine.device
+        self.timing = None                           # set to [] to record per-step phase timestamps (bench.py --phases)
         outs = list(engine.outputs) if not isinstance(engine.out, torch.Tensor) else [engine.out]   # Texture engine: 2 images
         self._multi = not isinstance(engine.out, torch.Tensor)
         self.peer = None
@@ -244,8 +245,29 @@ class ShardedRenderEngine:
                 self.ev_done.record(self.comm)
 
     def step(self):
+        if self.timing is not None:                  # per-step device timestamps: [start, compute done, gather issued/done]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            cur = torch.cuda.current_stream(self.dev)
+            ev[0].record(cur)
+            self.engine.step_device()
+            ev[1].record(cur)
+            self._gather()
+            ev[2].record(cur)
+            self.timing.append(ev)
+            return
         self.engine.step_device()
         self._gather()
+
+    def phase_times(self):
+        """(mean compute ms, mean gather ms on the compute stream, mean step-to-step ms) of the steps recorded since `timing = []`;
+        call after a synchronize."""
+        t = self.timing or []
+        if not t:
+            return None
+        comp = sum(e[0].elapsed_time(e[1]) for e in t) / len(t)
+        gath = sum(e[1].elapsed_time(e[2]) for e in t) / len(t)
+        period = (t[0][0].elapsed_time(t[-1][0]) / (len(t) - 1)) if len(t) > 1 else comp + gath
+        return comp, gath, period
 
     def submit(self, *host_inputs) -> int:
         t = self.engine.submit(*host_inputs)
