@@ -171,11 +171,11 @@ class ShardedRenderEngine:
     def __init__(self, engine, gather: str = "nccl_sync", group=None):
         """gather: "nccl_sync" (default) = ncclAllGather on the COMPUTE stream right after the step, straight from the engine's
         output buffer; "nccl" = the same collective on a side stream, overlapped with the next step; "peer" = copy-engine P2P
-        writes (PeerImageGather); "none".  Measured on 8 x B200 (profiles/r02_scale8_*.json, fast precision, 24 renders per GPU
-        and step): no gather 37.5 ms/step, overlapped NCCL 40.6, peer 44.9.  The overlapped collective is NOT free: the
-        persistent convolution kernels occupy every SM (1 CTA/SM, ~210 KB of shared memory each), so NCCL's CTAs only get SMs at
-        kernel boundaries and the next convolution then starts short of SMs -- 3.2 ms per step for a transfer that needs < 1 ms
-        of NVLink time.  Running it between two steps costs just that transfer time."""
+        writes (PeerImageGather); "none".  Measured on 8 x B200 (profiles/r02_scale8*_*.json): all three cost
+        2.5-3.5 ms per step -- the bare 604 MB transfer is 0.94 ms, the rest is every rank waiting, each step, for the slowest of
+        eight power-capped GPUs; overlapping does not hide it because the persistent convolution kernels occupy every SM (NCCL's
+        CTAs only get SMs at kernel boundaries and slow every rank's compute by the same amount).  The stream-ordered form needs
+        no staging copy and no second gathered buffer in flight."""
         if gather not in ("nccl", "nccl_sync", "peer", "none"):
             raise ValueError("gather must be nccl_sync | nccl | peer | none")
         self.engine, self.group = engine, group
