@@ -217,3 +217,61 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["vs_baseline"] is None
+
+
+def test_pose_matrix_vjp_matches_finite_differences_host():
+    """backward.pose_matrix_jacobian_vjp: the 3 -> 12 chain rule from dL/dMinv to dL/d(azimuth, elevation, scale) (host, float64)
+    against central differences of the float32 matrix construction the forward pass uses (engine.pose_to_matrix)."""
+    from rendernet_b200.backward import pose_matrix_jacobian_vjp
+    from rendernet_b200.engine import pose_to_matrix
+    rng = np.random.default_rng(1)
+    vp = np.stack([rng.uniform(0, 6.28, 4), rng.uniform(-1.0, 1.0, 4), rng.uniform(0.8, 1.3, 4)], 1)
+    dm = rng.standard_normal((4, 3, 4))
+    got = pose_matrix_jacobian_vjp(vp, dm)
+    assert got.shape == (4, 3)
+    eps = 1e-3
+    for j in range(3):
+        d = np.zeros_like(vp)
+        d[:, j] = eps
+        fd = ((pose_to_matrix(vp + d).astype(np.float64) - pose_to_matrix(vp - d).astype(np.float64)) / (2 * eps) * dm).sum((1, 2))
+        assert np.allclose(got[:, j], fd, rtol=2e-2, atol=2e-2 * np.abs(fd).max()), (j, got[:, j], fd)
+
+
+def test_banded_filter_sizes_and_abi_rejections():
+    """Host-only checks of the C ABI: the banded filter holds two arrangements (single CTA / CTA pair) of 9 x kblocks tiles;
+    geometry the depth-folded form cannot take is rejected before any launch; exact-mode descriptors need their plane offsets."""
+    from rendernet_b200._lib import lib
+    assert lib.rn_conv3d_banded_bytes(32, 32, 1) == 2 * 9 * 3 * 128 * 64 * 2        # res1: 3 K blocks
+    assert lib.rn_conv3d_banded_bytes(16, 32, 1) == 2 * 9 * 2 * 128 * 64 * 2        # e_conv3: 2 K blocks
+    assert lib.rn_conv3d_banded_bytes(8, 16, 2) == 2 * 9 * 3 * 128 * 64 * 2         # e_conv2 (z stride 2)
+    assert lib.rn_conv3d_banded_bytes(16, 16, 1) == 2 * 9 * 3 * 128 * 64 * 2        # Texture net res1
+    assert lib.rn_conv3d_banded_bytes(48, 32, 1) == -1 and lib.rn_conv3d_banded_bytes(32, 32, 3) == -1
+    assert lib.rn_xfold_factor(16, 512) == 4 and lib.rn_xfold_factor(32, 512) == 2 and lib.rn_xfold_factor(64, 512) == 1
+    assert lib.rn_version() >= 100 and lib.rn_launch_count() >= 0
+
+
+def test_variable_store_strict_and_per_engine_isolation():
+    """loading a weight dict makes the store strict (a missing variable raises instead of silently falling back to a
+    random initialiser; unused loaded keys are reported) and stores are independent objects (tf.use_store)."""
+    from rendernet_b200 import tfcompat as tf
+    a, b = tf.VariableStore(precision="exact"), tf.VariableStore(precision="fast")
+    assert a.fmt == 2 and b.fmt == 0
+    with tf.use_store(a):
+        tf.load_weight_dict({"encoder/e_conv1/alpha": np.full(8, 0.25, np.float32), "encoder/never/used": np.zeros(1, np.float32)})
+        with tf.variable_scope("encoder"):
+            with tf.variable_scope("e_conv1"):
+                v = tf.get_variable("alpha", [8], initializer=tf.constant_initializer(0.0))
+                with pytest.raises(KeyError, match="e_conv1/biases"):
+                    tf.get_variable("biases", [8], initializer=tf.constant_initializer(0.001))
+                w = tf.get_variable("from_array", initializer=np.ones(3, np.float32))       # explicit arrays are always allowed
+        assert torch.all(v == 0.25) and torch.all(w == 1.0) and a.unused() == ["encoder/never/used"]
+        with tf.use_store(b):
+            assert tf.get_store() is b and tf.compute_fmt() == 0
+            with tf.variable_scope("encoder"):
+                with tf.variable_scope("e_conv1"):
+                    v2 = tf.get_variable("alpha", [8], initializer=tf.constant_initializer(0.0))    # b is not strict: initialiser
+            assert torch.all(v2 == 0.0)
+        assert tf.get_store() is a
+    assert tf.get_store() is not a and "encoder/e_conv1/alpha" not in b.loaded
+    with pytest.raises(ValueError):
+        tf.VariableStore(precision="bf16")
