@@ -82,6 +82,17 @@ int rn_bias_act_16(const void* x, const float* bias, const float* alpha, int act
  * with zero outside the input (TF SAME padding is expressed through the tap offsets).
  * The output element offset is o_base + b*o_b + y*o_y + x*o_x + z*o_z + n, which lets one call write a
  * strided sub-lattice (the 4 phases of a stride-2 transposed convolution). */
+/* Phong composite + uint8 quantisation (tools/Phong_shading.py:202-228, RenderNet_demo.py:58) fused into the sigmoid epilogue of
+ * the Shader net's last up-conv (rn_conv2d_transpose_s1_xfold with Cout = 3): out32 then receives the SHADED colour instead of
+ * the normal map, out_u8 (may be NULL) its clip(255 x) uint8 form; bit-identical to rn_phong_composite applied afterwards. */
+typedef struct rn_phong {
+  const float* light_dir;   /* [B,3] */
+  const float* light_col;   /* [B,3] */
+  uint8_t* out_u8;          /* [B,H,W,3] or NULL */
+  float ambient, k_diffuse;
+  int background_white, with_mask;
+} rn_phong;
+
 typedef struct rn_conv_desc {
   int ndim;                 /* 2 or 3 spatial dims */
   int B, H, W, D;           /* extents (D ignored for ndim == 2) */
@@ -127,6 +138,7 @@ typedef struct rn_conv_desc {
   /* per-call overrides of the launch heuristics, 0 = library default: epilogue warp groups (1 or 2); residual register
    * prefetch / TMA-store epilogue (1 = on, -1 = off) */
   int epi_groups, res_prefetch, tma_store;
+  const rn_phong* phong;    /* NULL, or the fused Phong epilogue (act = RN_ACT_SIGMOID, N = F pixels x 3 channels <= 16) */
 } rn_conv_desc;
 int rn_conv_igemm(const rn_conv_desc* d, void* stream);
 /* Per-call overrides of the launch heuristics for the reference-shaped wrappers below (their last argument before
@@ -195,7 +207,7 @@ int rn_pack_conv2d_transpose_xfold(const float* w, void* packed, int kh, int kw,
                                    int fmt, void* stream);
 int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, const float* bias_x, const float* alpha_x, int act,
                                  void* out16, float* out32, int B, int H, int W, int Cin, int Cout, int kh, int kw, int F,
-                                 int cout_pad, int fmt, const rn_tuning* tune, void* stream);
+                                 int cout_pad, int fmt, const rn_phong* phong, const rn_tuning* tune, void* stream);
 
 /* ---- thin 3-D convolutions on CUDA cores (too few channels for the tensor pipe) ---------------------
  * tf.nn.conv3d SAME + bias + PReLU (layer_util.py:228-265, RenderNet_Shader.py:36-43): e_conv1 (Cin=1,

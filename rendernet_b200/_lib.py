@@ -29,7 +29,13 @@ class rn_conv_desc(C.Structure):
         ("o_nsplit", C.c_int), ("o_nhi", C.c_longlong),
         ("x_plane", C.c_longlong), ("w_plane", C.c_longlong), ("o_plane", C.c_longlong),
         ("epi_groups", C.c_int), ("res_prefetch", C.c_int), ("tma_store", C.c_int),
+        ("phong", C.c_void_p),
     ]
+
+
+class rn_phong(C.Structure):
+    _fields_ = [("light_dir", C.c_void_p), ("light_col", C.c_void_p), ("out_u8", C.c_void_p), ("ambient", C.c_float),
+                ("k_diffuse", C.c_float), ("background_white", C.c_int), ("with_mask", C.c_int)]
 
 
 class rn_tuning(C.Structure):
@@ -66,7 +72,7 @@ SIGNATURES = {
     "rn_conv2d_transpose_s2_merged": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _tp, _vp]),
     "rn_xfold_factor": (_i, [_i, _i]),
     "rn_pack_conv2d_transpose_xfold": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "rn_conv2d_transpose_s1_xfold": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _tp, _vp]),
+    "rn_conv2d_transpose_s1_xfold": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(rn_phong), _tp, _vp]),
     "rn_conv3d_direct": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rn_resample_conv1_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rn_resample5_conv1_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

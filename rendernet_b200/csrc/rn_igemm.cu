@@ -457,6 +457,14 @@ extern "C" int rn_conv_igemm(const rn_conv_desc* d, void* stream_v) {
   p.o_nsplit = d->o_nsplit; p.o_nhi = d->o_nhi;
   p.res_prefetch = res_pre ? 1 : 0;
   p.o_plane = d->o_plane;
+  if (d->phong != nullptr) {      // fused Phong composite (16-column kernels, sigmoid epilogue, direct fp32 / uint8 stores)
+    if (BN != 16 || d->act != ACT_SIGMOID || d->Cout % 3 != 0 || d->Cout > 15 || d->o_nsplit != 0 || d->residual != nullptr ||
+        d->phong->light_dir == nullptr || d->phong->light_col == nullptr || (d->out32 == nullptr && d->phong->out_u8 == nullptr))
+      return -21;
+    p.phong_light_dir = d->phong->light_dir; p.phong_light_col = d->phong->light_col; p.out_u8 = d->phong->out_u8;
+    p.phong_ambient = d->phong->ambient; p.phong_kd = d->phong->k_diffuse; p.phong_F = d->Cout / 3;
+    p.phong_white = d->phong->background_white; p.phong_mask = d->phong->with_mask;
+  }
   if (d->o_nsplit > 0 && (d->o_nsplit % 32 != 0 || d->o_nhi % 8 != 0)) return -15;
   const bool strides8 = (d->o_base % 8 == 0) && (d->o_b % 8 == 0) && (d->o_y % 8 == 0) && (d->o_x % 8 == 0) &&
                         (d->o_z % 8 == 0);

@@ -65,6 +65,13 @@ struct alignas(64) IgemmParams {
   int vec_ok;                     // output/residual rows are 16B aligned -> vector path
   long long o_base, o_b, o_y, o_x, o_z;  // output element offset = o_base + b*o_b + y*o_y + x*o_x + z*o_z + n
   int tma_store;                  // 1: epilogue stages 64-column panels in swizzled smem and stores them with TMA
+  // Phong composite + uint8 fused into the sigmoid epilogue of the x-folded last up-conv (16-column kernels only):
+  // a GEMM row holds the 3 channels of phong_F adjacent pixels; out32 then receives the SHADED colour and out_u8 its uint8 form.
+  const float* phong_light_dir;   // [B,3] or nullptr (off)
+  const float* phong_light_col;   // [B,3]
+  uint8_t* out_u8;                // [B,H,W,3] uint8, same element indexing as out32
+  float phong_ambient, phong_kd;
+  int phong_F, phong_white, phong_mask;
   int o_nsplit;                   // > 0: column n lands at (n / o_nsplit) * o_nhi + (n % o_nsplit) instead of n (merged
   long long o_nhi;                //      phases of a stride-2 transposed conv: n = (ay, ax, co))
 };

@@ -28,6 +28,7 @@
 #include <cuda_bf16.h>
 
 #include "rn_igemm.cuh"
+#include "rn_phong.cuh"
 #include "rn_ptx.cuh"
 
 namespace rn {
@@ -64,7 +65,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile,
 template <int CW, bool SPLIT = false>
 __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint32_t* __restrict__ r, int n0,
                                                long long off, bool row_valid, uint32_t stg = 0, int m = 0,
-                                               int chunk0 = 0, int prow = 128, const uint4* rpre = nullptr) {
+                                               int chunk0 = 0, int prow = 128, const uint4* rpre = nullptr, int bidx = 0) {
   if (!row_valid && stg == 0) return;
   float v[CW];
 #pragma unroll
@@ -87,6 +88,31 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
   } else if (p.act == ACT_SIGMOID) {
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] = 1.f / (1.f + __expf(-v[i]));
+  }
+  if constexpr (CW == 16) {
+    // Last up-conv of the Shader net (x-folded, N = F pixels x 3 channels <= 16): Phong composite + uint8 quantisation of the
+    // sigmoid output while it is still in registers (tools/Phong_shading.py:202-228, RenderNet_demo.py:58).
+    if (p.phong_light_dir != nullptr && p.act == ACT_SIGMOID && n0 == 0) {
+      if (row_valid) {
+        const float* ld = p.phong_light_dir + 3 * bidx;
+        const float lx = __ldg(ld), ly = __ldg(ld + 1), lz = __ldg(ld + 2);
+        float col[3] = {__ldg(p.phong_light_col + 3 * bidx), __ldg(p.phong_light_col + 3 * bidx + 1), __ldg(p.phong_light_col + 3 * bidx + 2)};
+#pragma unroll
+        for (int px = 0; px < 5; ++px) {
+          if (px < p.phong_F) {
+            float sh[3];
+            phong_pixel(v[3 * px], v[3 * px + 1], v[3 * px + 2], lx, ly, lz, col, p.phong_ambient, p.phong_kd, p.phong_white,
+                        p.phong_mask, sh);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              if (p.out32 != nullptr) p.out32[off + 3 * px + c] = sh[c];
+              if (p.out_u8 != nullptr) p.out_u8[off + 3 * px + c] = phong_u8(sh[c]);
+            }
+          }
+        }
+      }
+      return;
+    }
   }
   const bool full = p.vec_ok && (n0 + CW <= p.n_valid);
   if (full) {
@@ -484,7 +510,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
               for (int c = 0; c < PC; c += CW) {
                 const int nc = t.n0 + pc + c;
                 const long long offc = p.o_nsplit > 0 ? off + (nc / p.o_nsplit) * p.o_nhi + (nc % p.o_nsplit) - nc : off;
-                epilogue_chunk<CW, SPLIT>(p, r + c, nc, offc, row_valid, 0, 0, 0, 128, res_pre ? res + c / 8 : nullptr);
+                epilogue_chunk<CW, SPLIT>(p, r + c, nc, offc, row_valid, 0, 0, 0, 128, res_pre ? res + c / 8 : nullptr, t.b);
               }
               if constexpr (res_pre) { if (q + 1 < q_hi) prefetch_res(q + 1); }
             } else {
@@ -592,7 +618,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
               for (int c = 0; c < PC; c += CW) {
                 const int nc = t.n0 + sc + pc + c;
                 const long long offc = p.o_nsplit > 0 ? off + (nc / p.o_nsplit) * p.o_nhi + (nc % p.o_nsplit) - nc : off;
-                epilogue_chunk<CW, SPLIT>(p, r + pc + c, nc, offc, row_valid, 0, 0, 0, 128, res_pre ? res + c / 8 : nullptr);
+                epilogue_chunk<CW, SPLIT>(p, r + pc + c, nc, offc, row_valid, 0, 0, 0, 128, res_pre ? res + c / 8 : nullptr, t.b);
               }
               ++q;
               if constexpr (res_pre) { if (q < nq) prefetch_res(q); }

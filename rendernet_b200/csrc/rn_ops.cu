@@ -16,6 +16,7 @@
 
 #include <atomic>
 #include "rn_igemm.cuh"
+#include "rn_phong.cuh"
 namespace rn {
 extern std::atomic<long long> g_launch_count;
 #define RN_COUNT_LAUNCH() rn::g_launch_count.fetch_add(1, std::memory_order_relaxed)
@@ -990,26 +991,13 @@ __global__ void phong_kernel(const float* __restrict__ img, const float* __restr
   if (i >= static_cast<long long>(B) * npix) return;
   const int b = static_cast<int>(i / npix);
   const float r = img[3 * i], g = img[3 * i + 1], bl = img[3 * i + 2];
-  // np_phong_shading (:162-200): n = (img-0.5)/|img-0.5| ; diffuse = k_d * max(n.l, 0) * light_col, clipped
-  const float nx = r - 0.5f, ny = g - 0.5f, nz = bl - 0.5f;
-  const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
-  float lx = light_dir[3 * b], ly = light_dir[3 * b + 1], lz = light_dir[3 * b + 2];
-  const float linv = 1.0f / sqrtf(lx * lx + ly * ly + lz * lz);
-  lx *= linv; ly *= linv; lz *= linv;
-  const float ndl = fmaxf((nx * lx + ny * ly + nz * lz) * inv, 0.f);
-  float mask = 1.f;
-  if (with_mask) {  // np_mask (:138-148) / np_mask_white (:150-160)
-    const float nrm = white ? sqrtf((1.f - r) * (1.f - r) + (1.f - g) * (1.f - g) + (1.f - bl) * (1.f - bl))
-                            : sqrtf(r * r + g * g + bl * bl);
-    mask = 1.f / (1.f + expf(-(255.f * nrm - (white ? 80.f : 150.f))));
-  }
+  float v[3];
+  phong_pixel(r, g, bl, light_dir[3 * b], light_dir[3 * b + 1], light_dir[3 * b + 2], light_col + 3 * b, ambient, k_diffuse, white,
+              with_mask, v);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float diff = fminf(fmaxf(k_diffuse * ndl * light_col[3 * b + c], 0.f), 1.f);
-    float v = with_mask ? mask * (ambient + diff) + (1.f - mask) : ambient + diff;
-    v = fminf(fmaxf(v, 0.f), 1.f);
-    if (out_f32 != nullptr) out_f32[3 * i + c] = v;
-    if (out_u8 != nullptr) out_u8[3 * i + c] = static_cast<uint8_t>(fminf(fmaxf(255.f * v, 0.f), 255.f));
+    if (out_f32 != nullptr) out_f32[3 * i + c] = v[c];
+    if (out_u8 != nullptr) out_u8[3 * i + c] = phong_u8(v[c]);
   }
 }
 
@@ -1450,8 +1438,8 @@ extern "C" int rn_pack_conv2d_transpose_xfold(const float* w, void* packed, int 
 // per-Cout vectors tiled F times and zero padded to cout_pad (rn_expand_channels + padding by the caller).
 extern "C" int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, const float* bias_x, const float* alpha_x,
                                             int act, void* out16, float* out32, int B, int H, int W, int Cin, int Cout,
-                                            int kh, int kw, int F, int cout_pad, int fmt, const rn_tuning* tune,
-                                            void* stream) {
+                                            int kh, int kw, int F, int cout_pad, int fmt, const rn_phong* phong,
+                                            const rn_tuning* tune, void* stream) {
   if (F < 2 || W % F != 0 || kh * 3 > kMaxTaps) return -20;
   int8_t taps[kMaxTaps * 3];
   const int pby = (kh - 1) / 2;                     // SAME stride-1 transposed: dy = pb - ky
@@ -1472,6 +1460,8 @@ extern "C" int rn_conv2d_transpose_s1_xfold(const void* x, const void* w_xfold, 
     d.w_plane = static_cast<long long>(kh) * 3 * cout_pad * F * Cin;
     d.o_plane = static_cast<long long>(B) * H * W * Cout;
   }
+  if (phong != nullptr && (Cout != 3 || act != RN_ACT_SIGMOID || cout_pad != 16)) return -22;
+  d.phong = phong;
   apply_tuning(d, tune);
   if (want_yhalo(tune) && (F * Cin) % 64 == 0) d.ny = kh;    // tap = kyr*3 + j, dy consecutive in kyr: the kh taps share one halo load
   return rn_conv_igemm(&d, stream);

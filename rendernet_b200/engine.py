@@ -197,10 +197,11 @@ class _EngineBase:
 class RenderEngine(_EngineBase):
     def __init__(self, weights: Optional[Dict[str, np.ndarray]], batch: int, is_greyscale: bool = False,
                  size: int = 64, new_size: int = 128, use_graph: bool = True, phong: Optional[dict] = None,
-                 seed: int = 0, device: str = "cuda", precision: str = "fast", strict: bool = True):
+                 seed: int = 0, device: str = "cuda", precision: str = "fast", strict: bool = True,
+                 fuse_phong: bool = True):
         """weights: {tf variable name: array} (None -> the reference's initialisers, seeded).
-        phong: None, or dict(light_dir[1|B,3], light_col, ambient, k_diffuse) to fuse the demo's
-        Phong composite + uint8 quantisation after the network.
+        phong: None, or dict(light_dir[1|B,3], light_col, ambient, k_diffuse) to apply the demo's
+        Phong composite + uint8 quantisation; fuse_phong: inside the output layer's epilogue (default) or as a separate pass.
         precision: "fast" | "exact" (module docstring)."""
         super().__init__(weights, precision, seed, device, use_graph, strict)
         self.B, self.size, self.new_size = batch, size, new_size
@@ -210,6 +211,7 @@ class RenderEngine(_EngineBase):
         self.minv = torch.zeros((batch, 3, 4), device=dev, dtype=torch.float32)
         self.inputs = [self.vox, self.minv]
         self.phong = phong
+        self.fuse_phong = fuse_phong
         if phong is not None:
             self.light_dir = torch.as_tensor(np.asarray(phong["light_dir"], np.float32)).reshape(-1, 3).to(dev)
             self.light_col = torch.as_tensor(np.asarray(phong["light_col"], np.float32)).reshape(-1, 3).to(dev)
@@ -223,10 +225,25 @@ class RenderEngine(_EngineBase):
     # -------------------------------------------------------------------------------------------
     def _forward(self):
         grid = ResampledGrid(self.vox, self.minv, self.new_size, transform=True)   # deferred: fuses into e_conv1
-        img = RenderNet(grid, is_training=False, is_greyscale=self.is_greyscale)
+        st = self.store
+        if self.phong is not None and self.fuse_phong and not self.is_greyscale:
+            # the composite runs in the sigmoid epilogue of the last up-conv: no separate pass, no normal-map round trip
+            st.phong = dict(light_dir=self.light_dir, light_col=self.light_col, ambient=self.phong["ambient"],
+                            k_diffuse=self.phong["k_diffuse"], background_white=self.phong.get("background_white", False),
+                            with_mask=self.phong.get("with_mask", True))
+        st.phong_u8 = None
+        try:
+            img = RenderNet(grid, is_training=False, is_greyscale=self.is_greyscale)
+        finally:
+            st.phong = None
         if self.phong is not None:
-            shaded, u8 = ops.phong_composite(img, self.light_dir, self.light_col, self.phong["ambient"],
-                                             self.phong["k_diffuse"], want_u8=True)
+            if st.phong_u8 is not None:
+                shaded, u8, st.phong_u8 = img, st.phong_u8, None
+            else:
+                shaded, u8 = ops.phong_composite(img, self.light_dir, self.light_col, self.phong["ambient"],
+                                                 self.phong["k_diffuse"],
+                                                 background_white=self.phong.get("background_white", False),
+                                                 with_mask=self.phong.get("with_mask", True), want_u8=True)
             self.out, self.out_u8 = shaded, u8
             return [shaded, u8]
         self.out = img

@@ -409,6 +409,11 @@ def _deferred_conv(kind, x, w, b, stride):
             al = None
             if act == "prelu":
                 al = _dev_vec(alpha) if not isinstance(alpha, str) else torch.zeros(int(w.shape[2]), device=xt.device)
+            ph = _store().phong
+            if ph is not None and act == "sigmoid" and want32 and Lx.cout == 3:
+                # "encoder/output" with the demo's Phong composite + uint8 quantisation applied in the same epilogue
+                shaded, _store().phong_u8 = ops.conv2d_transpose_xfold(xt, Lx, act=act, want16=False, want32=True, phong=ph)
+                return shaded
             return ops.conv2d_transpose_xfold(xt, Lx, act=act, alpha=al, alpha_tag=getattr(alpha, "_rn_name", None),
                                               want16=want16, want32=want32)
         if residual is not None:

@@ -10,7 +10,7 @@ from typing import Optional, Sequence
 
 import torch
 
-from ._lib import check, lib, rn_conv_desc, rn_tuning
+from ._lib import check, lib, rn_conv_desc, rn_phong, rn_tuning
 
 ACT_NONE, ACT_PRELU, ACT_SIGMOID = 0, 1, 2
 _ACT = {None: ACT_NONE, "none": ACT_NONE, "prelu": ACT_PRELU, "sigmoid": ACT_SIGMOID}
@@ -433,10 +433,30 @@ class XFoldConvT:
 
 
 def conv2d_transpose_xfold(x: torch.Tensor, L: XFoldConvT, act: Optional[str] = None, alpha: Optional[torch.Tensor] = None,
-                           alpha_tag=None, want16: bool = True, want32: bool = False, out16=None, out32=None, tune=None):
+                           alpha_tag=None, want16: bool = True, want32: bool = False, out16=None, out32=None, tune=None,
+                           phong: Optional[dict] = None):
+    """phong (only with act="sigmoid", Cout = 3, want32): dict(light_dir [B,3], light_col [B,3] fp32 device tensors, ambient,
+    k_diffuse, background_white=False, with_mask=True, want_u8=True) -> the Phong composite is applied in the epilogue; returns
+    (shaded fp32 image, uint8 image or None)."""
     x = _act_in(x, L.fmt, L.dtype)
     B, H, W, Cin = x.shape
     assert Cin == L.cin and W % L.F == 0
+    ph, u8 = None, None
+    if phong is not None:
+        if act != "sigmoid" or L.cout != 3 or not want32 or want16:
+            raise ValueError("the fused Phong epilogue needs the sigmoid 3-channel fp32 output layer")
+        ld, lc = _cuda(phong["light_dir"], torch.float32), _cuda(phong["light_col"], torch.float32)
+        if ld.shape[0] == 1 and B > 1:
+            ld = ld.expand(B, 3).contiguous()
+        if lc.shape[0] == 1 and B > 1:
+            lc = lc.expand(B, 3).contiguous()
+        assert tuple(ld.shape) == (B, 3) and tuple(lc.shape) == (B, 3)
+        if phong.get("want_u8", True):
+            u8 = torch.empty((B, H, W, 3), device=x.device, dtype=torch.uint8)
+        ph = rn_phong()
+        ph.light_dir, ph.light_col, ph.out_u8 = ld.data_ptr(), lc.data_ptr(), _ptr(u8)
+        ph.ambient, ph.k_diffuse = float(phong["ambient"]), float(phong["k_diffuse"])
+        ph.background_white, ph.with_mask = int(bool(phong.get("background_white", False))), int(bool(phong.get("with_mask", True)))
     out16, out32 = _out_buffers((B, H, W, L.cout), L.dtype, x.device, want16, want32, out16, out32, L.fmt)
     a = _ACT[act]
     alpha_x = None
@@ -448,7 +468,10 @@ def conv2d_transpose_xfold(x: torch.Tensor, L: XFoldConvT, act: Optional[str] = 
                 L._alpha[alpha_tag] = alpha_x
     check(lib.rn_conv2d_transpose_s1_xfold(x.data_ptr(), L.w.data_ptr(), L.bias.data_ptr(), _ptr(alpha_x), a, _ptr(out16),
                                            _ptr(out32), B, H, W, Cin, L.cout, L.kh, L.kw, L.F, L.cout_pad, L.fmt,
-                                           _tune(tune), _stream()), "rn_conv2d_transpose_s1_xfold")
+                                           C.byref(ph) if ph is not None else None, _tune(tune), _stream()),
+          "rn_conv2d_transpose_s1_xfold")
+    if ph is not None:
+        return out32, u8
     return _ret(out16, out32, want16, want32, L.fmt)
 
 

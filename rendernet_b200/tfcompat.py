@@ -51,6 +51,8 @@ class VariableStore:
         self.loaded: set = set()       # names installed by load_weight_dict
         self.consumed: set = set()     # loaded names a model function has asked for
         self.tape = None               # list -> every realised layer appends a record (rendernet_b200/backward.py)
+        self.phong = None              # dict (ops.conv2d_transpose_xfold) -> the output layer applies the Phong composite itself
+        self.phong_u8 = None           # ... and leaves the uint8 image here
 
     @property
     def fmt(self) -> int:

@@ -1,6 +1,8 @@
 #!/bin/bash
 # round-2 GPU check #7: backward incl. full-size weight gradients; wgrad kernel timing + ncu; final bench lines
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_model.py -q -s -k 'phong or demo or golden' > gpurun_out/r02_run7_phong.log 2>&1; echo "phong rc=$?"
+grep -E "passed|failed|^E  |Error" gpurun_out/r02_run7_phong.log | head -20
 timeout 1500 python -m pytest tests/test_gpu_backward.py -q -s > gpurun_out/r02_run7_backward.log 2>&1; echo "backward rc=$?"
 grep -E "passed|failed|dL/d|^E  |Error" gpurun_out/r02_run7_backward.log | head -40
 timeout 600 python scripts/wgrad_time.py 2>&1 | tee gpurun_out/r02_wgrad_time.log

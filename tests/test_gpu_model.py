@@ -303,3 +303,32 @@ def test_texture_engine_fused_input_matches_unfused():
         assert torch.equal(ia, ib) and torch.equal(na, nb)
         assert a.launches_per_step == b.launches_per_step - 3          # 2 resamplings + concat + conv -> 1 kernel
         del a, b
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_fused_phong_epilogue_is_bit_identical_to_the_separate_pass(precision):
+    """The Phong composite + uint8 quantisation applied inside the output layer's sigmoid epilogue (RenderEngine default) ==
+    the same network followed by rn_phong_composite, bit for bit (fp32 shaded image and uint8 image), B = 2, two lights,
+    and == the oracle's np_phong_composite (tools/Phong_shading.py:202-228) of that normal map."""
+    from rendernet_b200.engine import RenderEngine
+    rng = np.random.default_rng(5)
+    W = orc.init_shader_weights(seed=3, gain=1.0)
+    vox = np.zeros((2, 64, 64, 64, 1), np.float32)
+    vox[0, 16:48, 20:44, 12:52] = 1.0
+    vox[1, 24:40, 8:56, 24:40] = 1.0
+    poses = np.array([[40.0, 20.0, 3.3], [200.0, 35.0, 2.9]], np.float32)
+    phong = dict(light_dir=np.stack([orc.generate_light_pos(60.0, 250.0), orc.generate_light_pos(30.0, 90.0)]).astype(np.float32),
+                 light_col=np.array([[1.0, 1.0, 1.0], [0.9, 0.8, 0.7]], np.float32), ambient=0.3, k_diffuse=0.7)
+    outs = {}
+    for fuse in (True, False):
+        eng = RenderEngine(W, batch=2, precision=precision, phong=phong, fuse_phong=fuse, use_graph=fuse)
+        shaded, u8 = eng.render(vox, poses)
+        outs[fuse] = (shaded.clone().numpy(), u8.clone().numpy(), eng.launches_per_step)
+    assert outs[True][2] == outs[False][2] - 1, (outs[True][2], outs[False][2])     # one launch fewer
+    assert np.array_equal(outs[True][0], outs[False][0])
+    assert np.array_equal(outs[True][1], outs[False][1])
+    assert outs[True][1].std() > 5          # not a constant image
+    plain = RenderEngine(W, batch=2, precision=precision, use_graph=False).render(vox, poses).numpy()
+    for b in range(2):
+        ref = orc.np_phong_composite(plain[b:b + 1], phong["light_dir"][b], phong["light_col"][b], 0.3, 0.7)
+        assert np.abs(ref - outs[True][0][b:b + 1]).max() < 2e-6

@@ -37,7 +37,7 @@ def test_conv_desc_struct_matches_header_field_order():
         decl = decl.strip()
         if not decl:
             continue
-        decl = re.sub(r"^(const\s+)?(int8_t|void|float|int|long long)\s*\**\s*", "", decl)
+        decl = re.sub(r"^(const\s+)?(int8_t|void|float|int|long long|rn_phong)\s*\**\s*", "", decl)
         names += [n.strip().lstrip("*") for n in decl.split(",")]
     assert names == [f[0] for f in rn_conv_desc._fields_]
 
