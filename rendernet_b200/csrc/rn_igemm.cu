@@ -99,6 +99,7 @@ static Tuning parse_tuning() {
   get("tma_store", &t.tma_store, 0, 1);
   get("yhalo", &t.yhalo, 0, 1);
   get("tiled_tex_conv", &t.tiled_tex_conv, 0, 1);
+  get("pdl", &t.pdl, 0, 1);
   return t;
 }
 const Tuning& tuning() {

@@ -122,6 +122,8 @@ struct Tuning {
   int tma_store = 1;      // TMA-store epilogue where the output is a dense 16-bit NHWC tensor
   int yhalo = 1;          // y-halo sharing of the activation operand (3x3, banded 3^3, merged / x-folded transposed)
   int tiled_tex_conv = 1; // shared-memory tiled kernel for the texture decoder's 4^3 8->4 conv (0: generic kernel; A/B, tests)
+  int pdl = 0;            // programmatic dependent launch: igemm launches carry the programmatic-stream-serialization attribute,
+                          // trigger their dependents after the prologue and griddepcontrol.wait before touching global memory
 };
 const Tuning& tuning();
 

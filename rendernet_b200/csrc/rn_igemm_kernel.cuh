@@ -284,6 +284,12 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) igemm_kernel(const __grid_co
   if constexpr (CL > 1) cluster_sync();   // peers' barriers are initialised before any multicast / remote commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch (no-ops for a normally launched grid): everything above — barrier init, TMEM allocation,
+  // descriptor prefetch, the cluster handshake — touched only kernel parameters and this CTA's own resources, so it may run
+  // while the previous kernel of the stream drains.  Let OUR dependents be scheduled as our CTAs retire, then wait for the
+  // previous grid to complete (and its writes to be visible) before any thread reads or writes global memory.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int cta_rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   // tile walk: cluster c handles "cluster tiles" c, c+nclusters, ...; cluster tile ct -> tiles (mg*CL + rank, n)
   const int ncl = static_cast<int>(gridDim.x) / CL;
@@ -677,25 +683,29 @@ cudaError_t launch_ms(const IgemmParams& p, int grid, size_t smem, cudaStream_t 
     attr_set[dev].store(true, std::memory_order_release);
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  if constexpr (CL == 1) {
-    igemm_kernel<BN, 1, 1, MS, EG, SPLIT><<<grid, 64 + 128 * EG, smem, stream>>>(p);
-    return cudaGetLastError();
-  } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(64 + 128 * EG);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, igemm_kernel<BN, CL, CG, MS, EG, SPLIT>, p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(64 + 128 * EG);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if constexpr (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (tuning().pdl) {       // this grid may start its prologue before the previous kernel of the stream has drained
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, igemm_kernel<BN, CL, CG, MS, EG, SPLIT>, p);
 }
 
 }  // namespace rn
