@@ -296,6 +296,36 @@ int rn_conv2d_weight_grad(const void* x, const void* g, float* dw, int B, int H,
 /* db[c] = sum over the npix pixels of g[p][c] (bias gradient of any conv); g 16-bit [npix, C], db fp32 [C], overwritten. */
 int rn_bias_grad_16(const void* g, float* db, long long npix, int C, int fmt, void* stream);
 
+/* ---- training step (RenderNet_Shader.py:154-167): remaining weight gradients, PReLU slopes, dropout, loss, Adam -----------
+ * Weight gradient of ANY convolution / transposed convolution (2-D: D = kd = 1; 3-D; any stride; TF SAME) as a strided
+ * correlation on the CUDA cores, fp32 accumulation (atomics):
+ *   dW[tap = (kz*kh + ky)*kw + kx][a][b] = scale * sum_{n,z,y,x} P[n,z,y,x,a] * Q[n, z*sd+kz-pd, y*sh+ky-ph, x*sw+kx-pw, b]
+ * (terms whose Q index falls outside the grid are zero padding).  Forward conv (layer_util.conv3d tools/layer_util.py:228-265,
+ * slim.conv2d): P = dL/d(conv output), Q = the layer's input, (pd,ph,pw) = TF SAME pad-before -> dW[tap][co][ci].  Transposed
+ * conv (slim.conv2d_transpose, RenderNet_Shader.py:106-129; o = i*s + k - pb): P = the layer's input, Q = dL/d(output)
+ * -> dW[tap][ci][co].  P is [B,Dp,Hp,Wp,Cap] with Ca <= Cap channels used, Q [B,Dq,Hq,Wq,Cbp]; fmtP / fmtQ: RN_FMT_F16,
+ * RN_FMT_BF16, RN_FMT_F16X2 or 3 = fp32.  dW fp32, overwritten. */
+int rn_conv_weight_grad_direct(const void* P, const void* Q, float* dW, int B, int Dp, int Hp, int Wp, int Ca, int Cap, int Dq,
+                               int Hq, int Wq, int Cb, int Cbp, int kd, int kh, int kw, int sd, int sh, int sw, int pd, int ph,
+                               int pw, int fmtP, int fmtQ, float scale, void* stream);
+/* PReLU slope gradient (tools/layer_util.py:27-45: y = max(0,z) + alpha*min(0,z)): dalpha[c] = scale * sum_{z<0} g*z over the
+ * n elements (channel-last, n % C == 0) of g = dL/dy and the PRE-activation z, both 16-bit in `fmt`; dalpha fp32 [C], overwritten. */
+int rn_prelu_alpha_grad(const void* g, const void* z, float* dalpha, long long n, int C, int fmt, float scale, void* stream);
+/* tf.nn.dropout (RenderNet_Shader.py:39...123): out[i] = x[i] / keep where hash(seed, salt, i) < keep * 2^32, else 0 (16-bit in
+ * `fmt`, out may alias x).  Stateless: the same call on the gradient is the backward pass; rn_dropout_mask_host reproduces the
+ * mask on the host (1 = kept).  salt = index of the dropout call within the step. */
+int rn_dropout_16(const void* x, void* out, long long n, float keep, unsigned seed, unsigned salt, int fmt, void* stream);
+int rn_dropout_mask_host(unsigned char* mask, long long n, float keep, unsigned seed, unsigned salt);
+/* Reconstruction loss and its gradient w.r.t. the image (RenderNet_Shader.py:158-163): kind 0 = tf.losses.mean_squared_error
+ * (mean over all n elements), kind 1 = binary cross entropy summed per image and averaged over the batch, 1e-6 inside the logs.
+ * img / target / dimg fp32 [n] (dimg may be NULL), *loss (device double) is overwritten. */
+int rn_image_loss_grad(const float* img, const float* target, float* dimg, double* loss, long long n, int batch, int kind,
+                       void* stream);
+/* One tf.train.AdamOptimizer update of a flat fp32 parameter (RenderNet_Shader.py:167, beta1 = 0.5): m += (g-m)(1-beta1),
+ * v += (g^2-v)(1-beta2), param -= lr_t * m / (sqrt(v) + eps), with lr_t = lr * sqrt(1-beta2^t) / (1-beta1^t) passed by the caller. */
+int rn_adam_step(float* param, const float* grad, float* m, float* v, long long n, float lr_t, float beta1, float beta2, float eps,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

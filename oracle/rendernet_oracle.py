@@ -351,11 +351,21 @@ def init_shader_weights(seed: int = 0, is_greyscale: bool = False, width: int = 
 # ----------------------------------------------------------------------------------
 # Shader model fn  (RenderNet_Shader.py:32-131), inference (dropout identity)
 # ----------------------------------------------------------------------------------
-def rendernet_shader(models_in, W: Dict[str, np.ndarray], return_stages: bool = False):
+def rendernet_shader(models_in, W: Dict[str, np.ndarray], return_stages: bool = False, dropout=None):
     """models_in [B,H,W,128,1] (already resampled + axis-transformed).  Returns the
-    sigmoid image [B,4H,4W,3|1]; with return_stages also a dict of stage tensors."""
+    sigmoid image [B,4H,4W,3|1]; with return_stages also a dict of stage tensors.
+    dropout: None (inference, keep_prob 1) or callable(call_index, tensor) -> tensor applied at the ten tf.nn.dropout sites of
+    RenderNet_Shader.py:39,43,47,88,103,107,111,115,119,123 in graph order (the training graph; the caller supplies the masks)."""
     g = lambda n: W[n]
     st = {}
+    calls = [0]
+
+    def drop(t):
+        if dropout is None:
+            return t
+        t = dropout(calls[0], t)
+        calls[0] += 1
+        return t
 
     def c3(x, scope, stride=(1, 1, 1)):
         return conv3d(x, g(scope + "/weights"), g(scope + "/biases"), stride)
@@ -367,9 +377,9 @@ def rendernet_shader(models_in, W: Dict[str, np.ndarray], return_stages: bool = 
         return conv2d_transpose(x, g(scope + "/weights"), g(scope + "/biases"), (s, s))
 
     x = _t(models_in).float()
-    enc1 = prelu(c3(x, "encoder/e_conv1/e_conv1", (2, 2, 2)), g("encoder/e_conv1/alpha"))      # :36-39
-    enc2 = prelu(c3(enc1, "encoder/e_conv2/e_conv2", (1, 1, 2)), g("encoder/e_conv2/alpha"))   # :40-43
-    enc3 = prelu(c3(enc2, "encoder/e_conv3/e_conv3"), g("encoder/e_conv3/alpha"))              # :44-47
+    enc1 = drop(prelu(c3(x, "encoder/e_conv1/e_conv1", (2, 2, 2)), g("encoder/e_conv1/alpha")))      # :36-39
+    enc2 = drop(prelu(c3(enc1, "encoder/e_conv2/e_conv2", (1, 1, 2)), g("encoder/e_conv2/alpha")))   # :40-43
+    enc3 = drop(prelu(c3(enc2, "encoder/e_conv3/e_conv3"), g("encoder/e_conv3/alpha")))              # :44-47
     st["enc1"], st["enc2"], st["enc3"] = enc1, enc2, enc3
     h = enc3
     for k in range(1, 11):                                                                     # :51-60
@@ -386,7 +396,7 @@ def rendernet_shader(models_in, W: Dict[str, np.ndarray], return_stages: bool = 
         h = c2(t, f"encoder/res2_{k}/conv2_3x3") + h
     enc4_skip = c2(h, "encoder/res2_skip/con1_3X3") + enc4                                     # :82-84
     st["enc4_skip"] = enc4_skip
-    enc5 = prelu(c2(enc4_skip, "encoder/e_conv5/e_conv5"), g("encoder/e_conv5/alpha"))         # :86-88
+    enc5 = drop(prelu(c2(enc4_skip, "encoder/e_conv5/e_conv5"), g("encoder/e_conv5/alpha")))         # :86-88
     st["enc5"] = enc5
     h = enc5
     for k in range(1, 6):                                                                      # :91-95
@@ -394,12 +404,12 @@ def rendernet_shader(models_in, W: Dict[str, np.ndarray], return_stages: bool = 
         h = c2(t, f"encoder/res3_{k}/conv2_3x3") + h
     enc5_skip = c2(h, "encoder/res3_skip/con1_3X3") + enc5                                     # :97-99
     st["enc5_skip"] = enc5_skip
-    enc6 = prelu(c2(enc5_skip, "encoder/e_conv6/e_conv6"), g("encoder/e_conv6/alpha"))         # :101-103
-    enc7 = prelu(ct(enc6, "encoder/e_conv7/e_conv7", 2), g("encoder/e_conv7/alpha"))           # :105-107
-    enc7_1 = prelu(ct(enc7, "encoder/e_conv7_1/e_conv7_1", 1), g("encoder/e_conv7_1/alpha"))   # :109-111
-    enc8 = prelu(ct(enc7_1, "encoder/e_conv8/e_conv8", 2), g("encoder/e_conv8/alpha"))         # :113-115
-    enc9 = prelu(ct(enc8, "encoder/e_conv9/e_conv9", 2), g("encoder/e_conv9/alpha"))           # :117-119
-    enc10 = prelu(ct(enc9, "encoder/e_conv10/e_conv10", 1), g("encoder/e_conv10/alpha"))       # :121-123
+    enc6 = drop(prelu(c2(enc5_skip, "encoder/e_conv6/e_conv6"), g("encoder/e_conv6/alpha")))         # :101-103
+    enc7 = drop(prelu(ct(enc6, "encoder/e_conv7/e_conv7", 2), g("encoder/e_conv7/alpha")))           # :105-107
+    enc7_1 = drop(prelu(ct(enc7, "encoder/e_conv7_1/e_conv7_1", 1), g("encoder/e_conv7_1/alpha")))   # :109-111
+    enc8 = drop(prelu(ct(enc7_1, "encoder/e_conv8/e_conv8", 2), g("encoder/e_conv8/alpha")))         # :113-115
+    enc9 = drop(prelu(ct(enc8, "encoder/e_conv9/e_conv9", 2), g("encoder/e_conv9/alpha")))           # :117-119
+    enc10 = drop(prelu(ct(enc9, "encoder/e_conv10/e_conv10", 1), g("encoder/e_conv10/alpha")))       # :121-123
     st["enc6"], st["enc7"], st["enc7_1"], st["enc8"], st["enc9"], st["enc10"] = enc6, enc7, enc7_1, enc8, enc9, enc10
     logits = ct(enc10, "encoder/e_conv11", 1)                                                  # :125-129
     st["logits"] = logits

@@ -2,8 +2,8 @@
 
 This is what the reference's inverse rendering differentiates (Reconstruct_RenderNet_Face.py:383-412: `tf.gradients` of an
 image loss w.r.t. the latent shape / texture / pose, through the frozen RenderNet and through the trilinear weights of
-tools/resampling_voxel_grid.py:465-485).  Weight gradients / Adam (the training step of RenderNet_Shader.py:159-167) are the
-next stage and not built yet.
+tools/resampling_voxel_grid.py:465-485).  With `want_weight_grads` the same walk also produces dL/d(every variable) -- filters,
+biases, PReLU slopes -- which rendernet_b200/training.py turns into the training step of RenderNet_Shader.py:154-167.
 
 How it works: the model function (RenderNet_Shader.RenderNet) is run once with a TAPE attached to the variable store; every
 realised layer appends (kind, input, filter, activation, residual, output).  `backward()` walks the tape in reverse:
@@ -192,11 +192,14 @@ class ShaderInputGradients:
         return a
 
     # ------------------------------------------------------------------------------------------- backward
-    def backward(self, dimg, want_dvox: bool = True, want_dpose: bool = True, want_weight_grads: bool = False):
+    def backward(self, dimg, want_dvox: bool = True, want_dpose: bool = True, want_weight_grads: bool = False,
+                 tensor_core_wgrad: bool = True):
         """dimg: dL/dimg [B,512,512,3|1] (NumPy or tensor).  Returns (dL/dvoxels [B,S,S,S,1] or None, dL/dview_params [B,3] or None).
-        want_weight_grads (stage 2, partial): also fills `self.weight_grads` {variable name: fp32 device tensor} with dL/dW and
-        dL/dbias of every stride-1 conv2d layer (projection unit, res2 / res3 trunks, e_conv5 / e_conv6: 97 % of the parameters)
-        through the tcgen05 weight-gradient kernel (rn_conv2d_weight_grad)."""
+        want_weight_grads: also fills `self.weight_grads` {variable name: fp32 device tensor in the variable's TF layout} for EVERY
+        variable the forward pass used -- filters (tcgen05 weight-gradient kernel for the wide stride-1 2-D layers and, depth-folded,
+        the 3^3 layers; the strided-correlation kernel rn_conv_weight_grad_direct for the thin / strided / transposed ones), biases
+        and PReLU slopes (pre-activation recomputed: alpha starts at 0, tools/layer_util.py:38).  tensor_core_wgrad=False sends
+        every filter through the direct kernel (cross-check)."""
         if self.tape is None:
             raise RuntimeError("call forward() first")
         dev = self.store.device
@@ -207,6 +210,8 @@ class ShaderInputGradients:
         grads = {_key(self.img): dimg.contiguous()}
         dgrid = None
         self.weight_grads = {}
+        inv = 1.0 / self.loss_scale
+        need_inputs = want_dvox or want_dpose
         with torch.cuda.device(self.device), tf.use_store(self.store):
             for rec in reversed(self.tape):
                 y = rec["y"]
@@ -215,28 +220,33 @@ class ShaderInputGradients:
                     continue                                   # no gradient reaches this layer
                 if tuple(g.shape) != tuple(y.shape):           # the consumer saw a reshaped view (projection unit: [..,D,C] -> [..,D*C])
                     g = g.reshape(tuple(y.shape))
+                if rec["op"] == "dropout":                     # d(x * mask / keep) = g * mask / keep: the same stateless kernel
+                    grads[_key(rec["x"])] = ops.dropout(g, rec["keep"], rec["seed"], rec["salt"])
+                    continue
                 act = rec["act"]
                 if act == "sigmoid":
                     co = int(y.shape[-1])
                     g = ops.sigmoid_backward(g, y, ops.round_up(co, 16), self.loss_scale, fmt)
                 elif act == "prelu":
-                    g = ops.prelu_backward(g, y, self._alpha(rec["alpha"], int(y.shape[-1])))
+                    alpha = rec["alpha"]
+                    if want_weight_grads and not isinstance(alpha, str):
+                        # dL/dalpha = sum_{z<0} g*z needs the pre-activation (alpha may be 0): re-run the layer without its PReLU
+                        self.weight_grads[alpha._rn_name] = ops.prelu_alpha_grad(g, rec["rerun"](), inv)
+                    g = ops.prelu_backward(g, y, self._alpha(alpha, int(y.shape[-1])))
+                if want_weight_grads:
+                    self._weight_grads_of(rec, g, inv, tensor_core_wgrad)
                 if rec["op"] == "resample_conv1":              # e_conv1 (5^3 s2, 1 -> 8) fused with the resampler in the forward pass
-                    N = self.new_size
-                    w32 = rec["w"].to(dev).float().contiguous()
-                    dgrid = ops.conv3d_backward_data_direct(g, w32, (self.B, N, N, N, 1), rec["stride"], want32=True,
-                                                            out_scale=1.0 / self.loss_scale)
+                    if need_inputs:
+                        N = self.new_size
+                        w32 = rec["w"].to(dev).float().contiguous()
+                        dgrid = ops.conv3d_backward_data_direct(g, w32, (self.B, N, N, N, 1), rec["stride"], want32=True,
+                                                                out_scale=inv)
                     continue
                 res = rec.get("residual")
-                if res is not None:                            # y = conv(x) + res: the gradient flows to res unchanged
+                if res is not None:                            # y = act(conv(x) + res): the gradient flows to res unchanged
                     k = _key(res)
                     grads[k] = ops.bias_act(g, None, None, None, residual=grads[k]) if k in grads else g
                 x, kind, stride = rec["x"], rec["kind"], rec["stride"]
-                if want_weight_grads and kind == "conv2d" and int(x.shape[-1]) % 128 == 0 and int(y.shape[-1]) % 128 == 0:
-                    k = int(rec["w"].shape[0])
-                    self.weight_grads[rec["w"]._rn_name] = ops.conv2d_weight_grad(x, g, k, k) * (1.0 / self.loss_scale)
-                    if rec["b"] is not None:
-                        self.weight_grads[rec["b"]._rn_name] = ops.bias_grad(g) * (1.0 / self.loss_scale)
                 acc = grads.pop(_key(x), None)                 # gradient already collected for x (fan-out): fused as `residual`
                 if kind == "conv3d" and stride == 2:           # e_conv2: thin, z-strided -> CUDA cores
                     w32 = rec["w"].to(dev).float().contiguous()
@@ -259,12 +269,65 @@ class ShaderInputGradients:
                     else:                                      # transposed conv, stride 2
                         gx = ops.conv2d(self._space_to_depth(g), L, residual=acc)
                 grads[_key(x)] = gx
-            if dgrid is None:
-                raise RuntimeError("the tape holds no fused resample + e_conv1 record (is this the Shader path?)")
-            dvox, dminv = ops.resample_backward(self.vox, self.minv, dgrid, True, want_dvox, want_dpose)
+            dvox = dminv = None
+            if need_inputs:
+                if dgrid is None:
+                    raise RuntimeError("the tape holds no fused resample + e_conv1 record (is this the Shader path?)")
+                dvox, dminv = ops.resample_backward(self.vox, self.minv, dgrid, True, want_dvox, want_dpose)
             torch.cuda.synchronize()
         self.last_dgrid = dgrid
         dpose = None
         if want_dpose:
             dpose = pose_matrix_jacobian_vjp(self.view_params, dminv.cpu().numpy(), self.size, self.new_size)
         return (dvox.cpu().numpy() if dvox is not None else None), dpose
+
+    # ------------------------------------------------------------------------------------------- weight gradients
+    def _weight_grads_of(self, rec, g, inv: float, tensor_core: bool):
+        """dL/dW and dL/db of one recorded layer from g = dL/d(pre-activation) (16-bit, carrying the loss scale)."""
+        w, b = rec["w"], rec["b"]
+        wg = self.weight_grads
+        cout = int(w.shape[2]) if rec.get("kind") == "conv2d_transpose" else int(w.shape[-1])
+        if b is not None:
+            wg[b._rn_name] = ops.bias_grad(g)[:cout] * inv          # g may carry zero-padded channels (e_conv11: 3 of 16)
+        if rec["op"] == "resample_conv1":
+            # e_conv1 read the resampled grid straight out of the fused kernel: materialise it once for the correlation
+            q = ops.resample(rec["grid"].voxel, rec["grid"].minv, self.new_size, True)
+            st = tuple(int(v) for v in rec["stride"])
+            ks = tuple(int(v) for v in w.shape[:3])
+            pad = tuple(ops.same_pad_before(self.new_size, ks[i], st[i]) for i in range(3))
+            d = ops.conv_weight_grad_direct(g, q, ks, st, pad, Ca=cout, Cb=int(w.shape[3]), scale=inv)      # [k,k,k,co,ci]
+            wg[w._rn_name] = d.permute(0, 1, 2, 4, 3).contiguous()
+            return
+        x, kind, stride = rec["x"], rec["kind"], rec["stride"]
+        if kind == "conv2d":
+            kh, kw, ci, co = (int(v) for v in w.shape)
+            if tensor_core and ci % 128 == 0 and co % 128 == 0 and kh * kw <= 16:
+                wg[w._rn_name] = ops.conv2d_weight_grad(x, g, kh, kw) * inv
+            else:
+                pad = (ops.same_pad_before(int(x.shape[1]), kh, 1), ops.same_pad_before(int(x.shape[2]), kw, 1))
+                d = ops.conv_weight_grad_direct(g, x, (kh, kw), (1, 1), pad, Ca=co, Cb=ci, scale=inv)           # [kh,kw,co,ci]
+                wg[w._rn_name] = d.permute(0, 1, 3, 2).contiguous()
+        elif kind == "conv3d":
+            k1, k2, k3, ci, co = (int(v) for v in w.shape)
+            st = (1, 1, int(stride))                                   # stride 2 = the z-strided e_conv2 ([1,1,2])
+            D = int(x.shape[3])
+            if (tensor_core and st == (1, 1, 1) and (k1, k2, k3) == (3, 3, 3) and (D * ci) % 128 == 0 and (D * co) % 128 == 0):
+                # depth-folded: a 3x3 conv2d over [B,H,W,D*ci] -> [B,H,W,D*co] whose filter is block-banded; its tensor-core
+                # weight gradient holds dW[k1][k2][k3] on the (k3-1)-th block diagonal, summed over the D depth slices
+                B_, H, Wd = (int(v) for v in x.shape[:3])
+                full = ops.conv2d_weight_grad(x.reshape(B_, H, Wd, D * ci), g.reshape(B_, H, Wd, D * co), 3, 3)
+                full = full.view(3, 3, D, ci, D, co)
+                d = torch.stack([torch.diagonal(full, offset=-(k - 1), dim1=2, dim2=4).sum(-1) for k in range(3)], dim=2)
+                wg[w._rn_name] = (d * inv).contiguous()                # [3,3,3,ci,co]
+            else:
+                pad = tuple(ops.same_pad_before(int(x.shape[1 + i]), (k1, k2, k3)[i], st[i]) for i in range(3))
+                d = ops.conv_weight_grad_direct(g, x, (k1, k2, k3), st, pad, Ca=co, Cb=ci, scale=inv)           # [k,k,k,co,ci]
+                wg[w._rn_name] = d.permute(0, 1, 2, 4, 3).contiguous()
+        elif kind == "conv2d_transpose":
+            kh, kw, co, ci = (int(v) for v in w.shape)                 # TF transposed-conv filter [kh,kw,Cout,Cin]
+            s = int(stride)
+            pad = (ops.same_pad_before(int(x.shape[1]) * s, kh, s), ops.same_pad_before(int(x.shape[2]) * s, kw, s))
+            d = ops.conv_weight_grad_direct(x, g, (kh, kw), (s, s), pad, Ca=ci, Cb=co, scale=inv)               # [kh,kw,ci,co]
+            wg[w._rn_name] = d.permute(0, 1, 3, 2).contiguous()
+        else:
+            raise NotImplementedError(f"no weight-gradient path for {kind}")

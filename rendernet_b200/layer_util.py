@@ -362,7 +362,8 @@ def _deferred_conv(kind, x, w, b, stride):
     def run(act, alpha, residual, want32):
         xt = _as16(xin)
         y = _run(xt, act, alpha, residual, want32)
-        _record(op="conv", kind=kind, stride=stride, x=xt, w=w, b=b, act=act, alpha=alpha, residual=residual, y=y)
+        _record(op="conv", kind=kind, stride=stride, x=xt, w=w, b=b, act=act, alpha=alpha, residual=residual, y=y,
+                rerun=lambda: _run(xt, None, None, residual, False))      # the pre-activation z (PReLU slope gradient)
         return y
 
     def _run(xt, act, alpha, residual, want32):
@@ -482,7 +483,9 @@ def _deferred_direct3d(x, w, b, stride):
             bd = _dev_vec(b) if b is not None else torch.zeros(cout, device=wd.device, dtype=torch.float32)
             ad = _alpha_arg(alpha, cout) if act == "prelu" else None
             y = ops.resample_conv1(xin.voxel, xin.minv, xin.new_size, wd, bd, ad, tf.COMPUTE_DTYPE, fmt=_store().fmt)
-            _record(op="resample_conv1", grid=xin, w=w, b=b, act=act, alpha=alpha, stride=list(stride), y=y)
+            _record(op="resample_conv1", grid=xin, w=w, b=b, act=act, alpha=alpha, stride=list(stride), y=y,
+                    rerun=lambda: ops.resample_conv1(xin.voxel, xin.minv, xin.new_size, wd, bd, None, tf.COMPUTE_DTYPE,
+                                                     fmt=_store().fmt))
             return y
         if (USE_FUSED_RESAMPLE_CONV1 and isinstance(xin, ConcatResampledGrid) and xin.transform and xin._value is None
                 and key == (5, 8, 5) and list(stride) == [2, 2, 2] and xin.new_size % 16 == 0

@@ -810,3 +810,94 @@ def bias_grad(g) -> torch.Tensor:
     db = torch.empty(Cc, device=g.device, dtype=torch.float32)
     check(lib.rn_bias_grad_16(g.data_ptr(), db.data_ptr(), g.numel() // Cc, Cc, fmt, _stream()), "rn_bias_grad_16")
     return db
+
+
+# --------------------------------------------------------------------------------------------- training step (rn_train.cu)
+def _fmt_any(t) -> int:
+    if isinstance(t, Split16):
+        return 2
+    return 3 if t.dtype == torch.float32 else fmt_of(t.dtype)
+
+
+def same_pad_before(n_in: int, k: int, s: int) -> int:
+    """TF SAME padding in front of a dimension (tools/layer_util.py conv wrappers all use padding='SAME')."""
+    n_out = -(-n_in // s)
+    return max((n_out - 1) * s + k - n_in, 0) // 2
+
+
+def conv_weight_grad_direct(P, Q, ksize: Sequence[int], stride: Sequence[int], pad: Sequence[int], Ca: Optional[int] = None,
+                            Cb: Optional[int] = None, scale: float = 1.0) -> torch.Tensor:
+    """dW[tap][a][b] = scale * sum_pos P[pos][a] * Q[pos*stride + tap - pad][b] (rn_conv_weight_grad_direct): P on the coarse
+    grid, Q on the fine grid, channel-last, 4-D ([B,H,W,C]: 2-D conv) or 5-D ([B,d1,d2,d3,C]); 16-bit / Split16 / fp32 each.
+    Ca / Cb: channels actually used (<= the tensors' channel pitch).  -> fp32 [*ksize, Ca, Cb]."""
+    P, Q = _cuda(P), _cuda(Q)
+    if len(P.shape) == 4:
+        P5, Q5 = (P.shape[0], 1) + tuple(P.shape[1:]), (Q.shape[0], 1) + tuple(Q.shape[1:])
+        ks, st, pd = (1,) + tuple(ksize), (1,) + tuple(stride), (0,) + tuple(pad)
+    else:
+        P5, Q5, ks, st, pd = tuple(P.shape), tuple(Q.shape), tuple(ksize), tuple(stride), tuple(pad)
+    B, Dp, Hp, Wp, Cap = (int(v) for v in P5)
+    _, Dq, Hq, Wq, Cbp = (int(v) for v in Q5)
+    assert int(Q5[0]) == B
+    Ca, Cb = int(Ca or Cap), int(Cb or Cbp)
+    dW = torch.empty(tuple(int(k) for k in ksize) + (Ca, Cb), device=P.device, dtype=torch.float32)
+    check(lib.rn_conv_weight_grad_direct(P.data_ptr(), Q.data_ptr(), dW.data_ptr(), B, Dp, Hp, Wp, Ca, Cap, Dq, Hq, Wq, Cb, Cbp,
+                                         int(ks[0]), int(ks[1]), int(ks[2]), int(st[0]), int(st[1]), int(st[2]),
+                                         int(pd[0]), int(pd[1]), int(pd[2]), _fmt_any(P), _fmt_any(Q), float(scale), _stream()),
+          "rn_conv_weight_grad_direct")
+    return dW
+
+
+def prelu_alpha_grad(g, z, scale: float = 1.0) -> torch.Tensor:
+    """dalpha[c] = scale * sum_{z<0} g*z over a channel-last pair of 16-bit tensors (rn_prelu_alpha_grad) -> fp32 [C]."""
+    g, z = _cuda(g), _cuda(z)
+    fmt = 2 if isinstance(g, Split16) else fmt_of(g.dtype)
+    if isinstance(z, Split16) != (fmt == 2) or tuple(z.shape) != tuple(g.shape):
+        raise TypeError("prelu_alpha_grad: g and z must share shape and 16-bit format")
+    Cc = int(g.shape[-1])
+    da = torch.empty(Cc, device=g.device, dtype=torch.float32)
+    check(lib.rn_prelu_alpha_grad(g.data_ptr(), z.data_ptr(), da.data_ptr(), g.numel(), Cc, fmt, float(scale), _stream()),
+          "rn_prelu_alpha_grad")
+    return da
+
+
+def dropout(x, keep: float, seed: int, salt: int):
+    """tf.nn.dropout on a 16-bit activation (rn_dropout_16): x / keep where kept, 0 elsewhere; the mask is a pure function of
+    (seed, salt, element index), so calling this on the gradient with the same (seed, salt) is the backward pass."""
+    x = _cuda(x)
+    fmt = 2 if isinstance(x, Split16) else fmt_of(x.dtype)
+    out = _alloc16(tuple(x.shape), fmt, torch.float16 if fmt == 2 else x.dtype, x.device)
+    check(lib.rn_dropout_16(x.data_ptr(), out.data_ptr(), x.numel(), float(keep), int(seed) & 0xFFFFFFFF, int(salt) & 0xFFFFFFFF,
+                            fmt, _stream()), "rn_dropout_16")
+    return _wrap16(out, fmt)
+
+
+def dropout_mask_host(n: int, keep: float, seed: int, salt: int):
+    """The mask rn_dropout_16 applies, recomputed on the host (NumPy uint8 [n], 1 = kept)."""
+    import numpy as np
+    m = np.empty(int(n), np.uint8)
+    check(lib.rn_dropout_mask_host(m.ctypes.data, int(n), float(keep), int(seed) & 0xFFFFFFFF, int(salt) & 0xFFFFFFFF),
+          "rn_dropout_mask_host")
+    return m
+
+
+def image_loss_grad(img: torch.Tensor, target: torch.Tensor, kind: str = "mse", want_grad: bool = True):
+    """Reconstruction loss of RenderNet_Shader.py:158-163 ("mse" | "bce") and dL/dimg (rn_image_loss_grad)
+    -> (loss: 0-d float64 device tensor, dimg fp32 like img or None)."""
+    img, target = _cuda(img, torch.float32), _cuda(target, torch.float32)
+    assert tuple(img.shape) == tuple(target.shape) and img.is_contiguous() and target.is_contiguous()
+    loss = torch.empty((), device=img.device, dtype=torch.float64)
+    dimg = torch.empty_like(img) if want_grad else None
+    check(lib.rn_image_loss_grad(img.data_ptr(), target.data_ptr(), _ptr(dimg), loss.data_ptr(), img.numel(), int(img.shape[0]),
+                                 {"mse": 0, "bce": 1}[kind], _stream()), "rn_image_loss_grad")
+    return loss, dimg
+
+
+def adam_step(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr_t: float, beta1: float, beta2: float,
+              eps: float):
+    """In-place tf.train.AdamOptimizer update of one fp32 device parameter (rn_adam_step)."""
+    for t in (param, grad, m, v):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()) or t.numel() != param.numel():
+            raise TypeError("adam_step: contiguous fp32 CUDA tensors of one size expected")
+    check(lib.rn_adam_step(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(), float(lr_t), float(beta1),
+                           float(beta2), float(eps), _stream()), "rn_adam_step")

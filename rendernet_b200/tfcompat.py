@@ -51,6 +51,8 @@ class VariableStore:
         self.loaded: set = set()       # names installed by load_weight_dict
         self.consumed: set = set()     # loaded names a model function has asked for
         self.tape = None               # list -> every realised layer appends a record (rendernet_b200/backward.py)
+        self.dropout_seed = None       # int -> tf.nn.dropout(keep < 1) draws its masks from (seed, call index, element)
+        self.dropout_calls = 0
         self.phong = None              # dict (ops.conv2d_transpose_xfold) -> the output layer applies the Phong composite itself
         self.phong_u8 = None           # ... and leaves the uint8 image here
 
@@ -292,10 +294,21 @@ class _NN:
     @staticmethod
     def dropout(x, keep_prob):
         kp = float(keep_prob)
-        if kp != 1.0:
-            raise NotImplementedError("rendernet_b200 is the inference path: dropout keep_prob must be 1 "
-                                      "(layer_util.keep_prob(prob, is_training=False))")
-        return x
+        if kp == 1.0:
+            return x
+        st = _STORE
+        if st.dropout_seed is None:
+            raise NotImplementedError("dropout with keep_prob < 1 is the training path: it needs a store with a dropout seed "
+                                      "(rendernet_b200.training.ShaderTrainer); inference uses keep_prob(prob, is_training=False)")
+        y = realize(x)                         # 16-bit activation of the producing layer (its PReLU already applied)
+        if not isinstance(y, ops.Split16) and y.dtype == torch.float32:
+            raise NotImplementedError("dropout on an fp32 tensor is not on the Shader path")
+        salt = st.dropout_calls                # index of this dropout call within the step: part of the mask's counter
+        st.dropout_calls += 1
+        yd = ops.dropout(y, kp, st.dropout_seed, salt)
+        if st.tape is not None:
+            st.tape.append(dict(op="dropout", x=y, y=yd, keep=kp, seed=st.dropout_seed, salt=salt))
+        return yd
 
     @staticmethod
     def sigmoid(x, name=None):
