@@ -267,8 +267,10 @@ int rn_phong_composite(const float* img, const float* light_dir, const float* li
  * What inverse rendering differentiates through the frozen network (Reconstruct_RenderNet_Face.py:383-412).  The data
  * gradient of every stride-1 convolution / transposed convolution is itself a convolution and runs through rn_conv_igemm
  * (mirrored taps, filters packed with the channel roles swapped: rendernet_b200/backward.py); these are the remaining pieces. */
-/* dL/d(pre) = g * (y > 0 ? 1 : alpha[c]) for y = prelu(pre) stored post-activation (alpha >= 0); 16-bit in/out, n elements,
- * C = innermost (channel) extent.  tools/layer_util.py:27-45. */
+/* dL/d(pre) = g * (y > 0 ? 1 : alpha[c]); 16-bit in/out, n elements, C = innermost (channel) extent (tools/layer_util.py:27-45).
+ * `y` decides the side of the kink: the stored post-activation output works while every slope is >= 0; with a negative slope
+ * (y = alpha*pre > 0 for pre < 0) pass the PRE-activation instead (rendernet_b200/backward.py re-runs the layer without its
+ * PReLU in that case, and always in the training step, whose slope gradient needs it anyway). */
 int rn_prelu_backward_16(const void* g, const void* y, const float* alpha, void* out, long long n, int C, int fmt, void* stream);
 /* Network output img = sigmoid(logits) (RenderNet_Shader.py:127-130): out16[p, c] = scale * g[p,c] * img[p,c] * (1 - img[p,c])
  * for c < C, 0 for C <= c < Cpad (the last up-conv's data-gradient GEMM needs K % 16 == 0).  g, img fp32 [npix, C]. */

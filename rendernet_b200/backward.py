@@ -181,6 +181,14 @@ class ShaderInputGradients:
         t = t.reshape(*lead, H2 // 2, W2 // 2, 4 * Cc).contiguous()
         return ops.Split16(t) if isinstance(g, ops.Split16) else t
 
+    def _has_negative_slope(self, alpha, a_dev) -> bool:
+        key = ("alpha<0", alpha._rn_name)
+        v = self._dgrad_cache.get(key)
+        if v is None:
+            v = bool((a_dev < 0).any().item())
+            self._dgrad_cache[key] = v
+        return v
+
     def _alpha(self, alpha, n):
         if isinstance(alpha, str):                 # tf.nn.relu branch
             return self._zeros(n)
@@ -229,10 +237,16 @@ class ShaderInputGradients:
                     g = ops.sigmoid_backward(g, y, ops.round_up(co, 16), self.loss_scale, fmt)
                 elif act == "prelu":
                     alpha = rec["alpha"]
-                    if want_weight_grads and not isinstance(alpha, str):
-                        # dL/dalpha = sum_{z<0} g*z needs the pre-activation (alpha may be 0): re-run the layer without its PReLU
-                        self.weight_grads[alpha._rn_name] = ops.prelu_alpha_grad(g, rec["rerun"](), inv)
-                    g = ops.prelu_backward(g, y, self._alpha(alpha, int(y.shape[-1])))
+                    a_dev = self._alpha(alpha, int(y.shape[-1]))
+                    sign_src = y                    # the stored output tells the side of the kink as long as every slope is >= 0
+                    if not isinstance(alpha, str) and (want_weight_grads or self._has_negative_slope(alpha, a_dev)):
+                        # Re-run the layer without its PReLU to get the pre-activation z: dL/dalpha = sum_{z<0} g*z needs it (alpha
+                        # starts at 0), and so does the derivative itself once a slope is negative (y = alpha*z > 0 for z < 0;
+                        # Adam's first step already makes half of the slopes negative).
+                        sign_src = rec["rerun"]()
+                        if want_weight_grads:
+                            self.weight_grads[alpha._rn_name] = ops.prelu_alpha_grad(g, sign_src, inv)
+                    g = ops.prelu_backward(g, sign_src, a_dev)
                 if want_weight_grads:
                     self._weight_grads_of(rec, g, inv, tensor_core_wgrad)
                 if rec["op"] == "resample_conv1":              # e_conv1 (5^3 s2, 1 -> 8) fused with the resampler in the forward pass

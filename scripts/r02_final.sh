@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 final validation on a fresh box: the whole GPU suite, smoke(), the default bench line, configs 4 / 5, the reference arm
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r02_final_gpu_suite.log 2>&1; echo "gpu suite rc=$?"
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02_final_gpu_suite.log 2>&1; echo "gpu suite rc=$?"
 tail -4 gpurun_out/r02_final_gpu_suite.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 900 python bench.py > gpurun_out/r02_final_bench_c2.json 2> gpurun_out/r02_final_bench_c2.err; echo "bench rc=$?"

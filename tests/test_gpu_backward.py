@@ -206,7 +206,7 @@ def test_full_size_input_gradients_match_oracle_autograd(golden_dir, precision):
         c = float((got.ravel() * want.ravel()).sum() / (np.linalg.norm(got) * np.linalg.norm(want)))
         print(f"[{precision}] dL/d({n}) {tuple(got.shape)}: rms err {_rms_err(got, want):.2e}, cosine {c:.6f}")
         assert got.shape == want.shape and c > (0.9995 if precision == "exact" else 0.99)
-    assert len(ig.weight_grads) == 2 * 35          # filters and biases of projection, res2 x21, e_conv5, res3 x11, e_conv6
+    assert len(ig.weight_grads) == 166             # every filter, bias and PReLU slope (tests/test_gpu_training.py checks them all)
     # Why percent-level and not 1e-6 like the single layers: the two forward passes differ by ~1.6e-4 (exact) / 2e-3 (fast)
     # relative at the deep layers, so a fraction f ~ 0.8 x that of all units sits on opposite sides of the PReLU kink in the two
     # implementations; each such unit contributes a full-size, independent error to the gradient, i.e. a relative rms error of

@@ -330,5 +330,5 @@ def test_fused_phong_epilogue_is_bit_identical_to_the_separate_pass(precision):
     assert outs[True][1].std() > 5          # not a constant image
     plain = RenderEngine(W, batch=2, precision=precision, use_graph=False).render(vox, poses).numpy()
     for b in range(2):
-        ref = orc.np_phong_composite(plain[b:b + 1], phong["light_dir"][b], phong["light_col"][b], 0.3, 0.7)
+        ref = orc.np_phong_composite(plain[b:b + 1], phong["light_dir"][b:b + 1], phong["light_col"][b:b + 1], 0.3, 0.7)
         assert np.abs(ref - outs[True][0][b:b + 1]).max() < 2e-6
