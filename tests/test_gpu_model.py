@@ -317,7 +317,7 @@ def test_fused_phong_epilogue_is_bit_identical_to_the_separate_pass(precision):
     vox[0, 16:48, 20:44, 12:52] = 1.0
     vox[1, 24:40, 8:56, 24:40] = 1.0
     poses = np.array([[40.0, 20.0, 3.3], [200.0, 35.0, 2.9]], np.float32)
-    phong = dict(light_dir=np.stack([orc.generate_light_pos(60.0, 250.0), orc.generate_light_pos(30.0, 90.0)]).astype(np.float32),
+    phong = dict(light_dir=np.concatenate([orc.generate_light_pos(60.0, 250.0), orc.generate_light_pos(30.0, 90.0)]).astype(np.float32),
                  light_col=np.array([[1.0, 1.0, 1.0], [0.9, 0.8, 0.7]], np.float32), ambient=0.3, k_diffuse=0.7)
     outs = {}
     for fuse in (True, False):
