@@ -123,6 +123,59 @@ __global__ void __launch_bounds__(256) wgrad_direct_kernel(const WgradDirectPara
     }
 }
 
+// Thin layers (e_conv1: 8 x 1 channels, 125 taps; e_conv11: 16 x 3): a 32 x 32 tile would be >95 % padding.  Here a thread owns a
+// whole CA x CB block of partial sums over its own positions (consecutive threads = consecutive positions: coalesced), and the
+// CTA (one tap) reduces them by warp shuffles + shared memory before CA x CB atomics.
+template <int CA, int CB>
+__global__ void __launch_bounds__(256) wgrad_thin_kernel(const WgradDirectParams p) {
+  __shared__ float red[8][CA * CB];
+  const int tap = blockIdx.y;
+  const int kx = tap % p.kw, ky = (tap / p.kw) % p.kh, kz = tap / (p.kw * p.kh);
+  float acc[CA][CB];
+#pragma unroll
+  for (int a = 0; a < CA; ++a)
+#pragma unroll
+    for (int b = 0; b < CB; ++b) acc[a][b] = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long pos = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pos < p.npos; pos += stride) {
+    long long r = pos;
+    const int x = static_cast<int>(r % p.Wp); r /= p.Wp;
+    const int y = static_cast<int>(r % p.Hp); r /= p.Hp;
+    const int z = static_cast<int>(r % p.Dp);
+    const int n = static_cast<int>(r / p.Dp);
+    const int qx = x * p.sw + kx - p.pw, qy = y * p.sh + ky - p.ph, qz = z * p.sd + kz - p.pd;
+    if (qx < 0 || qx >= p.Wq || qy < 0 || qy >= p.Hq || qz < 0 || qz >= p.Dq) continue;
+    const long long pb = pos * p.Cap;
+    const long long qb = (((static_cast<long long>(n) * p.Dq + qz) * p.Hq + qy) * p.Wq + qx) * p.Cbp;
+    float qv[CB];
+#pragma unroll
+    for (int b = 0; b < CB; ++b) qv[b] = ld_any(p.Q, qb + b, p.fmtQ, p.planeQ);
+#pragma unroll
+    for (int a = 0; a < CA; ++a) {
+      const float pv = ld_any(p.P, pb + a, p.fmtP, p.planeP);
+#pragma unroll
+      for (int b = 0; b < CB; ++b) acc[a][b] = fmaf(pv, qv[b], acc[a][b]);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < CA; ++a)
+#pragma unroll
+    for (int b = 0; b < CB; ++b) {
+      float v = acc[a][b];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][a * CB + b] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < CA * CB) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    if (v != 0.f) atomicAdd(&p.dW[static_cast<long long>(tap) * CA * CB + threadIdx.x], v * p.scale);
+  }
+}
+
 // dalpha[c] += scale * sum over elements of channel c with z < 0 of g * z
 __global__ void __launch_bounds__(256) prelu_alpha_grad_kernel(const void* __restrict__ g, const void* __restrict__ z,
                                                                float* __restrict__ dalpha, long long n, int C, int fmt, float scale) {
@@ -220,6 +273,17 @@ extern "C" int rn_conv_weight_grad_direct(const void* P, const void* Q, float* d
   p.a_tiles = (Ca + kTile - 1) / kTile;
   p.b_tiles = (Cb + kTile - 1) / kTile;
   p.scale = scale;
+  if ((Ca == 8 && Cb == 1) || (Ca == 16 && Cb == 3)) {               // thin layers: per-thread channel blocks, positions across threads
+    long long nsplit = (148LL * 8 + taps - 1) / taps;
+    const long long maxsplit = (p.npos + 255) / 256;
+    if (nsplit > maxsplit) nsplit = maxsplit;
+    if (nsplit < 1) nsplit = 1;
+    dim3 grid(static_cast<unsigned>(nsplit), static_cast<unsigned>(taps));
+    if (Ca == 8) wgrad_thin_kernel<8, 1><<<grid, 256, 0, st>>>(p);
+    else wgrad_thin_kernel<16, 3><<<grid, 256, 0, st>>>(p);
+    RN_COUNT_LAUNCH();
+    return static_cast<int>(cudaGetLastError());
+  }
   const long long tiles = taps * p.a_tiles * p.b_tiles;
   const long long nchunks = (p.npos + kChunk - 1) / kChunk;
   long long nsplit = (148LL * 8 + tiles - 1) / tiles;               // ~8 CTAs per SM in flight
