@@ -190,8 +190,9 @@ def _oracle_step(grid, Wt, target, keep, seed):
 def test_gradients_of_every_variable_match_oracle_autograd(golden_dir, precision):
     """Full-size Shader network, chair, B = 1, dropout keep 0.75, MSE against a random target: loss, image and dL/d(variable) for
     all 166 variables (filters, biases, PReLU slopes) vs torch.autograd through the CPU oracle with the same dropout masks.
-    Percent-level agreement is what two fp32-class implementations of this graph give (PReLU units that sit on opposite sides
-    of the kink, see tests/test_gpu_backward.py); the per-variable bar is the gradient's direction (cosine) and norm."""
+    The per-variable bar is the gradient's direction (cosine) and norm: with a coherent (real) loss gradient the PReLU units
+    that sit on opposite sides of the kink in the two implementations no longer dominate (they do for the white-noise image
+    gradient of tests/test_gpu_backward.py) and the agreement is 1e-4-level in exact precision."""
     from rendernet_b200.training import ShaderTrainer
     vox, poses, grid, target = _scene(golden_dir)
     W = orc.init_shader_weights(seed=1, alpha_range=(-0.1, 0.3), bias_jitter=0.02)     # a quarter of the slopes negative
@@ -221,9 +222,9 @@ def test_gradients_of_every_variable_match_oracle_autograd(golden_dir, precision
     for k, v in kinds.items():
         print(f"[{precision}] {k}: {len(v)} variables, cosine min {min(c for c, _ in v):.5f} median {np.median([c for c, _ in v]):.5f}, "
               f"norm ratio {min(r for _, r in v):.4f}..{max(r for _, r in v):.4f}")
-    bar = 0.995 if precision == "exact" else 0.95
+    bar = 0.9999 if precision == "exact" else 0.999          # measured: 1.00000 / 0.99988 (profiles/r02_training_parity.log)
     assert c_min > bar, (worst, c_min)
-    assert all(abs(r - 1) < (0.05 if precision == "exact" else 0.3) for _, r, _ in rows)
+    assert all(abs(r - 1) < (5e-3 if precision == "exact" else 2e-2) for _, r, _ in rows)      # measured: 4e-4 / 4.7e-3
 
 
 def test_two_adam_steps_follow_the_oracle(golden_dir):
