@@ -124,6 +124,10 @@ class ShaderTrainer(ShaderInputGradients):
         with torch.cuda.device(self.device):
             loss, dimg = ops.image_loss_grad(img.contiguous(), tgt, self.loss_kind)
         self.backward(dimg, want_dvox=False, want_dpose=False, want_weight_grads=True)
+        # a 16-bit gradient that overflowed the loss scale turns into inf / NaN and reaches the first layer through every path
+        first = next((g for n, g in self.weight_grads.items() if n.endswith("e_conv1/e_conv1/weights")), None)
+        if first is not None and not bool(torch.isfinite(first).all().item()):
+            raise FloatingPointError(f"gradient overflow in the 16-bit backward pass at loss_scale={self.loss_scale:g}")
         missing = sorted(set(self.store.vars) - set(self.weight_grads))
         if missing:
             raise RuntimeError(f"{len(missing)} variables received no gradient, e.g. {missing[:3]}")
@@ -132,7 +136,14 @@ class ShaderTrainer(ShaderInputGradients):
 
     def step(self, voxels, view_params, target) -> float:
         """One optimiser step (RenderNet_Shader.py:156-167); returns the loss BEFORE the update."""
-        loss, grads = self.loss_and_gradients(voxels, view_params, target, training=True)
+        for _ in range(12):
+            try:
+                loss, grads = self.loss_and_gradients(voxels, view_params, target, training=True)
+                break
+            except FloatingPointError:                 # dynamic loss scaling: halve and redo the step (same dropout masks)
+                self.loss_scale *= 0.5
+        else:
+            raise FloatingPointError("the backward pass overflows even at a loss scale of %g" % self.loss_scale)
         self.apply_gradients(grads)
         return loss
 

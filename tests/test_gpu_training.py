@@ -268,3 +268,33 @@ def test_two_adam_steps_follow_the_oracle(golden_dir):
         c = _cos(du, dr)
         print(f"  update of {n}: cosine {c:.4f}, |update| mean {np.abs(du).mean():.2e} vs {np.abs(dr).mean():.2e}")
         assert c > 0.9
+
+
+def test_greyscale_bce_batch2_gradients_match_oracle_autograd(golden_dir):
+    """The configuration the reference ships (config_RenderNet.json: is_greyscale, keep_prob 1.0, batch > 1 allowed): one-channel
+    output, binary cross entropy (RenderNet_Shader.py:158-161), B = 2 with two poses.  Loss and the gradients of all variables vs
+    torch.autograd through the oracle, exact precision."""
+    from rendernet_b200.training import ShaderTrainer
+    bv = np.load(os.path.join(golden_dir, "binvox.npz"))
+    chair = np.unpackbits(bv["chair_bits"]).reshape(1, 64, 64, 64, 1).astype(np.float32)
+    vox = np.concatenate([chair, chair[:, ::-1].copy()], 0)
+    poses = np.concatenate([orc.compute_pose_param(250.0, 60.0, 3.3), orc.compute_pose_param(40.0, 75.0, 3.0)]).astype(np.float32)
+    grid = orc.transform_voxel_to_match_image(orc.rotation_resampling(vox, poses)).astype(np.float32)
+    sil = (grid[..., 0].sum(axis=3) > 0.5).astype(np.float32)                                   # [B,128,128]
+    target = np.ascontiguousarray(np.repeat(np.repeat(sil, 4, 1), 4, 2)[..., None])             # [B,512,512,1] in {0,1}
+    W = orc.init_shader_weights(seed=3, is_greyscale=True, alpha_range=(-0.05, 0.25), bias_jitter=0.02)
+    tr = ShaderTrainer(W, 2, precision="exact", is_greyscale=True, keep_prob=1.0)
+    assert tr.loss_kind == "bce"
+    loss, grads = tr.loss_and_gradients(vox, poses, target)
+    Wt = {n: torch.tensor(v, requires_grad=True) for n, v in W.items()}
+    img = orc.rendernet_shader(torch.from_numpy(grid), Wt)
+    t = torch.from_numpy(target)
+    ref = (-(t * torch.log(1e-6 + img) + (1 - t) * torch.log(1e-6 + 1 - img)).sum(dim=(1, 2, 3))).mean()
+    g_ref = dict(zip(sorted(Wt), torch.autograd.grad(ref, [Wt[n] for n in sorted(Wt)])))
+    print(f"[greyscale BCE, B=2] loss {loss:.4f} vs {float(ref):.4f}; image err {float(np.abs(tr.img.cpu().numpy() - img.detach().numpy()).max()):.2e}")
+    assert abs(loss - float(ref)) < 5e-5 * float(ref)
+    assert set(grads) == set(g_ref)
+    worst = min((_cos(grads[n].cpu().numpy(), g_ref[n].numpy()), n) for n in g_ref)
+    ratios = [float(np.linalg.norm(grads[n].cpu().numpy()) / max(np.linalg.norm(g_ref[n].numpy()), 1e-30)) for n in g_ref]
+    print(f"[greyscale BCE, B=2] {len(grads)} variables: lowest cosine {worst[0]:.5f} ({worst[1]}), norm ratio {min(ratios):.4f}..{max(ratios):.4f}")
+    assert worst[0] > 0.9995 and all(abs(r - 1) < 1e-2 for r in ratios)
