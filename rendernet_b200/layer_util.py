@@ -361,6 +361,15 @@ def _deferred_conv(kind, x, w, b, stride):
 
     def run(act, alpha, residual, want32):
         xt = _as16(xin)
+        st = _store()
+        if act == "prelu" and st.tape is not None and st.keep_preact and not isinstance(alpha, str) and not want32:
+            # training step: the PReLU-slope gradient needs the pre-activation, so the layer is run without its fused PReLU, z is
+            # kept on the tape and the activation becomes its own (cheap) pass -- instead of re-running the convolution later
+            z = _run(xt, None, None, residual, False)
+            y = ops.bias_act(z, None, _dev_vec(alpha), "prelu")
+            _record(op="conv", kind=kind, stride=stride, x=xt, w=w, b=b, act=act, alpha=alpha, residual=residual, y=y,
+                    rerun=lambda: z)
+            return y
         y = _run(xt, act, alpha, residual, want32)
         _record(op="conv", kind=kind, stride=stride, x=xt, w=w, b=b, act=act, alpha=alpha, residual=residual, y=y,
                 rerun=lambda: _run(xt, None, None, residual, False))      # the pre-activation z (PReLU slope gradient)
@@ -482,6 +491,11 @@ def _deferred_direct3d(x, w, b, stride):
             # resample + axis transform + e_conv1 + bias + PReLU in one kernel; the 128^3 grid is never written
             bd = _dev_vec(b) if b is not None else torch.zeros(cout, device=wd.device, dtype=torch.float32)
             ad = _alpha_arg(alpha, cout) if act == "prelu" else None
+            if act == "prelu" and _store().tape is not None and _store().keep_preact and not isinstance(alpha, str):
+                z = ops.resample_conv1(xin.voxel, xin.minv, xin.new_size, wd, bd, None, tf.COMPUTE_DTYPE, fmt=_store().fmt)
+                y = ops.bias_act(z, None, _dev_vec(alpha), "prelu")         # training step: keep z (see _deferred_conv.run)
+                _record(op="resample_conv1", grid=xin, w=w, b=b, act=act, alpha=alpha, stride=list(stride), y=y, rerun=lambda: z)
+                return y
             y = ops.resample_conv1(xin.voxel, xin.minv, xin.new_size, wd, bd, ad, tf.COMPUTE_DTYPE, fmt=_store().fmt)
             _record(op="resample_conv1", grid=xin, w=w, b=b, act=act, alpha=alpha, stride=list(stride), y=y,
                     rerun=lambda: ops.resample_conv1(xin.voxel, xin.minv, xin.new_size, wd, bd, None, tf.COMPUTE_DTYPE,

@@ -51,6 +51,7 @@ class VariableStore:
         self.loaded: set = set()       # names installed by load_weight_dict
         self.consumed: set = set()     # loaded names a model function has asked for
         self.tape = None               # list -> every realised layer appends a record (rendernet_b200/backward.py)
+        self.keep_preact = False       # with a tape: PReLU layers keep their pre-activation (training step) instead of fusing it away
         self.dropout_seed = None       # int -> tf.nn.dropout(keep < 1) draws its masks from (seed, call index, element)
         self.dropout_calls = 0
         self.phong = None              # dict (ops.conv2d_transpose_xfold) -> the output layer applies the Phong composite itself
@@ -68,6 +69,10 @@ class VariableStore:
         self.strict = False
         self.loaded = set()
         self.consumed = set()
+        self.tape = None
+        self.keep_preact = False
+        self.dropout_seed, self.dropout_calls = None, 0
+        self.phong, self.phong_u8 = None, None
 
     def full_name(self, name: str) -> str:
         return "/".join(self.scope + [name])

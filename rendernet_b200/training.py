@@ -74,6 +74,7 @@ class ShaderTrainer(ShaderInputGradients):
         self.tape = []
         st = self.store
         st.tape = self.tape
+        st.keep_preact = True              # PReLU layers leave their pre-activation on the tape (slope gradient, derivative)
         st.dropout_seed = self.dropout_seed(self.global_step) if (training and self.keep_prob < 1.0) else None
         st.dropout_calls = 0
         try:
@@ -83,6 +84,7 @@ class ShaderTrainer(ShaderInputGradients):
                 self._adopt_variables()
         finally:
             st.tape = None
+            st.keep_preact = False
             st.dropout_seed = None
         return self.img
 
