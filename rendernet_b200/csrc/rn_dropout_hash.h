@@ -11,15 +11,15 @@
 #endif
 
 RN_HD uint32_t rn_dropout_hash(uint32_t seed, uint32_t salt, unsigned long long i) {
-  const unsigned long long key = (static_cast<unsigned long long>(seed) << 32) | salt;
+  const unsigned long long key = ((unsigned long long)seed << 32) | salt;
   unsigned long long z = (i + 1ULL) * 0x9E3779B97F4A7C15ULL + key * 0xD1B54A32D192ED03ULL;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
   z ^= z >> 31;
-  return static_cast<uint32_t>(z >> 32);
+  return (uint32_t)(z >> 32);
 }
 // keep probability -> threshold in [1, 2^32]
 RN_HD unsigned long long rn_dropout_threshold(float keep) {
-  const double t = static_cast<double>(keep) * 4294967296.0;
-  return t >= 4294967296.0 ? 4294967296ULL : static_cast<unsigned long long>(t);
+  const double t = (double)keep * 4294967296.0;
+  return t >= 4294967296.0 ? 4294967296ULL : (unsigned long long)t;
 }
