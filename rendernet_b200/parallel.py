@@ -304,6 +304,43 @@ class ShardedRenderEngine:
             self.peer = None
 
 
+def all_reduce_gradients(grads: Dict[str, torch.Tensor], average: bool = True, bucket_bytes: int = 256 << 20, group=None):
+    """Data-parallel training: sum (or average) every gradient of `grads` over the ranks, in place.  The tensors are packed,
+    in name order (identical on every rank), into flat fp32 buckets of <= bucket_bytes so that the 166 variables of the Shader
+    network cost a handful of all-reduces sized for NVSwitch bandwidth rather than 166 latency-bound ones (the 1024 x 1024
+    3 x 3 filters are 37.7 MB each and travel alone-ish; biases and slopes share a bucket).  Backend-agnostic (NCCL on GPUs,
+    gloo in the CPU tests)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return grads
+    world = dist.get_world_size(group)
+    if world == 1:
+        return grads
+    names = sorted(grads)
+    i = 0
+    while i < len(names):
+        j, size = i, 0
+        while j < len(names) and (j == i or size + grads[names[j]].numel() * 4 <= bucket_bytes):
+            size += grads[names[j]].numel() * 4
+            j += 1
+        chunk = [grads[n] for n in names[i:j]]
+        if len(chunk) == 1 and chunk[0].is_contiguous() and chunk[0].dtype == torch.float32:
+            flat = chunk[0].view(-1)                       # big filters: reduce in place, no staging copy
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                flat.mul_(1.0 / world)
+        else:
+            flat = torch.cat([t.reshape(-1).float() for t in chunk])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                flat.mul_(1.0 / world)
+            off = 0
+            for t in chunk:
+                t.copy_(flat[off:off + t.numel()].view(t.shape))
+                off += t.numel()
+        i = j
+    return grads
+
+
 def broadcast_weight_dict(weights: Optional[Dict[str, np.ndarray]], src: int = 0, device="cpu", group=None):
     """Replicate a weight dict from `src` to every rank (names first, then one flat fp32 buffer)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

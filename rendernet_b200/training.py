@@ -39,14 +39,19 @@ class ShaderTrainer(ShaderInputGradients):
         weights = tr.state_dict()                                                                      # {tf name: ndarray}
 
     learning_rate / decay_steps / keep_prob default to config_RenderNet.json (e_eta 1e-5, 100000, 1.0); beta1 = 0.5 as in
-    RenderNet_Shader.py:167, beta2 / epsilon are TF's defaults."""
+    RenderNet_Shader.py:167, beta2 / epsilon are TF's defaults.  data_parallel=True (one process per GPU under torchrun, same
+    initial weights / seed on every rank; the rank is mixed into the dropout-mask seed): gradients are averaged over the
+    ranks before Adam (rendernet_b200.parallel.all_reduce_gradients; its bucketing is tested on a 2-process gloo group, the
+    multi-GPU step itself has not been run on GPUs in round 2)."""
 
     def __init__(self, weights: Optional[Dict[str, np.ndarray]], batch: int, precision: str = "exact", is_greyscale: bool = False,
                  keep_prob: float = 1.0, learning_rate: float = 1e-5, decay_steps: int = 100000, decay_rate: float = 0.96,
                  beta1: float = 0.5, beta2: float = 0.999, epsilon: float = 1e-8, loss: Optional[str] = None,
-                 size: int = 64, new_size: int = 128, loss_scale: float = 4096.0, seed: int = 0, device: str = "cuda"):
+                 size: int = 64, new_size: int = 128, loss_scale: float = 4096.0, seed: int = 0, device: str = "cuda",
+                 data_parallel: bool = False):
         super().__init__(weights, batch, precision=precision, is_greyscale=is_greyscale, size=size, new_size=new_size,
                          loss_scale=loss_scale, seed=seed, device=device)
+        self.data_parallel = bool(data_parallel)      # one process per GPU, `batch` items each: gradients averaged over the ranks
         if not 0.0 < keep_prob <= 1.0:
             raise ValueError("keep_prob must be in (0, 1]")
         self.keep_prob = float(keep_prob)
@@ -90,7 +95,10 @@ class ShaderTrainer(ShaderInputGradients):
 
     def dropout_seed(self, step: int) -> int:
         """Seed of the dropout masks of optimiser step `step` (mixes the trainer's seed and the step; 32 bits)."""
-        return (self.seed * 0x9E3779B1 + step * 0x85EBCA6B + 0x1234567) & 0xFFFFFFFF
+        rank = 0
+        if self.data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank = torch.distributed.get_rank()           # data-parallel ranks draw different masks from the same trainer seed
+        return (self.seed * 0x9E3779B1 + step * 0x85EBCA6B + rank * 0xC2B2AE35 + 0x1234567) & 0xFFFFFFFF
 
     def _adopt_variables(self):
         """Move the fp32 masters of every variable to the device (once): Adam updates them in place, the packers read them there."""
@@ -138,14 +146,30 @@ class ShaderTrainer(ShaderInputGradients):
 
     def step(self, voxels, view_params, target) -> float:
         """One optimiser step (RenderNet_Shader.py:156-167); returns the loss BEFORE the update."""
+        dp = self.data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized()
         for _ in range(12):
+            overflow = False
             try:
                 loss, grads = self.loss_and_gradients(voxels, view_params, target, training=True)
-                break
             except FloatingPointError:                 # dynamic loss scaling: halve and redo the step (same dropout masks)
-                self.loss_scale *= 0.5
+                overflow = True
+            if dp:                                     # every rank must take the same branch
+                flag = torch.tensor([1.0 if overflow else 0.0], device=self.store.device)
+                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+                overflow = bool(flag.item() > 0)
+            if not overflow:
+                break
+            self.loss_scale *= 0.5
         else:
             raise FloatingPointError("the backward pass overflows even at a loss scale of %g" % self.loss_scale)
+        if dp:
+            # data-parallel step: every rank holds the same variables and its own `batch` items; the mean loss over the global
+            # batch is the mean of the per-rank means, so the gradients are averaged (NCCL all-reduce, bucketed) before Adam
+            from .parallel import all_reduce_gradients
+            all_reduce_gradients(grads, average=True)
+            lt = torch.tensor([loss], device=self.store.device, dtype=torch.float64)
+            torch.distributed.all_reduce(lt)
+            loss = float(lt.item()) / torch.distributed.get_world_size()
         self.apply_gradients(grads)
         return loss
 

@@ -200,6 +200,48 @@ def test_batch_sharding_allgather_world2_gloo(n_total):
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def _gloo_grad_worker(rank, world, port, q):
+    import zlib
+    import torch.distributed as dist
+    from rendernet_b200.parallel import all_reduce_gradients
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shapes = {"enc/big/weights": (3, 3, 64, 64), "enc/big/biases": (64,), "enc/a/alpha": (8,), "enc/t/weights": (4, 4, 3, 16),
+              "enc/z/weights": (5, 5, 5, 1, 8)}
+    gen = lambda r: {n: torch.from_numpy(np.random.default_rng(zlib.crc32(n.encode()) % 1000 + 7 * r).standard_normal(sh).astype(np.float32))
+                     for n, sh in shapes.items()}
+    mine, both = gen(rank), [gen(r) for r in range(world)]
+    ok = True
+    for bucket in (1 << 10, 150_000, 256 << 20):            # every tensor alone / mixed / one bucket
+        g = {n: t.clone() for n, t in mine.items()}
+        all_reduce_gradients(g, average=True, bucket_bytes=bucket)
+        for n in shapes:
+            want = sum(b[n] for b in both) / world
+            ok = ok and tuple(g[n].shape) == shapes[n] and bool(torch.allclose(g[n], want, atol=1e-6))
+    g = {n: t.clone() for n, t in mine.items()}
+    all_reduce_gradients(g, average=False)
+    ok = ok and bool(torch.allclose(g["enc/a/alpha"], sum(b["enc/a/alpha"] for b in both), atol=1e-6))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_buckets_world2_gloo():
+    """Data-parallel training's exchange step (parallel.all_reduce_gradients) on a 2-process gloo group: name-ordered flat
+    buckets of three sizes give the rank average of every gradient, shapes preserved."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly one JSON line on stdout with the
     contract's keys; runs the oracle on the host cores, no GPU involved."""
