@@ -170,3 +170,16 @@ def test_trainer_needs_cuda_and_schedule_formula():
     fake = types.SimpleNamespace(e_eta=1e-5, decay_rate=0.96, decay_steps=100000, global_step=0)
     assert sched(fake, 0) == 1e-5 and sched(fake, 99999) == 1e-5
     assert abs(sched(fake, 100000) - 0.96e-5) < 1e-18 and abs(sched(fake, 250000) - 1e-5 * 0.96 ** 2) < 1e-18
+
+
+def test_dropout_is_refused_outside_the_training_path_and_gradient_allreduce_is_a_noop_without_a_group():
+    """tf.nn.dropout(keep < 1) without a seeded store is the inference path misused: loud error, nothing launched; keep == 1 is
+    the identity.  all_reduce_gradients without an initialised process group returns the gradients untouched."""
+    from rendernet_b200 import tfcompat as tf
+    from rendernet_b200.parallel import all_reduce_gradients
+    x = torch.ones(2, 3)
+    assert tf.nn.dropout(x, 1.0) is x
+    with pytest.raises(NotImplementedError):
+        tf.nn.dropout(x, 0.75)
+    g = {"a": torch.ones(3), "b": torch.zeros(2, 2)}
+    assert all_reduce_gradients(g) is g and torch.equal(g["a"], torch.ones(3))
