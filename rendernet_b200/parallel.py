@@ -208,7 +208,7 @@ class ShardedRenderEngine:
             else:
                 self.kind_note = "copy-engine P2P writes over NVLink (CUDA IPC)"
         if self.kind in ("nccl", "nccl_sync"):
-            self.comm = torch.cuda.Stream(device=self.dev)
+            self.comm = torch.cuda.Stream(device=self.dev) if self.kind == "nccl" else None     # side stream of the overlapped form
             self.gathered = [torch.empty((self.world * o.shape[0],) + tuple(o.shape[1:]), device=self.dev, dtype=o.dtype)
                              for o in outs]
         if self.kind in ("nccl", "peer"):

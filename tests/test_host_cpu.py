@@ -200,6 +200,60 @@ def test_batch_sharding_allgather_world2_gloo(n_total):
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def _gloo_sharded_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from rendernet_b200.parallel import ShardedRenderEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class FakeEngine:                       # the engine surface ShardedRenderEngine drives (engine.py), on CPU tensors
+        B, device = 3, torch.device("cpu")
+
+        def __init__(self):
+            self.out = torch.zeros(self.B, 4, 4, 3)
+            self.steps = 0
+
+        def step_device(self):
+            self.steps += 1
+            self.out.copy_(torch.arange(self.B * 48, dtype=torch.float32).reshape(self.B, 4, 4, 3) + 1000.0 * rank + 0.5 * self.steps)
+
+    ok = True
+    sh = ShardedRenderEngine(FakeEngine(), gather="nccl_sync")            # the default product mode: gather between the steps
+    ok = ok and sh.world == world and sh.kind == "nccl_sync"
+    for step in (1, 2):
+        sh.step()
+        full = sh.wait()
+        want = torch.cat([torch.arange(3 * 48, dtype=torch.float32).reshape(3, 4, 4, 3) + 1000.0 * r + 0.5 * step for r in range(world)])
+        ok = ok and tuple(full.shape) == (world * 3, 4, 4, 3) and bool(torch.equal(full, want))
+    none = ShardedRenderEngine(FakeEngine(), gather="none")
+    none.step()
+    ok = ok and none.wait() is none.engine.out
+    try:
+        ShardedRenderEngine(FakeEngine(), gather="bogus")
+        ok = False
+    except ValueError:
+        pass
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_sharded_render_engine_world2_gloo():
+    """parallel.ShardedRenderEngine (the N > 1 product API) on a 2-process gloo group with a CPU stand-in for the engine: every
+    rank steps its own shard, the stream-ordered all-gather returns the whole batch in rank order, step after step."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def _gloo_grad_worker(rank, world, port, q):
     import zlib
     import torch.distributed as dist
